@@ -1,0 +1,104 @@
+"""ctypes binding of ``libemd_b200.so`` (the C ABI declared in ``include/emd_b200.h``).
+
+Every entry point takes raw device pointers, sizes and a ``cudaStream_t``; all
+memory is allocated and owned by PyTorch on the Python side.  There is no CPU
+fallback: a missing library, a non-CUDA tensor or a non-zero status raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_float, c_int, c_int64, c_size_t, c_void_p
+from typing import Optional
+
+import torch
+
+from . import build as _build
+
+_lib = None
+
+P = c_void_p
+_SIGS = {
+    # name: (restype, argtypes)
+    "emd_last_error_string": (ctypes.c_char_p, []),
+    "emd_abi_version": (c_int, []),
+    "emd_device_check": (c_int, []),
+    "emd_projection_fwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int, c_int, c_float, c_float, c_float, c_float,
+                                   c_int, c_int, P, P, P, P, P, P, P]),
+    "emd_projection_bwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int, c_int, c_float, c_float, c_float, c_float,
+                                   P, P, P, P, P, P, P, P]),
+    "emd_scan_workspace_bytes": (c_size_t, [c_int64]),
+    "emd_cumsum_i32_i64": (c_int, [P, P, c_int64, P, P, c_size_t, P]),
+    "emd_exclusive_scan_u32": (c_int, [P, P, c_int64, P, c_size_t, P]),
+    "emd_isect_emit": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, P, P, P]),
+    "emd_isect_offsets": (c_int, [P, c_int64, c_int64, c_int, c_int, c_int, P, P]),
+    "emd_radix_sort_workspace_bytes": (c_size_t, [c_int64]),
+    "emd_radix_sort_pairs": (c_int, [P, P, P, P, c_int64, c_int, c_int, P, c_size_t, ctypes.POINTER(c_int), P]),
+    "emd_raster_pack": (c_int, [P, P, P, c_int, P, c_int, c_int, P, c_int, P, c_int64, c_int64, P, P]),
+    "emd_rasterize_fwd": (c_int, [P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
+    "emd_rasterize_bwd_workspace_bytes": (c_size_t, [c_int64]),
+    "emd_sh_fwd": (c_int, [c_int, P, P, c_int64, c_int, P, P]),
+    "emd_sh_bwd": (c_int, [c_int, P, c_int64, c_int, P, P, P]),
+    "emd_activate_fwd": (c_int, [P] * 8 + [ctypes.POINTER(c_float), c_int64, c_int, c_int] + [P] * 5 + [P]),
+    "emd_activate_bwd": (c_int, [P] * 8 + [ctypes.POINTER(c_float), c_int64, c_int, c_int] + [P] * 11 + [P]),
+    "emd_rasterize_bwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  P, P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
+}
+
+
+class EmdError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load (building first if the .so is absent and nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not path.exists():
+        try:
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise EmdError(
+                f"emd_b200: {path} is missing and could not be built ({e}). There is no CPU fallback; "
+                "run `python -m emd_b200.build` with the CUDA 12.9 toolkit."
+            ) from e
+    try:
+        L = ctypes.CDLL(str(path))
+    except OSError as e:
+        raise EmdError(f"emd_b200: cannot load {path}: {e}. There is no CPU fallback.") from e
+    for name, (res, args) in _SIGS.items():
+        if not hasattr(L, name):
+            raise EmdError(f"emd_b200: {path} does not export {name}; rebuild with `python -m emd_b200.build --force`")
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def declared_symbols():
+    return sorted(_SIGS)
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().emd_last_error_string().decode("utf-8", "replace")
+        raise EmdError(f"{what} failed with status {status}: {msg}")
+
+
+def ptr(t: Optional[torch.Tensor], dtype=None, name: str = "tensor") -> Optional[int]:
+    """Device pointer of a contiguous CUDA tensor (None passes through as NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise EmdError(f"emd_b200: {name} must be a CUDA tensor (got {t.device}); there is no CPU path")
+    if not t.is_contiguous():
+        raise EmdError(f"emd_b200: {name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise EmdError(f"emd_b200: {name} must be {dtype} (got {t.dtype})")
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream

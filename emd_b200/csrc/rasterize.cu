@@ -1,0 +1,429 @@
+// K6 / K7: front-to-back alpha compositing of RGB(+depth) and opacity per 16x16
+// tile, forward and backward (gsplat rasterize_to_pixels semantics; the
+// reference reaches it through OmniRe/models/trainers/base.py:393).
+//
+// Forward: one CTA per (camera, tile); the tile's depth-sorted Gaussians are
+// staged through shared memory in batches of 256 packed records (48 B each),
+// every thread composites one pixel, the CTA leaves as soon as all 256 pixels
+// have saturated (barrier-count early termination).
+//
+// Backward: same CTA shape, back-to-front replay.  Per-pair gradients are
+// reduced across the warp with a 16-value butterfly (16 shuffles instead of
+// 12x5), across the CTA's 8 warps through fixed-order shared-memory slabs, and
+// written ONCE per (tile, Gaussian) pair into that pair's private slot of an
+// n_isects-long buffer (slot = the pair's index in emission order, which makes
+// every Gaussian's slots contiguous).  A second kernel sums each Gaussian's
+// contiguous run.  No global float atomics anywhere; results are bit-reproducible.
+#include "common.cuh"
+#include "proj_math.cuh"
+
+namespace {
+
+constexpr int RB = 256;  // threads per CTA == pixels per tile == Gaussians per staged batch
+constexpr float ALPHA_MIN = 1.0f / 255.0f;
+constexpr int NPART = 12;  // floats per (tile, Gaussian) gradient slot
+
+// ---------------------------------------------------------------------------
+// pack: gather the per-(camera,Gaussian) fields the compositor reads into three
+// aligned float4 records so a staged Gaussian costs three 128-bit loads.
+//   rec0 = (mean_x, mean_y, opacity, conic_a)
+//   rec1 = (conic_b, conic_c, ch0, ch1)
+//   rec2 = (ch2, ch3, 0, 0)
+// Channels: the D_color colour channels, then (optionally) the camera depth.
+// ---------------------------------------------------------------------------
+__global__ void raster_pack_kernel(const float* __restrict__ means2d, const float* __restrict__ conics,
+                                   const float* __restrict__ opacities, int opac_per_cam,
+                                   const float* __restrict__ colors, int colors_per_cam, int d_color,
+                                   const float* __restrict__ depths, int with_depth,
+                                   const int32_t* __restrict__ radii, int64_t N, int64_t CN,
+                                   float4* __restrict__ recs) {
+    const int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= CN) return;
+    if (radii[ci] <= 0) return;  // never gathered
+    const int64_t i = ci % N;
+    const float2 m = __ldg(reinterpret_cast<const float2*>(means2d) + ci);
+    const float ca = __ldg(conics + ci * 3 + 0), cb = __ldg(conics + ci * 3 + 1), cc = __ldg(conics + ci * 3 + 2);
+    const float op = __ldg(opacities + (opac_per_cam ? ci : i));
+    float ch[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* cp = colors + (colors_per_cam ? ci : i) * d_color;
+    for (int k = 0; k < d_color; ++k) ch[k] = __ldg(cp + k);
+    if (with_depth) ch[d_color] = __ldg(depths + ci);
+    recs[ci * 3 + 0] = make_float4(m.x, m.y, op, ca);
+    recs[ci * 3 + 1] = make_float4(cb, cc, ch[0], ch[1]);
+    recs[ci * 3 + 2] = make_float4(ch[2], ch[3], 0.f, 0.f);
+}
+
+// ---------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(RB) raster_fwd_kernel(
+    const float4* __restrict__ recs, const int32_t* __restrict__ tile_offsets, const int32_t* __restrict__ flatten_ids,
+    int64_t P, int C, int width, int height, int tile_w, int tile_h, int CH, int ed_mode,
+    const float* __restrict__ backgrounds, float* __restrict__ out_colors, float* __restrict__ out_alphas,
+    int32_t* __restrict__ last_ids) {
+    __shared__ float4 s_r0[RB];
+    __shared__ float4 s_r1[RB];
+    __shared__ float2 s_r2[RB];
+
+    const int cam = blockIdx.z;
+    const int tile_id = (cam * tile_h + blockIdx.y) * tile_w + blockIdx.x;
+    const int tr = threadIdx.y * EMD_TILE + threadIdx.x;
+    const int i = blockIdx.y * EMD_TILE + threadIdx.y;
+    const int j = blockIdx.x * EMD_TILE + threadIdx.x;
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const bool inside = i < height && j < width;
+    bool done = !inside;
+
+    const int64_t range_start = tile_offsets[tile_id];
+    const int64_t range_end = (tile_id == C * tile_h * tile_w - 1) ? P : (int64_t)tile_offsets[tile_id + 1];
+    const int num_batches = (int)((range_end - range_start + RB - 1) / RB);
+
+    float T = 1.0f;
+    int32_t cur_idx = 0;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (int b = 0; b < num_batches; ++b) {
+        if (__syncthreads_count(done) >= RB) break;
+        const int64_t batch_start = range_start + (int64_t)RB * b;
+        const int64_t idx = batch_start + tr;
+        if (idx < range_end) {
+            const int64_t g = flatten_ids[idx];
+            s_r0[tr] = __ldg(recs + g * 3 + 0);
+            s_r1[tr] = __ldg(recs + g * 3 + 1);
+            const float4 r2 = __ldg(recs + g * 3 + 2);
+            s_r2[tr] = make_float2(r2.x, r2.y);
+        }
+        __syncthreads();
+        const int batch_size = (int)min((int64_t)RB, range_end - batch_start);
+        for (int t = 0; t < batch_size && !done; ++t) {
+            const float4 r0 = s_r0[t];
+            const float4 r1 = s_r1[t];
+            const float dx = r0.x - px, dy = r0.y - py;
+            const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
+            const float alpha = fminf(0.999f, r0.z * __expf(-sigma));
+            if (sigma < 0.f || alpha < ALPHA_MIN) continue;
+            const float next_T = T * (1.0f - alpha);
+            if (next_T <= 1e-4f) { done = true; break; }
+            const float vis = alpha * T;
+            const float2 r2 = s_r2[t];
+            acc[0] += r1.z * vis; acc[1] += r1.w * vis; acc[2] += r2.x * vis; acc[3] += r2.y * vis;
+            cur_idx = (int32_t)(batch_start + t);
+            T = next_T;
+        }
+    }
+    if (inside) {
+        const int64_t pix = ((int64_t)cam * height + i) * width + j;
+        const float alpha_out = 1.0f - T;
+        out_alphas[pix] = alpha_out;
+        if (backgrounds) {
+            for (int k = 0; k < CH; ++k) acc[k] += T * backgrounds[cam * CH + k];
+        }
+        if (ed_mode) acc[CH - 1] = acc[CH - 1] / fmaxf(alpha_out, 1e-10f);
+        float* o = out_colors + pix * CH;
+        if (CH == 4) {
+            *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        } else {
+            for (int k = 0; k < CH; ++k) o[k] = acc[k];
+        }
+        last_ids[pix] = cur_idx;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------
+// Butterfly all-lanes reduction of 16 values: after the call, lane l holds the
+// warp-wide sum of value index ((l>>1)&15 with bits reversed as below) in v[0]:
+//   idx(l) = ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1)
+__device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int k = 0; k < half; ++k) {
+            const float send = up ? v[k] : v[k + half];
+            const float keep = up ? v[k + half] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+__global__ void __launch_bounds__(RB) raster_bwd_kernel(
+    const float4* __restrict__ recs, const int32_t* __restrict__ tile_offsets, const int32_t* __restrict__ flatten_ids,
+    const int32_t* __restrict__ radii, const int64_t* __restrict__ cum_tiles, int64_t P, int C, int width, int height,
+    int tile_w, int tile_h, int CH, int ed_mode, const float* __restrict__ backgrounds,
+    const float* __restrict__ out_colors, const float* __restrict__ out_alphas, const int32_t* __restrict__ last_ids,
+    const float* __restrict__ v_out_colors, const float* __restrict__ v_out_alphas, float* __restrict__ partials,
+    uint8_t* __restrict__ touched) {
+    __shared__ float4 s_r0[RB];
+    __shared__ float4 s_r1[RB];
+    __shared__ float2 s_r2[RB];
+    __shared__ uint32_t s_slot[RB];
+    __shared__ float s_slab[RB / 32][32][NPART];
+    __shared__ uint32_t s_tmask[RB / 32];
+    __shared__ int s_red[RB / 32];
+
+    const int cam = blockIdx.z;
+    const int tile_id = (cam * tile_h + blockIdx.y) * tile_w + blockIdx.x;
+    const int tr = threadIdx.y * EMD_TILE + threadIdx.x;
+    const int lane = tr & 31, warp = tr >> 5;
+    const int i = blockIdx.y * EMD_TILE + threadIdx.y;
+    const int j = blockIdx.x * EMD_TILE + threadIdx.x;
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const bool inside = i < height && j < width;
+    const int64_t pix = ((int64_t)cam * height + min(i, height - 1)) * width + min(j, width - 1);
+
+    const int64_t range_start = tile_offsets[tile_id];
+    const int64_t range_end = (tile_id == C * tile_h * tile_w - 1) ? P : (int64_t)tile_offsets[tile_id + 1];
+    if (range_end <= range_start) return;
+
+    // per-pixel state
+    const float alpha_out = inside ? out_alphas[pix] : 0.f;
+    const float T_final = 1.0f - alpha_out;
+    float T = T_final;
+    const int64_t bin_final = inside ? (int64_t)last_ids[pix] : -1;
+    float v_c[4] = {0.f, 0.f, 0.f, 0.f};
+    float v_a = 0.f;
+    if (inside) {
+        for (int k = 0; k < CH; ++k) v_c[k] = v_out_colors[pix * CH + k];
+        v_a = v_out_alphas[pix];
+        if (ed_mode) {
+            // out = D / max(alpha, 1e-10):  v_D = v_out / a_c ;  v_alpha += -v_out * out / a_c  (when alpha > 1e-10)
+            const float ac = fmaxf(alpha_out, 1e-10f);
+            const float v_ed = v_c[CH - 1];
+            if (alpha_out > 1e-10f) v_a += -v_ed * out_colors[pix * CH + CH - 1] / ac;
+            v_c[CH - 1] = v_ed / ac;
+        }
+    }
+    float bg_dot = 0.f;
+    if (backgrounds) {
+        for (int k = 0; k < CH; ++k) bg_dot += backgrounds[cam * CH + k] * v_c[k];
+    }
+    float buf[4] = {0.f, 0.f, 0.f, 0.f};
+
+    // last sorted index any pixel of this tile blended
+    int wmax = (int)max(bin_final, (int64_t)-1);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) s_red[warp] = wmax;
+    __syncthreads();
+    int64_t tile_last = -1;
+    for (int w = 0; w < RB / 32; ++w) tile_last = max(tile_last, (int64_t)s_red[w]);
+    if (tile_last < range_start) return;  // nothing was blended in this tile
+    const int64_t hi_end = min(range_end, tile_last + 1);  // exclusive
+
+    const int num_batches = (int)((hi_end - range_start + RB - 1) / RB);
+    for (int b = 0; b < num_batches; ++b) {
+        // batch covers sorted indices [batch_lo, batch_hi), walked from the back
+        const int64_t batch_hi = hi_end - (int64_t)RB * b;
+        const int64_t batch_lo = max(range_start, batch_hi - RB);
+        const int batch_size = (int)(batch_hi - batch_lo);
+        __syncthreads();
+        if (tr < batch_size) {
+            // slot tr holds sorted index batch_hi-1-tr  (slot 0 = farthest)
+            const int64_t idx = batch_hi - 1 - tr;
+            const int64_t g = flatten_ids[idx];
+            const float4 r0 = __ldg(recs + g * 3 + 0);
+            s_r0[tr] = r0;
+            s_r1[tr] = __ldg(recs + g * 3 + 1);
+            const float4 r2 = __ldg(recs + g * 3 + 2);
+            s_r2[tr] = make_float2(r2.x, r2.y);
+            int x0, y0, x1, y1;
+            tile_rect_c(r0.x, r0.y, radii[g], tile_w, tile_h, x0, y0, x1, y1);
+            const int64_t base = g == 0 ? 0 : cum_tiles[g - 1];
+            s_slot[tr] = (uint32_t)(base + (int64_t)((int)blockIdx.y - y0) * (x1 - x0) + ((int)blockIdx.x - x0));
+        }
+        __syncthreads();
+        for (int sub = 0; sub < batch_size; sub += 32) {
+            const int sub_n = min(32, batch_size - sub);
+            uint32_t tmask = 0;
+            for (int u = 0; u < sub_n; ++u) {
+                const int t = sub + u;
+                const int64_t idx = batch_hi - 1 - t;
+                bool valid = inside && idx <= bin_final;
+                float4 r0, r1;
+                float dx = 0.f, dy = 0.f, vis = 0.f, alpha = 0.f;
+                if (valid) {
+                    r0 = s_r0[t];
+                    r1 = s_r1[t];
+                    dx = r0.x - px; dy = r0.y - py;
+                    const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
+                    vis = __expf(-sigma);
+                    alpha = fminf(0.999f, r0.z * vis);
+                    if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
+                }
+                if (!__any_sync(0xffffffffu, valid)) continue;
+                float v[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] = 0.f;
+                if (valid) {
+                    const float2 r2 = s_r2[t];
+                    const float col[4] = {r1.z, r1.w, r2.x, r2.y};
+                    const float ra = 1.0f / (1.0f - alpha);
+                    T *= ra;
+                    const float fac = alpha * T;
+                    float v_alpha = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        v[k] = fac * v_c[k];
+                        v_alpha += (col[k] * T - buf[k] * ra) * v_c[k];
+                    }
+                    v_alpha += T_final * ra * v_a;
+                    v_alpha -= T_final * ra * bg_dot;
+                    const float opac = r0.z;
+                    if (opac * vis <= 0.999f) {
+                        const float v_sigma = -opac * vis * v_alpha;
+                        v[4] = 0.5f * v_sigma * dx * dx;
+                        v[5] = v_sigma * dx * dy;
+                        v[6] = 0.5f * v_sigma * dy * dy;
+                        const float gx = v_sigma * (r0.w * dx + r1.x * dy);
+                        const float gy = v_sigma * (r1.x * dx + r1.y * dy);
+                        v[7] = gx; v[8] = gy;
+                        v[9] = fabsf(gx); v[10] = fabsf(gy);
+                        v[11] = vis * v_alpha;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) buf[k] += col[k] * fac;
+                }
+                const float tot = butterfly16(v, lane);
+                const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                if ((lane & 1) == 0 && vidx < NPART) s_slab[warp][u][vidx] = tot;
+                tmask |= 1u << u;
+            }
+            if (lane == 0) s_tmask[warp] = tmask;
+            __syncthreads();
+            // fixed-order cross-warp sum, one writer per (Gaussian, component)
+            for (int q = tr; q < sub_n * NPART; q += RB) {
+                const int u = q / NPART, k = q - u * NPART;
+                float sum = 0.f;
+                bool any = false;
+#pragma unroll
+                for (int w = 0; w < RB / 32; ++w) {
+                    if (s_tmask[w] & (1u << u)) { sum += s_slab[w][u][k]; any = true; }
+                }
+                if (any) {
+                    const uint32_t slot = s_slot[sub + u];
+                    partials[(int64_t)slot * NPART + k] = sum;
+                    if (k == 0) touched[slot] = 1;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Sum each Gaussian's contiguous run of slots -> dense per-(camera,Gaussian) grads.
+__global__ void raster_gather_kernel(const float* __restrict__ partials, const uint8_t* __restrict__ touched,
+                                     const int64_t* __restrict__ cum_tiles, int64_t CN, int d_color, int with_depth,
+                                     float* __restrict__ v_means2d, float* __restrict__ v_means2d_abs,
+                                     float* __restrict__ v_conics, float* __restrict__ v_colors,
+                                     float* __restrict__ v_depths, float* __restrict__ v_opacities) {
+    const int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= CN) return;
+    const int64_t lo = ci == 0 ? 0 : cum_tiles[ci - 1];
+    const int64_t hi = cum_tiles[ci];
+    float a[NPART];
+#pragma unroll
+    for (int k = 0; k < NPART; ++k) a[k] = 0.f;
+    for (int64_t e = lo; e < hi; ++e) {
+        if (!touched[e]) continue;
+        const float4* p = reinterpret_cast<const float4*>(partials + e * NPART);
+        const float4 p0 = __ldg(p), p1 = __ldg(p + 1), p2 = __ldg(p + 2);
+        a[0] += p0.x; a[1] += p0.y; a[2] += p0.z; a[3] += p0.w;
+        a[4] += p1.x; a[5] += p1.y; a[6] += p1.z; a[7] += p1.w;
+        a[8] += p2.x; a[9] += p2.y; a[10] += p2.z; a[11] += p2.w;
+    }
+    for (int k = 0; k < d_color; ++k) v_colors[ci * d_color + k] = a[k];
+    if (with_depth) v_depths[ci] = a[d_color];
+    v_conics[ci * 3 + 0] = a[4]; v_conics[ci * 3 + 1] = a[5]; v_conics[ci * 3 + 2] = a[6];
+    reinterpret_cast<float2*>(v_means2d)[ci] = make_float2(a[7], a[8]);
+    if (v_means2d_abs) reinterpret_cast<float2*>(v_means2d_abs)[ci] = make_float2(a[9], a[10]);
+    v_opacities[ci] = a[11];
+}
+
+}  // namespace
+
+extern "C" int emd_raster_pack(const float* means2d, const float* conics, const float* opacities, int opac_per_cam,
+                               const float* colors, int colors_per_cam, int d_color, const float* depths,
+                               int with_depth, const int32_t* radii, int64_t N, int64_t C, float* recs,
+                               cudaStream_t stream) {
+    EMD_CHECK_ARG(d_color >= 0 && d_color + (with_depth ? 1 : 0) <= 4 && d_color + (with_depth ? 1 : 0) >= 1,
+                  "raster_pack: need 1..4 channels (got %d colour + %d depth)", d_color, with_depth);
+    if (!emd_aligned(recs, 16) || !emd_aligned(means2d, 8)) {
+        emd_set_error("raster_pack: recs must be 16-B, means2d 8-B aligned");
+        return EMD_ERR_ALIGN;
+    }
+    const int64_t CN = C * N;
+    if (CN == 0) return EMD_OK;
+    raster_pack_kernel<<<(unsigned)emd_cdiv(CN, 256), 256, 0, stream>>>(
+        means2d, conics, opacities, opac_per_cam, colors, colors_per_cam, d_color, depths, with_depth, radii, N, CN,
+        reinterpret_cast<float4*>(recs));
+    EMD_CHECK_LAUNCH("raster_pack");
+    return EMD_OK;
+}
+
+extern "C" int emd_rasterize_fwd(const float* recs, const int32_t* tile_offsets, const int32_t* flatten_ids,
+                                 int64_t P, int64_t C, int width, int height, int tile_w, int tile_h, int channels,
+                                 int ed_mode, const float* backgrounds, float* out_colors, float* out_alphas,
+                                 int32_t* last_ids, cudaStream_t stream) {
+    EMD_CHECK_ARG(channels >= 1 && channels <= 4, "rasterize_fwd: channels must be 1..4");
+    EMD_CHECK_ARG(C >= 1 && C <= 65535 && tile_h <= 65535, "rasterize_fwd: grid too large");
+    EMD_CHECK_ARG(tile_w == (width + EMD_TILE - 1) / EMD_TILE && tile_h == (height + EMD_TILE - 1) / EMD_TILE,
+                  "rasterize_fwd: tile grid does not match image size (tile size is 16)");
+    if (!emd_aligned(recs, 16) || (channels == 4 && !emd_aligned(out_colors, 16))) {
+        emd_set_error("rasterize_fwd: recs/out_colors must be 16-B aligned");
+        return EMD_ERR_ALIGN;
+    }
+    dim3 grid(tile_w, tile_h, (unsigned)C), block(EMD_TILE, EMD_TILE, 1);
+    raster_fwd_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, P,
+                                                  (int)C, width, height, tile_w, tile_h, channels, ed_mode,
+                                                  backgrounds, out_colors, out_alphas, last_ids);
+    EMD_CHECK_LAUNCH("rasterize_fwd");
+    return EMD_OK;
+}
+
+extern "C" size_t emd_rasterize_bwd_workspace_bytes(int64_t P) {
+    // [P][12] float partial slots + [P] touched flags
+    const size_t part = ((size_t)P * NPART * sizeof(float) + 255) / 256 * 256;
+    return part + (((size_t)P + 255) / 256) * 256 + 256;
+}
+
+extern "C" int emd_rasterize_bwd(const float* recs, const int32_t* tile_offsets, const int32_t* flatten_ids,
+                                 const int32_t* radii, const int64_t* cum_tiles, int64_t P, int64_t N, int64_t C,
+                                 int width, int height, int tile_w, int tile_h, int channels, int ed_mode,
+                                 const float* backgrounds, const float* out_colors, const float* out_alphas,
+                                 const int32_t* last_ids, const float* v_out_colors, const float* v_out_alphas,
+                                 int d_color, int with_depth, float* v_means2d, float* v_means2d_abs, float* v_conics,
+                                 float* v_colors, float* v_depths, float* v_opacities, void* workspace,
+                                 size_t ws_bytes, cudaStream_t stream) {
+    EMD_CHECK_ARG(channels >= 1 && channels <= 4, "rasterize_bwd: channels must be 1..4");
+    EMD_CHECK_ARG(d_color + (with_depth ? 1 : 0) == channels, "rasterize_bwd: channel bookkeeping mismatch");
+    EMD_CHECK_ARG(P < ((int64_t)1 << 32), "rasterize_bwd: too many intersections");
+    if (ws_bytes < emd_rasterize_bwd_workspace_bytes(P)) {
+        emd_set_error("rasterize_bwd: workspace too small");
+        return EMD_ERR_WORKSPACE;
+    }
+    if (!emd_aligned(workspace, 16) || !emd_aligned(recs, 16)) {
+        emd_set_error("rasterize_bwd: workspace/recs must be 16-B aligned");
+        return EMD_ERR_ALIGN;
+    }
+    const int64_t CN = C * N;
+    if (CN == 0) return EMD_OK;
+    float* partials = reinterpret_cast<float*>(workspace);
+    const size_t part = ((size_t)P * NPART * sizeof(float) + 255) / 256 * 256;
+    uint8_t* touched = reinterpret_cast<uint8_t*>(workspace) + part;
+    if (P > 0) {
+        cudaMemsetAsync(touched, 0, (size_t)P, stream);
+        dim3 grid(tile_w, tile_h, (unsigned)C), block(EMD_TILE, EMD_TILE, 1);
+        raster_bwd_kernel<<<grid, block, 0, stream>>>(
+            reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, radii, cum_tiles, P, (int)C, width,
+            height, tile_w, tile_h, channels, ed_mode, backgrounds, out_colors, out_alphas, last_ids, v_out_colors,
+            v_out_alphas, partials, touched);
+    }
+    raster_gather_kernel<<<(unsigned)emd_cdiv(CN, 256), 256, 0, stream>>>(partials, touched, cum_tiles, CN, d_color,
+                                                                           with_depth, v_means2d, v_means2d_abs,
+                                                                           v_conics, v_colors, v_depths, v_opacities);
+    EMD_CHECK_LAUNCH("rasterize_bwd");
+    return EMD_OK;
+}
