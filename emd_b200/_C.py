@@ -40,6 +40,12 @@ _SIGS = {
     "emd_sh_bwd": (c_int, [c_int, P, c_int64, c_int, P, P, P]),
     "emd_activate_fwd": (c_int, [P] * 8 + [ctypes.POINTER(c_float), c_int64, c_int, c_int] + [P] * 5 + [P]),
     "emd_activate_bwd": (c_int, [P] * 8 + [ctypes.POINTER(c_float), c_int64, c_int, c_int] + [P] * 11 + [P]),
+    "emd_rigid_chunk_size": (c_int, []),
+    "emd_rigid_param_count": (c_int, [c_int, c_int]),
+    "emd_rigid_deform_fwd": (c_int, [P] * 11 + [c_int64, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int]
+                             + [P] * 5 + [P]),
+    "emd_rigid_deform_bwd": (c_int, [P] * 10 + [c_int64, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int]
+                             + [P] * 16 + [P]),
     "emd_rasterize_bwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
                                   P, P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
 }

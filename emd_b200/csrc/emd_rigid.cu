@@ -1,0 +1,279 @@
+// K1a: EMD motion-embedding deformation of rigid nodes, forward and backward.
+//
+// Replaces the three per-instance Python loops of RigidNodes.transform_means /
+// transform_quats (OmniRe/models/nodes/rigid.py:478-568; several hundred tiny
+// launches and >= 2 host syncs per instance per step) with:
+//   segmean  : per-instance mean of the Gaussian motion embeddings (fixed-order
+//              chunked reduction over the instance-sorted point list)
+//   instance : one thread per instance -- temporal-embedding taps, track_* heads,
+//              yaw-offset quaternion, final pose (R, t, Q)        [emd_math.cuh]
+//   points   : one thread per Gaussian -- x_w = R x + t, q_w = Q (x) normalize(q)
+// and the mirrored backward (per-instance gradients are reduced in a fixed
+// order: no float atomics, bit-reproducible).  HBM-bound on the per-point
+// streams: 64 B/Gaussian forward (mean 12 + quat 16 + id 8 read; 12 + 16 written).
+#include "common.cuh"
+#include "emd_math.cuh"
+
+namespace {
+
+constexpr int RG_THREADS = 256;
+constexpr int RG_CHUNK = 2048;  // points per (instance, chunk) block
+constexpr int RG_INST = 16;     // floats of per-instance pose: R[9] t[3] Q[4]
+
+// fixed-order block sum of NV values per thread; result valid in thread 0
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* s_scratch /*[RG_THREADS/32][NV]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) s_scratch[warp * NV + k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            float s = 0.f;
+            for (int w = 0; w < RG_THREADS / 32; ++w) s += s_scratch[w * NV + k];
+            v[k] = s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RG_THREADS) rigid_segmean_kernel(const float* __restrict__ emb, int g,
+                                                                   const int64_t* __restrict__ order,
+                                                                   const int64_t* __restrict__ seg_start,
+                                                                   int max_chunks, float* __restrict__ partial) {
+    __shared__ float s_scratch[RG_THREADS / 32 * EMD_GDIM_MAX];
+    const int inst = blockIdx.y, chunk = blockIdx.x;
+    const int64_t lo = seg_start[inst] + (int64_t)chunk * RG_CHUNK;
+    const int64_t hi = min(seg_start[inst + 1], lo + RG_CHUNK);
+    float acc[EMD_GDIM_MAX];
+#pragma unroll
+    for (int k = 0; k < EMD_GDIM_MAX; ++k) acc[k] = 0.f;
+    for (int64_t p = lo + threadIdx.x; p < hi; p += RG_THREADS) {
+        const int64_t n = order[p];
+#pragma unroll
+        for (int k = 0; k < EMD_GDIM_MAX; ++k)
+            if (k < g) acc[k] += emb[n * g + k];
+    }
+    block_sum<EMD_GDIM_MAX>(acc, s_scratch);
+    if (threadIdx.x == 0)
+        for (int k = 0; k < g; ++k) partial[((int64_t)inst * max_chunks + chunk) * g + k] = acc[k];
+}
+
+struct RigidArgs {
+    const float* table;  // weight [I][E][d]
+    int I, E, d, g;
+    float t;
+    int cur_c, cur_f;
+    RigidHeads H;
+    const float* pose_q_means;  // [I,4]
+    const float* pose_q_quats;  // [I,4]
+    const float* pose_t;        // [I,3]
+    const int64_t* seg_start;   // [I+1]
+    int max_chunks;
+};
+
+__global__ void rigid_instance_fwd_kernel(RigidArgs a, const float* __restrict__ seg_partial,
+                                          float* __restrict__ mean_emb, float* __restrict__ inst_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.I) return;
+    const int64_t cnt = a.seg_start[i + 1] - a.seg_start[i];
+    const int nch = (int)((cnt + RG_CHUNK - 1) / RG_CHUNK);
+    float m[EMD_GDIM_MAX];
+    for (int k = 0; k < a.g; ++k) {
+        float s = 0.f;
+        for (int c = 0; c < nch; ++c) s += seg_partial[((int64_t)i * a.max_chunks + c) * a.g + k];
+        m[k] = s / (float)cnt;  // 0/0 = NaN for an empty instance, exactly like torch.mean of an empty slice
+        mean_emb[i * a.g + k] = m[k];
+    }
+    RigidInstOut o;
+    rigid_instance_fwd(a.table + (int64_t)i * a.E * a.d, a.E, a.d, a.g, m, a.t, a.cur_c, a.cur_f, a.H,
+                       a.pose_q_means + i * 4, a.pose_q_quats + i * 4, a.pose_t + i * 3, o);
+    float* out = inst_out + i * RG_INST;
+    for (int k = 0; k < 9; ++k) out[k] = o.R[k];
+    for (int k = 0; k < 3; ++k) out[9 + k] = o.t[k];
+    for (int k = 0; k < 4; ++k) out[12 + k] = o.Q[k];
+}
+
+__global__ void __launch_bounds__(RG_THREADS) rigid_points_fwd_kernel(
+    const float* __restrict__ means, const float* __restrict__ quats, const int64_t* __restrict__ point_ids,
+    const float* __restrict__ inst_out, int64_t N, float* __restrict__ world_means, float* __restrict__ world_quats) {
+    const int64_t n = (int64_t)blockIdx.x * RG_THREADS + threadIdx.x;
+    if (n >= N) return;
+    const float* P = inst_out + point_ids[n] * RG_INST;
+    const float x = means[n * 3 + 0], y = means[n * 3 + 1], z = means[n * 3 + 2];
+    world_means[n * 3 + 0] = P[0] * x + P[1] * y + P[2] * z + P[9];
+    world_means[n * 3 + 1] = P[3] * x + P[4] * y + P[5] * z + P[10];
+    world_means[n * 3 + 2] = P[6] * x + P[7] * y + P[8] * z + P[11];
+    const float4 q4 = __ldg(reinterpret_cast<const float4*>(quats) + n);
+    const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+    float qn[4], o[4];
+    qnormalize(q, qn);
+    qmul(P + 12, qn, o);
+    reinterpret_cast<float4*>(world_quats)[n] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// grid (max_chunks, I): per-point input grads + fixed-order partial sums of the
+// per-instance pose gradient (v_R 9, v_t 3, v_Q 4)
+__global__ void __launch_bounds__(RG_THREADS) rigid_points_bwd_kernel(
+    const float* __restrict__ means, const float* __restrict__ quats, const int64_t* __restrict__ order,
+    const int64_t* __restrict__ seg_start, const float* __restrict__ inst_out, int max_chunks,
+    const float* __restrict__ v_world_means, const float* __restrict__ v_world_quats, float* __restrict__ v_means,
+    float* __restrict__ v_quats, float* __restrict__ pose_partial) {
+    __shared__ float s_scratch[RG_THREADS / 32 * RG_INST];
+    const int inst = blockIdx.y, chunk = blockIdx.x;
+    const int64_t lo = seg_start[inst] + (int64_t)chunk * RG_CHUNK;
+    const int64_t hi = min(seg_start[inst + 1], lo + RG_CHUNK);
+    if (lo >= hi) return;  // block-uniform
+    const float* P = inst_out + inst * RG_INST;
+    float acc[RG_INST];
+#pragma unroll
+    for (int k = 0; k < RG_INST; ++k) acc[k] = 0.f;
+    for (int64_t p = lo + threadIdx.x; p < hi; p += RG_THREADS) {
+        const int64_t n = order[p];
+        const float x = means[n * 3 + 0], y = means[n * 3 + 1], z = means[n * 3 + 2];
+        const float gx = v_world_means[n * 3 + 0], gy = v_world_means[n * 3 + 1], gz = v_world_means[n * 3 + 2];
+        v_means[n * 3 + 0] = P[0] * gx + P[3] * gy + P[6] * gz;
+        v_means[n * 3 + 1] = P[1] * gx + P[4] * gy + P[7] * gz;
+        v_means[n * 3 + 2] = P[2] * gx + P[5] * gy + P[8] * gz;
+        acc[0] += gx * x; acc[1] += gx * y; acc[2] += gx * z;
+        acc[3] += gy * x; acc[4] += gy * y; acc[5] += gy * z;
+        acc[6] += gz * x; acc[7] += gz * y; acc[8] += gz * z;
+        acc[9] += gx; acc[10] += gy; acc[11] += gz;
+        const float4 q4 = __ldg(reinterpret_cast<const float4*>(quats) + n);
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(v_world_quats) + n);
+        const float q[4] = {q4.x, q4.y, q4.z, q4.w}, vg[4] = {g4.x, g4.y, g4.z, g4.w};
+        float qn[4], vQ[4], vqn[4], vq[4];
+        const float inv = qnormalize(q, qn);
+        qmul_vjp(P + 12, qn, vg, vQ, vqn);
+        qnormalize_vjp(qn, inv, vqn, vq);
+        reinterpret_cast<float4*>(v_quats)[n] = make_float4(vq[0], vq[1], vq[2], vq[3]);
+        acc[12] += vQ[0]; acc[13] += vQ[1]; acc[14] += vQ[2]; acc[15] += vQ[3];
+    }
+    block_sum<RG_INST>(acc, s_scratch);
+    if (threadIdx.x == 0)
+        for (int k = 0; k < RG_INST; ++k) pose_partial[((int64_t)inst * max_chunks + chunk) * RG_INST + k] = acc[k];
+}
+
+__global__ void rigid_instance_bwd_kernel(RigidArgs a, const float* __restrict__ mean_emb,
+                                          const float* __restrict__ pose_partial, float* __restrict__ v_pose_q_means,
+                                          float* __restrict__ v_pose_q_quats, float* __restrict__ v_pose_t,
+                                          float* __restrict__ v_params_partial, float* __restrict__ v_table,
+                                          float* __restrict__ v_mean_emb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.I) return;
+    const int64_t cnt = a.seg_start[i + 1] - a.seg_start[i];
+    const int nch = (int)((cnt + RG_CHUNK - 1) / RG_CHUNK);
+    float v[RG_INST];
+    for (int k = 0; k < RG_INST; ++k) {
+        float s = 0.f;
+        for (int c = 0; c < nch; ++c) s += pose_partial[((int64_t)i * a.max_chunks + c) * RG_INST + k];
+        v[k] = s;
+    }
+    const int pc = rigid_param_count(a.d + a.g);
+    rigid_instance_bwd(a.table + (int64_t)i * a.E * a.d, a.E, a.d, a.g, mean_emb + i * a.g, a.t, a.cur_c, a.cur_f, a.H,
+                       a.pose_q_means + i * 4, a.pose_q_quats + i * 4, a.pose_t + i * 3, v, v + 9, v + 12,
+                       v_pose_q_means + i * 4, v_pose_q_quats + i * 4, v_pose_t + i * 3,
+                       v_params_partial + (int64_t)i * pc, v_table + (int64_t)i * a.E * a.d, v_mean_emb + i * a.g);
+}
+
+// v_params[k] = sum_i partial[i][k], fixed order
+__global__ void params_reduce_kernel(const float* __restrict__ partial, int I, int pc, float* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= pc) return;
+    float s = 0.f;
+    for (int i = 0; i < I; ++i) s += partial[(int64_t)i * pc + k];
+    out[k] = s;
+}
+
+__global__ void embed_bwd_kernel(const float* __restrict__ v_mean_emb, const int64_t* __restrict__ point_ids,
+                                 const int64_t* __restrict__ seg_start, int g, int64_t N, float* __restrict__ v_emb) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N * g) return;
+    const int64_t n = e / g;
+    const int k = (int)(e - n * g);
+    const int64_t id = point_ids[n];
+    const float cnt = (float)(seg_start[id + 1] - seg_start[id]);
+    v_emb[e] = v_mean_emb[id * g + k] / cnt;
+}
+
+int fill_args(RigidArgs& a, const float* table, int I, int E, int d, int g, float t, int cur_c, int cur_f,
+              const float* const* heads, const float* pose_q_means, const float* pose_q_quats, const float* pose_t,
+              const int64_t* seg_start, int max_chunks) {
+    EMD_CHECK_ARG(I >= 1 && E >= 2, "rigid: need I >= 1 instances and E >= 2 table rows");
+    EMD_CHECK_ARG(d >= 1 && d <= EMD_TDIM_MAX && g >= 0 && g <= EMD_GDIM_MAX, "rigid: temporal dim <= %d, embedding dim <= %d",
+                  EMD_TDIM_MAX, EMD_GDIM_MAX);
+    EMD_CHECK_ARG(cur_c >= 1 && cur_f >= 1, "rigid: bad current embedding counts");
+    EMD_CHECK_ARG(max_chunks >= 1 && max_chunks <= 65535, "rigid: bad chunk count");
+    a.table = table; a.I = I; a.E = E; a.d = d; a.g = g; a.t = t; a.cur_c = cur_c; a.cur_f = cur_f;
+    a.H.rot_c_w = heads[0]; a.H.rot_c_b = heads[1]; a.H.rot_f_w = heads[2]; a.H.rot_f_b = heads[3];
+    a.H.trans_c_w = heads[4]; a.H.trans_c_b = heads[5]; a.H.trans_f_w = heads[6]; a.H.trans_f_b = heads[7];
+    a.pose_q_means = pose_q_means; a.pose_q_quats = pose_q_quats; a.pose_t = pose_t;
+    a.seg_start = seg_start; a.max_chunks = max_chunks;
+    return EMD_OK;
+}
+
+}  // namespace
+
+extern "C" int emd_rigid_chunk_size() { return RG_CHUNK; }
+extern "C" int emd_rigid_param_count(int d, int g) { return rigid_param_count(d + g); }
+
+// heads: HOST array of 8 DEVICE pointers {rot_c_w, rot_c_b, rot_f_w, rot_f_b, trans_c_w, trans_c_b, trans_f_w, trans_f_b}
+// order/seg_start: points sorted by instance id (stable) and the I+1 segment boundaries.
+// scratch: seg_partial [I*max_chunks*g] floats.  Saved for backward: mean_emb [I,g], inst_out [I,16].
+extern "C" int emd_rigid_deform_fwd(const float* means, const float* quats, const float* embeddings,
+                                    const int64_t* point_ids, const int64_t* order, const int64_t* seg_start,
+                                    const float* table, const float* const* heads, const float* pose_q_means,
+                                    const float* pose_q_quats, const float* pose_t, int64_t N, int I, int E, int d,
+                                    int g, float t, int cur_c, int cur_f, int max_chunks, float* seg_partial,
+                                    float* mean_emb, float* inst_out, float* world_means, float* world_quats,
+                                    cudaStream_t stream) {
+    RigidArgs a;
+    int rc = fill_args(a, table, I, E, d, g, t, cur_c, cur_f, heads, pose_q_means, pose_q_quats, pose_t, seg_start, max_chunks);
+    if (rc != EMD_OK) return rc;
+    if (!emd_aligned(quats, 16) || !emd_aligned(world_quats, 16)) { emd_set_error("rigid_fwd: quats must be 16-B aligned"); return EMD_ERR_ALIGN; }
+    dim3 sg(max_chunks, I);
+    rigid_segmean_kernel<<<sg, RG_THREADS, 0, stream>>>(embeddings, g, order, seg_start, max_chunks, seg_partial);
+    rigid_instance_fwd_kernel<<<(I + 63) / 64, 64, 0, stream>>>(a, seg_partial, mean_emb, inst_out);
+    if (N > 0)
+        rigid_points_fwd_kernel<<<(unsigned)emd_cdiv(N, RG_THREADS), RG_THREADS, 0, stream>>>(
+            means, quats, point_ids, inst_out, N, world_means, world_quats);
+    EMD_CHECK_LAUNCH("rigid_deform_fwd");
+    return EMD_OK;
+}
+
+// scratch: pose_partial [I*max_chunks*16], params_partial [I*param_count]; v_table must be zero-filled by the caller.
+extern "C" int emd_rigid_deform_bwd(const float* means, const float* quats, const int64_t* point_ids,
+                                    const int64_t* order, const int64_t* seg_start, const float* table,
+                                    const float* const* heads, const float* pose_q_means, const float* pose_q_quats,
+                                    const float* pose_t, int64_t N, int I, int E, int d, int g, float t, int cur_c,
+                                    int cur_f, int max_chunks, const float* mean_emb, const float* inst_out,
+                                    const float* v_world_means, const float* v_world_quats, float* pose_partial,
+                                    float* params_partial, float* v_means, float* v_quats, float* v_embeddings,
+                                    float* v_table, float* v_params, float* v_pose_q_means, float* v_pose_q_quats,
+                                    float* v_pose_t, float* v_mean_emb, cudaStream_t stream) {
+    RigidArgs a;
+    int rc = fill_args(a, table, I, E, d, g, t, cur_c, cur_f, heads, pose_q_means, pose_q_quats, pose_t, seg_start, max_chunks);
+    if (rc != EMD_OK) return rc;
+    if (!emd_aligned(quats, 16) || !emd_aligned(v_world_quats, 16) || !emd_aligned(v_quats, 16)) {
+        emd_set_error("rigid_bwd: quats tensors must be 16-B aligned");
+        return EMD_ERR_ALIGN;
+    }
+    dim3 sg(max_chunks, I);
+    rigid_points_bwd_kernel<<<sg, RG_THREADS, 0, stream>>>(means, quats, order, seg_start, inst_out, max_chunks,
+                                                           v_world_means, v_world_quats, v_means, v_quats, pose_partial);
+    rigid_instance_bwd_kernel<<<(I + 63) / 64, 64, 0, stream>>>(a, mean_emb, pose_partial, v_pose_q_means,
+                                                                v_pose_q_quats, v_pose_t, params_partial, v_table, v_mean_emb);
+    const int pc = rigid_param_count(d + g);
+    params_reduce_kernel<<<(pc + 127) / 128, 128, 0, stream>>>(params_partial, I, pc, v_params);
+    if (N > 0 && g > 0)
+        embed_bwd_kernel<<<(unsigned)emd_cdiv(N * g, 256), 256, 0, stream>>>(v_mean_emb, point_ids, seg_start, g, N, v_embeddings);
+    EMD_CHECK_LAUNCH("rigid_deform_bwd");
+    return EMD_OK;
+}

@@ -67,3 +67,46 @@ extern "C" void emd_host_projection_bwd(const float* means, const float* quats, 
         for (int k = 0; k < 4; ++k) v_quats[i * 4 + k] = v_q[k];
     }
 }
+
+// ---- per-instance EMD heads (emd_math.cuh) -------------------------------------------------
+#include "emd_math.cuh"
+
+extern "C" int emd_host_rigid_param_count(int d, int g) { return rigid_param_count(d + g); }
+
+// heads: 8 host pointers in the order documented at emd_rigid_deform_fwd
+extern "C" void emd_host_rigid_instance_fwd(const float* table, int I, int E, int d, int g, const float* mean_emb,
+                                            float t, int cur_c, int cur_f, const float* const* heads,
+                                            const float* pose_q_means, const float* pose_q_quats, const float* pose_t,
+                                            float* inst_out /*[I][16]*/) {
+    RigidHeads H{heads[0], heads[1], heads[2], heads[3], heads[4], heads[5], heads[6], heads[7]};
+    for (int i = 0; i < I; ++i) {
+        RigidInstOut o;
+        rigid_instance_fwd(table + (int64_t)i * E * d, E, d, g, mean_emb + i * g, t, cur_c, cur_f, H,
+                           pose_q_means + i * 4, pose_q_quats + i * 4, pose_t + i * 3, o);
+        float* out = inst_out + i * 16;
+        for (int k = 0; k < 9; ++k) out[k] = o.R[k];
+        for (int k = 0; k < 3; ++k) out[9 + k] = o.t[k];
+        for (int k = 0; k < 4; ++k) out[12 + k] = o.Q[k];
+    }
+}
+
+extern "C" void emd_host_rigid_instance_bwd(const float* table, int I, int E, int d, int g, const float* mean_emb,
+                                            float t, int cur_c, int cur_f, const float* const* heads,
+                                            const float* pose_q_means, const float* pose_q_quats, const float* pose_t,
+                                            const float* v_inst /*[I][16]*/, float* v_pose_q_means,
+                                            float* v_pose_q_quats, float* v_pose_t, float* v_params /*[pc], summed*/,
+                                            float* v_table /*[I][E][d] zeroed*/, float* v_mean_emb) {
+    RigidHeads H{heads[0], heads[1], heads[2], heads[3], heads[4], heads[5], heads[6], heads[7]};
+    const int pc = rigid_param_count(d + g);
+    float* part = new float[pc];
+    for (int k = 0; k < pc; ++k) v_params[k] = 0.f;
+    for (int i = 0; i < I; ++i) {
+        const float* v = v_inst + i * 16;
+        rigid_instance_bwd(table + (int64_t)i * E * d, E, d, g, mean_emb + i * g, t, cur_c, cur_f, H,
+                           pose_q_means + i * 4, pose_q_quats + i * 4, pose_t + i * 3, v, v + 9, v + 12,
+                           v_pose_q_means + i * 4, v_pose_q_quats + i * 4, v_pose_t + i * 3, part,
+                           v_table + (int64_t)i * E * d, v_mean_emb + i * g);
+        for (int k = 0; k < pc; ++k) v_params[k] += part[k];
+    }
+    delete[] part;
+}

@@ -1,0 +1,149 @@
+"""CPU: the product's host-compilable math headers (proj_math.cuh, emd_math.cuh, built
+with g++ -ffp-contract=off) against the oracle.  Catches op-order and VJP mistakes
+without a GPU; the same headers are what the CUDA kernels include."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from emd_b200 import build, scenes
+from oracle import emd_rigid as ER
+from oracle import gsplat_ref as G
+
+P = ctypes.c_void_p
+
+
+@pytest.fixture(scope="module")
+def hostlib():
+    return ctypes.CDLL(str(build.build_hostmath()))
+
+
+def _fp(t):
+    return t.detach().contiguous().numpy().ctypes.data_as(P)
+
+
+@pytest.mark.parametrize("seed,yaws,near,clip", [(0, (0.0, 45.0, -45.0), 0.1, 0.0), (1, (10.0,), 0.01, 4.0)])
+def test_projection_bit_exact(hostlib, seed, yaws, near, clip):
+    g = torch.Generator().manual_seed(seed)
+    W, H, N = 960, 640, 60000
+    sc = scenes.simple_gaussians(N, g, W, H, depth=(0.05, 60.0))
+    viewmats, Ks, _ = scenes.cameras(yaws, W, H)
+    C = len(yaws)
+    radii, m2d, depths, conics, comps = G.projection(sc["means"], sc["quats"], sc["scales"], viewmats, Ks, W, H, 0.3,
+                                                     near, 1e10, clip)
+    r2 = np.zeros((C, N), np.int32); m2 = np.zeros((C, N, 2), np.float32); d2 = np.zeros((C, N), np.float32)
+    c2 = np.zeros((C, N, 3), np.float32); cp = np.zeros((C, N), np.float32); tp = np.zeros((C, N), np.int32)
+    rc = np.zeros((C, N, 4), np.int32)
+    f = hostlib.emd_host_projection_fwd
+    f.argtypes = [P] * 5 + [ctypes.c_int64] * 2 + [ctypes.c_int] * 2 + [ctypes.c_float] * 4 + [ctypes.c_int] * 2 + [P] * 7
+    f(_fp(sc["means"]), _fp(sc["quats"]), _fp(sc["scales"]), _fp(viewmats), _fp(Ks), N, C, W, H, 0.3, near, 1e10, clip,
+      60, 40, *[a.ctypes.data_as(P) for a in (r2, m2, d2, c2, cp, tp, rc)])
+    assert (radii > 0).sum() > N // 4
+    assert np.array_equal(r2, radii.numpy())
+    assert np.array_equal(m2.view(np.int32), m2d.numpy().view(np.int32))
+    assert np.array_equal(d2.view(np.int32), depths.numpy().view(np.int32))
+    assert np.array_equal(c2.view(np.int32), conics.numpy().view(np.int32))
+    tpg, ids, flat, bits = G.isect_tiles(m2d, radii, depths, 16, 60, 40)
+    assert np.array_equal(tp, tpg.numpy())
+    x0, y0, x1, y1 = G.tile_rects(m2d, radii, 16, 60, 40)
+    assert np.array_equal(rc, torch.stack([x0, y0, x1, y1], -1).numpy().astype(np.int32))
+
+
+def test_projection_vjp(hostlib):
+    g = torch.Generator().manual_seed(1)
+    W, H, N, C = 960, 640, 8000, 2
+    sc = scenes.simple_gaussians(N, g, W, H)
+    viewmats, Ks, _ = scenes.cameras((0.0, 30.0), W, H)
+    means = sc["means"].clone().requires_grad_(); quats = sc["quats"].clone().requires_grad_()
+    scales = sc["scales"].clone().requires_grad_()
+    radii, m2d, depths, conics, comps = G.projection(means, quats, scales, viewmats, Ks, W, H, 0.3, 0.1, 1e10, 0.0)
+    vm = torch.randn(C, N, 2, generator=g); vd = torch.randn(C, N, generator=g); vc = torch.randn(C, N, 3, generator=g)
+    ((m2d * vm).sum() + (depths * vd).sum() + (conics * vc).sum()).backward()
+    gm = np.zeros((N, 3), np.float32); gq = np.zeros((N, 4), np.float32); gs = np.zeros((N, 3), np.float32)
+    f = hostlib.emd_host_projection_bwd
+    f.argtypes = [P] * 5 + [ctypes.c_int64] * 2 + [ctypes.c_int] * 2 + [ctypes.c_float] * 4 + [P] * 6
+    f(_fp(means), _fp(quats), _fp(scales), _fp(viewmats), _fp(Ks), N, C, W, H, 0.3, 0.1, 1e10, 0.0, _fp(vm), _fp(vd),
+      _fp(vc), *[a.ctypes.data_as(P) for a in (gm, gq, gs)])
+    for got, ref in ((gm, means.grad), (gq, quats.grad), (gs, scales.grad)):
+        got = torch.from_numpy(got)
+        assert float((got - ref).abs().max() / ref.abs().max()) < 1e-4
+
+
+def _rigid_problem(seed, I=5, step=7000, frame=37, empty_instance=False):
+    g = torch.Generator().manual_seed(seed)
+    rs = scenes.rigid_nodes(I, 40, g, num_frames=60)
+    if empty_instance:
+        rs.point_ids[rs.point_ids == 2] = 1  # instance 2 owns no points -> NaN mean -> offsets skipped
+    p = ER.RigidEMD(point_ids=rs.point_ids[:, 0], embeddings=rs.embeddings, weight=rs.weight,
+                    instances_quats=rs.instances_quats + 0.05 * torch.randn(rs.instances_quats.shape, generator=g),
+                    instances_trans=rs.instances_trans, instances_fv=rs.instances_fv,
+                    **{k: v for k, v in rs.track.items()})
+    return rs, p, frame, step
+
+
+@pytest.mark.parametrize("seed,step,empty", [(0, 0, False), (1, 7000, False), (2, 20000, True), (3, 31000, False)])
+def test_rigid_instance_heads(hostlib, seed, step, empty):
+    """emd_math.cuh per-instance forward + VJP vs the oracle's restatement of rigid.py:150-246."""
+    rs, p, frame, step = _rigid_problem(seed, step=step, empty_instance=empty)
+    I, E, d = p.weight.shape
+    gdim = p.embeddings.shape[1]
+    leaves = dict(weight=p.weight, iq=p.instances_quats, it=p.instances_trans, emb=p.embeddings,
+                  **{k: getattr(p, k) for k in ("rot_c_w", "rot_c_b", "rot_f_w", "rot_f_b", "trans_c_w", "trans_c_b",
+                                                "trans_f_w", "trans_f_b")})
+    for v in leaves.values():
+        v.requires_grad_(True)
+    # oracle: per-instance pose (R, t, Q)
+    from oracle.quat import quat_act, quat_mult, quat_to_rotmat
+    dtrans, qoff, ok_t, ok_q = ER.track_offsets(p, frame, step)
+    assert bool(ok_t.all()) == (not empty)
+    R = quat_to_rotmat(quat_act(p.instances_quats[frame]))
+    tt = p.instances_trans[frame] + dtrans
+    Qg = torch.where(ok_q[:, None], quat_mult(p.instances_quats[frame], qoff), p.instances_quats[frame])
+    Q = quat_act(Qg)
+    ref = torch.cat([R.reshape(I, 9), tt, Q], dim=1)
+    v = torch.randn(I, 16, generator=torch.Generator().manual_seed(seed + 100))
+    (ref * v).sum().backward()
+
+    mean_emb = torch.stack([p.embeddings[p.point_ids == i].mean(0) for i in range(I)]).detach()
+    t = np.float32(frame / (p.num_frames - 1))
+    cur_c, cur_f = 30, ER.int_lininterp(step, 30, 150, 20000)
+    heads = [getattr(p, k).detach().contiguous() for k in ("rot_c_w", "rot_c_b", "rot_f_w", "rot_f_b", "trans_c_w",
+                                                           "trans_c_b", "trans_f_w", "trans_f_b")]
+    harr = (P * 8)(*[h.numpy().ctypes.data_as(P) for h in heads])
+    out = np.zeros((I, 16), np.float32)
+    pq = p.instances_quats[frame].detach().contiguous(); pt = p.instances_trans[frame].detach().contiguous()
+    f = hostlib.emd_host_rigid_instance_fwd
+    f.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, P, ctypes.c_float, ctypes.c_int,
+                  ctypes.c_int, P, P, P, P, P]
+    f(_fp(p.weight), I, E, d, gdim, _fp(mean_emb), t, cur_c, cur_f, harr, _fp(pq), _fp(pq), _fp(pt),
+      out.ctypes.data_as(P))
+    assert np.allclose(out, ref.detach().numpy(), rtol=2e-5, atol=2e-6), np.abs(out - ref.detach().numpy()).max()
+
+    pc = hostlib.emd_host_rigid_param_count(d, gdim)
+    v_pqm = np.zeros((I, 4), np.float32); v_pqq = np.zeros((I, 4), np.float32); v_pt = np.zeros((I, 3), np.float32)
+    v_params = np.zeros(pc, np.float32); v_table = np.zeros((I, E, d), np.float32); v_me = np.zeros((I, gdim), np.float32)
+    b = hostlib.emd_host_rigid_instance_bwd
+    b.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, P, ctypes.c_float, ctypes.c_int,
+                  ctypes.c_int, P, P, P, P, P, P, P, P, P, P, P]
+    b(_fp(p.weight), I, E, d, gdim, _fp(mean_emb), t, cur_c, cur_f, harr, _fp(pq), _fp(pq), _fp(pt), _fp(v),
+      *[a.ctypes.data_as(P) for a in (v_pqm, v_pqq, v_pt, v_params, v_table, v_me)])
+
+    def close(a, b_, name):
+        b_ = b_.detach().numpy()
+        scale = max(np.abs(b_).max(), 1e-12)
+        assert np.abs(a - b_).max() <= 2e-4 * scale, f"{name}: {np.abs(a - b_).max()} vs scale {scale}"
+
+    close(v_pqm + v_pqq, p.instances_quats.grad[frame], "instances_quats")
+    close(v_pt, p.instances_trans.grad[frame], "instances_trans")
+    close(v_table, p.weight.grad, "weight")
+    off = 0
+    for k in ("rot_c_w", "rot_c_b", "rot_f_w", "rot_f_b", "trans_c_w", "trans_c_b", "trans_f_w", "trans_f_b"):
+        ref_g = getattr(p, k).grad
+        n = ref_g.numel()
+        close(v_params[off:off + n].reshape(ref_g.shape), ref_g, k)
+        off += n
+    # mean-embedding gradient, spread over the instance's points
+    cnt = torch.stack([(p.point_ids == i).sum() for i in range(I)]).float()
+    per_point = torch.nan_to_num(torch.from_numpy(v_me))[p.point_ids] / cnt[p.point_ids][:, None]
+    close(per_point.numpy(), p.embeddings.grad, "embeddings")
