@@ -45,7 +45,7 @@ _SIGS = {
     "emd_rigid_deform_fwd": (c_int, [P] * 11 + [c_int64, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int]
                              + [P] * 5 + [P]),
     "emd_rigid_deform_bwd": (c_int, [P] * 10 + [c_int64, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int]
-                             + [P] * 16 + [P]),
+                             + [P] * 15 + [P]),
     "emd_rasterize_bwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
                                   P, P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
 }
