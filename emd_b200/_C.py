@@ -46,6 +46,11 @@ _SIGS = {
                              + [P] * 5 + [P]),
     "emd_rigid_deform_bwd": (c_int, [P] * 10 + [c_int64, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int]
                              + [P] * 15 + [P]),
+    "emd_smpl_param_count": (c_int, [c_int, c_int]),
+    "emd_smpl_max_chunks": (c_int, [c_int]),
+    "emd_smpl_reduce_width": (c_int, []),
+    "emd_smpl_deform_fwd": (c_int, [P] * 12 + [c_int] * 5 + [c_float, c_int, c_int] + [P] * 5 + [P]),
+    "emd_smpl_deform_bwd": (c_int, [P] * 11 + [c_int] * 5 + [c_float, c_int, c_int] + [P] * 14 + [P]),
     "emd_rasterize_bwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
                                   P, P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
 }

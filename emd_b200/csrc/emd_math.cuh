@@ -264,3 +264,230 @@ EMD_HD void rigid_instance_bwd(const float* table, int E, int d, int g, const fl
     temb_vjp(v_table, d, tf, v_hf);
     for (int k = 0; k < g; ++k) v_mean_emb[k] = v_hc[d + k] + v_hf[d + k];
 }
+
+// --------------------------------------------------------------------------
+// SMPL node: per-instance joint transforms with EMD joint-yaw offsets
+// (smpl.py:401-436, 459-489; human_body.py:158-172; smplx batch_rigid_transform)
+// --------------------------------------------------------------------------
+constexpr int SMPL_J = 24;
+EMD_HD int smpl_param_count(int in) { return 2 * (SMPL_J * in + SMPL_J); }
+
+struct SmplHeads { const float *c_w, *c_b, *f_w, *f_b; };  // track_smpl_{c,f}: nn.Linear(d+g, 24)
+
+// 3x4 helpers: T = [R(9) | t(3)], stored R row-major then t
+EMD_HD void mat3_mul(const float* A, const float* B, float* C) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+}
+EMD_HD void mat3_vec(const float* A, const float* v, float* o) {
+    for (int i = 0; i < 3; ++i) o[i] = A[i * 3] * v[0] + A[i * 3 + 1] * v[1] + A[i * 3 + 2] * v[2];
+}
+
+// theta: [24][4] pose quaternions (global orient + 23 joints); J: [24][3]; A0inv: [24][16] row-major 4x4;
+// parents: [24]; out A: [24][12] (R row-major, then t).  Saves offsets qoff[24][4] for nothing: recomputed in bwd.
+EMD_HD void smpl_instance_fwd(const float* table, int E, int d, int g, const float* mean_emb, float t, int cur_c,
+                              int cur_f, const SmplHeads& H, const float* theta, const float* J, const float* A0inv,
+                              const int* parents, float* A /*[24][12]*/) {
+    float hc[EMD_TDIM_MAX + EMD_GDIM_MAX], hf[EMD_TDIM_MAX + EMD_GDIM_MAX];
+    TembTaps tc, tf;
+    temb_taps(t, cur_c, E, tc);
+    temb_taps(t, cur_f, E, tf);
+    temb_eval(table, d, tc, hc);
+    temb_eval(table, d, tf, hf);
+    for (int k = 0; k < g; ++k) { hc[d + k] = mean_emb[k]; hf[d + k] = mean_emb[k]; }
+    const int in = d + g;
+    float ac[SMPL_J], af[SMPL_J];
+    linear_fwd(H.c_w, H.c_b, SMPL_J, in, hc, ac);
+    linear_fwd(H.f_w, H.f_b, SMPL_J, in, hf, af);
+    const bool skip = any_nan(ac, SMPL_J) || any_nan(af, SMPL_J);
+    float G[SMPL_J][12];
+    for (int j = 0; j < SMPL_J; ++j) {
+        float th[4];
+        if (skip) { for (int k = 0; k < 4; ++k) th[k] = theta[j * 4 + k]; }
+        else {
+            const float qc[4] = {cosf(ac[j]), 0.f, 0.f, sinf(ac[j])}, qf[4] = {cosf(af[j]), 0.f, 0.f, sinf(af[j])};
+            float qo[4];
+            qmul(qc, qf, qo);
+            qmul(theta + j * 4, qo, th);
+        }
+        float thn[4], R[9];
+        qnormalize(th, thn);
+        qrot(thn, R);
+        const int p = parents[j];
+        if (p < 0) {
+            for (int k = 0; k < 9; ++k) G[j][k] = R[k];
+            for (int k = 0; k < 3; ++k) G[j][9 + k] = J[j * 3 + k];
+        } else {
+            const float rel[3] = {J[j * 3] - J[p * 3], J[j * 3 + 1] - J[p * 3 + 1], J[j * 3 + 2] - J[p * 3 + 2]};
+            mat3_mul(G[p], R, G[j]);
+            float tr[3];
+            mat3_vec(G[p], rel, tr);
+            for (int k = 0; k < 3; ++k) G[j][9 + k] = tr[k] + G[p][9 + k];
+        }
+        // A' = [G.R | G.t - G.R J];  A = A' * A0inv
+        float RJ[3];
+        mat3_vec(G[j], J + j * 3, RJ);
+        const float tp[3] = {G[j][9] - RJ[0], G[j][10] - RJ[1], G[j][11] - RJ[2]};
+        const float* I4 = A0inv + j * 16;
+        const float Ri[9] = {I4[0], I4[1], I4[2], I4[4], I4[5], I4[6], I4[8], I4[9], I4[10]};
+        const float ti[3] = {I4[3], I4[7], I4[11]};
+        mat3_mul(G[j], Ri, A + j * 12);
+        float rt[3];
+        mat3_vec(G[j], ti, rt);
+        for (int k = 0; k < 3; ++k) A[j * 12 + 9 + k] = rt[k] + tp[k];
+    }
+}
+
+// v_A: [24][12].  Outputs: v_theta[24][4], v_params (this instance's partial, zeroed here),
+// v_table (accumulated), v_mean_emb[g].
+EMD_HD void smpl_instance_bwd(const float* table, int E, int d, int g, const float* mean_emb, float t, int cur_c,
+                              int cur_f, const SmplHeads& H, const float* theta, const float* J, const float* A0inv,
+                              const int* parents, const float* v_A, float* v_theta, float* v_params, float* v_table,
+                              float* v_mean_emb) {
+    const int in = d + g;
+    float hc[EMD_TDIM_MAX + EMD_GDIM_MAX], hf[EMD_TDIM_MAX + EMD_GDIM_MAX];
+    TembTaps tc, tf;
+    temb_taps(t, cur_c, E, tc);
+    temb_taps(t, cur_f, E, tf);
+    temb_eval(table, d, tc, hc);
+    temb_eval(table, d, tf, hf);
+    for (int k = 0; k < g; ++k) { hc[d + k] = mean_emb[k]; hf[d + k] = mean_emb[k]; }
+    float ac[SMPL_J], af[SMPL_J];
+    linear_fwd(H.c_w, H.c_b, SMPL_J, in, hc, ac);
+    linear_fwd(H.f_w, H.f_b, SMPL_J, in, hf, af);
+    const bool skip = any_nan(ac, SMPL_J) || any_nan(af, SMPL_J);
+    // forward replay
+    float G[SMPL_J][12], Rj[SMPL_J][9], thn[SMPL_J][4], thinv[SMPL_J], qo[SMPL_J][4];
+    for (int j = 0; j < SMPL_J; ++j) {
+        float th[4];
+        if (skip) { for (int k = 0; k < 4; ++k) th[k] = theta[j * 4 + k]; }
+        else {
+            const float qc[4] = {cosf(ac[j]), 0.f, 0.f, sinf(ac[j])}, qf[4] = {cosf(af[j]), 0.f, 0.f, sinf(af[j])};
+            qmul(qc, qf, qo[j]);
+            qmul(theta + j * 4, qo[j], th);
+        }
+        thinv[j] = qnormalize(th, thn[j]);
+        qrot(thn[j], Rj[j]);
+        const int p = parents[j];
+        if (p < 0) {
+            for (int k = 0; k < 9; ++k) G[j][k] = Rj[j][k];
+            for (int k = 0; k < 3; ++k) G[j][9 + k] = J[j * 3 + k];
+        } else {
+            const float rel[3] = {J[j * 3] - J[p * 3], J[j * 3 + 1] - J[p * 3 + 1], J[j * 3 + 2] - J[p * 3 + 2]};
+            mat3_mul(G[p], Rj[j], G[j]);
+            float tr[3];
+            mat3_vec(G[p], rel, tr);
+            for (int k = 0; k < 3; ++k) G[j][9 + k] = tr[k] + G[p][9 + k];
+        }
+    }
+    // v_G from v_A
+    float vG[SMPL_J][12];
+    for (int j = 0; j < SMPL_J; ++j) {
+        const float* I4 = A0inv + j * 16;
+        const float Ri[9] = {I4[0], I4[1], I4[2], I4[4], I4[5], I4[6], I4[8], I4[9], I4[10]};
+        const float ti[3] = {I4[3], I4[7], I4[11]};
+        const float* vAR = v_A + j * 12;
+        const float* vAt = v_A + j * 12 + 9;
+        // A.R = G.R Ri ; A.t = G.R ti + (G.t - G.R J)
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) {
+                float s = vAR[r * 3] * Ri[c * 3] + vAR[r * 3 + 1] * Ri[c * 3 + 1] + vAR[r * 3 + 2] * Ri[c * 3 + 2];  // vAR * Ri^T
+                s += vAt[r] * (ti[c] - J[j * 3 + c]);
+                vG[j][r * 3 + c] = s;
+            }
+        for (int k = 0; k < 3; ++k) vG[j][9 + k] = vAt[k];
+    }
+    float* p_ = v_params;
+    float* v_c_w = p_; p_ += SMPL_J * in; float* v_c_b = p_; p_ += SMPL_J;
+    float* v_f_w = p_; p_ += SMPL_J * in; float* v_f_b = p_;
+    for (int k = 0; k < smpl_param_count(in); ++k) v_params[k] = 0.0f;
+    float v_ac[SMPL_J];
+    for (int j = SMPL_J - 1; j >= 0; --j) {
+        const int p = parents[j];
+        float vR[9];
+        if (p < 0) {
+            for (int k = 0; k < 9; ++k) vR[k] = vG[j][k];
+        } else {
+            const float rel[3] = {J[j * 3] - J[p * 3], J[j * 3 + 1] - J[p * 3 + 1], J[j * 3 + 2] - J[p * 3 + 2]};
+            // G_j.R = G_p.R R_j ; G_j.t = G_p.R rel + G_p.t
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) {
+                    // v_Gp.R += vG_j.R R_j^T + vG_j.t (x) rel
+                    vG[p][r * 3 + c] += vG[j][r * 3] * Rj[j][c * 3] + vG[j][r * 3 + 1] * Rj[j][c * 3 + 1] +
+                                        vG[j][r * 3 + 2] * Rj[j][c * 3 + 2] + vG[j][9 + r] * rel[c];
+                    // v_R_j = G_p.R^T vG_j.R
+                    vR[r * 3 + c] = G[p][0 * 3 + r] * vG[j][0 * 3 + c] + G[p][1 * 3 + r] * vG[j][1 * 3 + c] +
+                                    G[p][2 * 3 + r] * vG[j][2 * 3 + c];
+                }
+            for (int k = 0; k < 3; ++k) vG[p][9 + k] += vG[j][9 + k];
+        }
+        float vthn[4], vth[4];
+        qrot_vjp(thn[j], vR, vthn);
+        qnormalize_vjp(thn[j], thinv[j], vthn, vth);
+        if (skip) {
+            for (int k = 0; k < 4; ++k) v_theta[j * 4 + k] = vth[k];
+            v_ac[j] = 0.0f;
+        } else {
+            float vqo[4];
+            qmul_vjp(theta + j * 4, qo[j], vth, v_theta + j * 4, vqo);
+            v_ac[j] = -qo[j][3] * vqo[0] + qo[j][0] * vqo[3];
+        }
+    }
+    float v_hc[EMD_TDIM_MAX + EMD_GDIM_MAX], v_hf[EMD_TDIM_MAX + EMD_GDIM_MAX];
+    for (int k = 0; k < in; ++k) { v_hc[k] = 0.0f; v_hf[k] = 0.0f; }
+    if (!skip) {
+        linear_vjp(H.c_w, SMPL_J, in, hc, v_ac, v_c_w, v_c_b, v_hc);
+        linear_vjp(H.f_w, SMPL_J, in, hf, v_ac, v_f_w, v_f_b, v_hf);
+    }
+    temb_vjp(v_table, d, tc, v_hc);
+    temb_vjp(v_table, d, tf, v_hf);
+    for (int k = 0; k < g; ++k) v_mean_emb[k] = v_hc[d + k] + v_hf[d + k];
+}
+
+// pytorch3d.transforms.matrix_to_quaternion (+ w >= 0 standardisation), row-major m[9] -> q[4]; returns branch | sign<<2
+EMD_HD int mat_to_quat(const float* m, float* q) {
+    const float m00 = m[0], m01 = m[1], m02 = m[2], m10 = m[3], m11 = m[4], m12 = m[5], m20 = m[6], m21 = m[7], m22 = m[8];
+    const float s[4] = {1.0f + m00 + m11 + m22, 1.0f + m00 - m11 - m22, 1.0f - m00 + m11 - m22, 1.0f - m00 - m11 + m22};
+    float qa[4];
+    int best = 0;
+    for (int k = 0; k < 4; ++k) { qa[k] = s[k] > 0.0f ? sqrtf(s[k]) : 0.0f; if (qa[k] > qa[best]) best = k; }
+    float num[4];
+    if (best == 0) { num[0] = qa[0] * qa[0]; num[1] = m21 - m12; num[2] = m02 - m20; num[3] = m10 - m01; }
+    else if (best == 1) { num[0] = m21 - m12; num[1] = qa[1] * qa[1]; num[2] = m10 + m01; num[3] = m02 + m20; }
+    else if (best == 2) { num[0] = m02 - m20; num[1] = m10 + m01; num[2] = qa[2] * qa[2]; num[3] = m12 + m21; }
+    else { num[0] = m10 - m01; num[1] = m20 + m02; num[2] = m21 + m12; num[3] = qa[3] * qa[3]; }
+    const float den = 2.0f * fmaxf(qa[best], 0.1f);
+    int flip = num[0] / den < 0.0f ? 1 : 0;
+    for (int k = 0; k < 4; ++k) q[k] = (flip ? -num[k] : num[k]) / den;
+    return best | (flip << 2);
+}
+
+EMD_HD void mat_to_quat_vjp(const float* m, const float* v_q_in, float* v_m) {
+    const float m00 = m[0], m01 = m[1], m02 = m[2], m10 = m[3], m11 = m[4], m12 = m[5], m20 = m[6], m21 = m[7], m22 = m[8];
+    const float s[4] = {1.0f + m00 + m11 + m22, 1.0f + m00 - m11 - m22, 1.0f - m00 + m11 - m22, 1.0f - m00 - m11 + m22};
+    float qa[4];
+    int best = 0;
+    for (int k = 0; k < 4; ++k) { qa[k] = s[k] > 0.0f ? sqrtf(s[k]) : 0.0f; if (qa[k] > qa[best]) best = k; }
+    float num[4];
+    if (best == 0) { num[0] = qa[0] * qa[0]; num[1] = m21 - m12; num[2] = m02 - m20; num[3] = m10 - m01; }
+    else if (best == 1) { num[0] = m21 - m12; num[1] = qa[1] * qa[1]; num[2] = m10 + m01; num[3] = m02 + m20; }
+    else if (best == 2) { num[0] = m02 - m20; num[1] = m10 + m01; num[2] = qa[2] * qa[2]; num[3] = m12 + m21; }
+    else { num[0] = m10 - m01; num[1] = m20 + m02; num[2] = m21 + m12; num[3] = qa[3] * qa[3]; }
+    const float den = 2.0f * fmaxf(qa[best], 0.1f);
+    const bool flip = num[0] / den < 0.0f;
+    float v_q[4];
+    for (int k = 0; k < 4; ++k) v_q[k] = flip ? -v_q_in[k] : v_q_in[k];
+    float v_num[4], v_den = 0.0f;
+    for (int k = 0; k < 4; ++k) { v_num[k] = v_q[k] / den; v_den -= v_q[k] * num[k] / (den * den); }
+    // den = 2 max(qa, .1); num[best] = qa^2 ; qa = sqrt(s_best)
+    float v_qa = (qa[best] > 0.1f ? 2.0f * v_den : 0.0f) + 2.0f * qa[best] * v_num[best];
+    const float v_s = qa[best] > 0.0f ? v_qa / (2.0f * qa[best]) : 0.0f;
+    for (int k = 0; k < 9; ++k) v_m[k] = 0.0f;
+    const float sg[4][3] = {{1, 1, 1}, {1, -1, -1}, {-1, 1, -1}, {-1, -1, 1}};
+    v_m[0] += sg[best][0] * v_s; v_m[4] += sg[best][1] * v_s; v_m[8] += sg[best][2] * v_s;
+    // off-diagonal combos: (index in m, sign) per numerator slot
+    if (best == 0) { v_m[7] += v_num[1]; v_m[5] -= v_num[1]; v_m[2] += v_num[2]; v_m[6] -= v_num[2]; v_m[3] += v_num[3]; v_m[1] -= v_num[3]; }
+    else if (best == 1) { v_m[7] += v_num[0]; v_m[5] -= v_num[0]; v_m[3] += v_num[2]; v_m[1] += v_num[2]; v_m[2] += v_num[3]; v_m[6] += v_num[3]; }
+    else if (best == 2) { v_m[2] += v_num[0]; v_m[6] -= v_num[0]; v_m[3] += v_num[1]; v_m[1] += v_num[1]; v_m[5] += v_num[3]; v_m[7] += v_num[3]; }
+    else { v_m[3] += v_num[0]; v_m[1] -= v_num[0]; v_m[6] += v_num[1]; v_m[2] += v_num[1]; v_m[7] += v_num[2]; v_m[5] += v_num[2]; }
+}

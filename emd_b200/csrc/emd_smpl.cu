@@ -1,0 +1,343 @@
+// K1c: EMD motion-embedding deformation of SMPL nodes, forward and backward.
+//
+// Replaces SMPLNodes.transform_means_and_quats (OmniRe/models/nodes/smpl.py:438-532)
+// + SMPLTemplate.forward's kinematic chain (human_body.py:158-172):
+//   segmean  : per-instance mean motion embedding (instances own V contiguous points)
+//   instance : one thread per instance -- 24 EMD joint-yaw offsets, pose quats -> rotations,
+//              24-joint kinematic chain, A = chain * A0_inv                  [emd_math.cuh]
+//   points   : one thread per Gaussian -- T = sum_j W[n,j] A[j] (linear-blend skinning),
+//              x' = T.R x + T.t + trans, q' = normalize(mat2quat(T.R)) (x) normalize(q);
+//              invisible instances get x' = trans, q' = identity (smpl.py:498-530)
+// Backward reduces dL/dA (24x12 per instance) as a fixed-order [24x256]x[256x12]
+// product per 256-point slab: no float atomics.
+#include "common.cuh"
+#include "emd_math.cuh"
+
+namespace {
+
+constexpr int SM_THREADS = 256;
+constexpr int SM_CHUNK = 1024;                 // points per (instance, chunk) block
+constexpr int SM_AOUT = SMPL_J * 12;           // 288 floats of A per instance
+constexpr int SM_RED = SM_AOUT + 3;            // + v_trans
+
+struct SmplArgs {
+    const float* table;   // [I][E][d]
+    int I, E, d, g, V;
+    float t;
+    int cur_c, cur_f;
+    SmplHeads H;
+    const float* theta;    // [I][24][4]
+    const float* trans;    // [I][3]
+    const uint8_t* visible;  // [I]
+    const float* J;        // [I][24][3]
+    const float* A0inv;    // [I][24][16]
+    const float* W;        // [I][V][24]
+    const int* parents;    // [24]
+    int max_chunks;
+};
+
+__global__ void __launch_bounds__(SM_THREADS) smpl_segmean_kernel(const float* __restrict__ emb, int g, int V,
+                                                                  int max_chunks, float* __restrict__ partial) {
+    __shared__ float s_scratch[SM_THREADS / 32 * EMD_GDIM_MAX];
+    const int inst = blockIdx.y, chunk = blockIdx.x;
+    const int64_t lo = (int64_t)inst * V + (int64_t)chunk * SM_CHUNK;
+    const int64_t hi = min((int64_t)(inst + 1) * V, lo + SM_CHUNK);
+    float acc[EMD_GDIM_MAX];
+#pragma unroll
+    for (int k = 0; k < EMD_GDIM_MAX; ++k) acc[k] = 0.f;
+    for (int64_t n = lo + threadIdx.x; n < hi; n += SM_THREADS) {
+#pragma unroll
+        for (int k = 0; k < EMD_GDIM_MAX; ++k)
+            if (k < g) acc[k] += emb[n * g + k];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < EMD_GDIM_MAX; ++k) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
+    }
+    if (lane == 0)
+        for (int k = 0; k < EMD_GDIM_MAX; ++k) s_scratch[warp * EMD_GDIM_MAX + k] = acc[k];
+    __syncthreads();
+    if (threadIdx.x < g) {
+        float s = 0.f;
+        for (int w = 0; w < SM_THREADS / 32; ++w) s += s_scratch[w * EMD_GDIM_MAX + threadIdx.x];
+        partial[((int64_t)inst * max_chunks + chunk) * g + threadIdx.x] = s;
+    }
+}
+
+__global__ void smpl_instance_fwd_kernel(SmplArgs a, const float* __restrict__ seg_partial,
+                                         float* __restrict__ mean_emb, float* __restrict__ A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.I) return;
+    const int nch = (a.V + SM_CHUNK - 1) / SM_CHUNK;
+    float m[EMD_GDIM_MAX];
+    for (int k = 0; k < a.g; ++k) {
+        float s = 0.f;
+        for (int c = 0; c < nch; ++c) s += seg_partial[((int64_t)i * a.max_chunks + c) * a.g + k];
+        m[k] = s / (float)a.V;
+        mean_emb[i * a.g + k] = m[k];
+    }
+    if (!a.visible[i]) return;
+    int par[SMPL_J];
+    for (int j = 0; j < SMPL_J; ++j) par[j] = a.parents[j];
+    smpl_instance_fwd(a.table + (int64_t)i * a.E * a.d, a.E, a.d, a.g, m, a.t, a.cur_c, a.cur_f, a.H,
+                      a.theta + (int64_t)i * SMPL_J * 4, a.J + (int64_t)i * SMPL_J * 3,
+                      a.A0inv + (int64_t)i * SMPL_J * 16, par, A + (int64_t)i * SM_AOUT);
+}
+
+__device__ __forceinline__ void blend_T(const float* __restrict__ Wn, const float* __restrict__ Ab, float* T) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = 0.f;
+    for (int j = 0; j < SMPL_J; ++j) {
+        const float w = Wn[j];
+        if (w == 0.f) continue;  // LBS weights are sparse; 0 * finite adds nothing
+#pragma unroll
+        for (int k = 0; k < 12; ++k) T[k] += w * Ab[j * 12 + k];
+    }
+}
+
+__global__ void __launch_bounds__(SM_THREADS) smpl_points_fwd_kernel(SmplArgs a, const float* __restrict__ A,
+                                                                     const float* __restrict__ means,
+                                                                     const float* __restrict__ quats, int64_t N,
+                                                                     float* __restrict__ world_means,
+                                                                     float* __restrict__ world_quats) {
+    const int64_t n = (int64_t)blockIdx.x * SM_THREADS + threadIdx.x;
+    if (n >= N) return;
+    const int b = (int)(n / a.V);
+    const float tx = a.trans[b * 3], ty = a.trans[b * 3 + 1], tz = a.trans[b * 3 + 2];
+    if (!a.visible[b]) {
+        world_means[n * 3] = tx; world_means[n * 3 + 1] = ty; world_means[n * 3 + 2] = tz;
+        reinterpret_cast<float4*>(world_quats)[n] = make_float4(1.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    float T[12];
+    blend_T(a.W + n * SMPL_J, A + (int64_t)b * SM_AOUT, T);
+    const float x = means[n * 3], y = means[n * 3 + 1], z = means[n * 3 + 2];
+    world_means[n * 3 + 0] = T[0] * x + T[1] * y + T[2] * z + T[9] + tx;
+    world_means[n * 3 + 1] = T[3] * x + T[4] * y + T[5] * z + T[10] + ty;
+    world_means[n * 3 + 2] = T[6] * x + T[7] * y + T[8] * z + T[11] + tz;
+    float qR[4], qRn[4], qn[4], o[4];
+    mat_to_quat(T, qR);
+    qnormalize(qR, qRn);
+    const float4 q4 = __ldg(reinterpret_cast<const float4*>(quats) + n);
+    const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+    qnormalize(q, qn);
+    qmul(qRn, qn, o);
+    reinterpret_cast<float4*>(world_quats)[n] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// grid (max_chunks, I)
+__global__ void __launch_bounds__(SM_THREADS) smpl_points_bwd_kernel(
+    SmplArgs a, const float* __restrict__ A, const float* __restrict__ means, const float* __restrict__ quats,
+    const float* __restrict__ v_world_means, const float* __restrict__ v_world_quats, float* __restrict__ v_means,
+    float* __restrict__ v_quats, float* __restrict__ red_partial) {
+    __shared__ float s_vT[SM_THREADS][13];
+    __shared__ float s_W[SM_THREADS][SMPL_J + 1];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int64_t lo = (int64_t)b * a.V + (int64_t)chunk * SM_CHUNK;
+    const int64_t hi = min((int64_t)(b + 1) * a.V, lo + SM_CHUNK);
+    if (lo >= hi) return;  // block-uniform
+    const bool vis = a.visible[b] != 0;
+    const float* Ab = A + (int64_t)b * SM_AOUT;
+    // each thread owns up to two of the 291 reduced outputs
+    float acc0 = 0.f, acc1 = 0.f;
+    const int o0 = threadIdx.x, o1 = threadIdx.x + SM_THREADS;
+    for (int64_t base = lo; base < hi; base += SM_THREADS) {
+        const int64_t n = base + threadIdx.x;
+        float vT[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) vT[k] = 0.f;
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+        if (n < hi) {
+            gx = v_world_means[n * 3]; gy = v_world_means[n * 3 + 1]; gz = v_world_means[n * 3 + 2];
+            if (!vis) {
+                v_means[n * 3] = 0.f; v_means[n * 3 + 1] = 0.f; v_means[n * 3 + 2] = 0.f;
+                reinterpret_cast<float4*>(v_quats)[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                float T[12];
+                blend_T(a.W + n * SMPL_J, Ab, T);
+                const float x = means[n * 3], y = means[n * 3 + 1], z = means[n * 3 + 2];
+                v_means[n * 3 + 0] = T[0] * gx + T[3] * gy + T[6] * gz;
+                v_means[n * 3 + 1] = T[1] * gx + T[4] * gy + T[7] * gz;
+                v_means[n * 3 + 2] = T[2] * gx + T[5] * gy + T[8] * gz;
+                vT[0] = gx * x; vT[1] = gx * y; vT[2] = gx * z;
+                vT[3] = gy * x; vT[4] = gy * y; vT[5] = gy * z;
+                vT[6] = gz * x; vT[7] = gz * y; vT[8] = gz * z;
+                vT[9] = gx; vT[10] = gy; vT[11] = gz;
+                // quaternion path
+                float qR[4], qRn[4], qn[4];
+                mat_to_quat(T, qR);
+                const float invR = qnormalize(qR, qRn);
+                const float4 q4 = __ldg(reinterpret_cast<const float4*>(quats) + n);
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(v_world_quats) + n);
+                const float q[4] = {q4.x, q4.y, q4.z, q4.w}, vg[4] = {g4.x, g4.y, g4.z, g4.w};
+                const float invq = qnormalize(q, qn);
+                float v_qRn[4], v_qn[4], v_qR[4], v_q[4], v_m[9];
+                qmul_vjp(qRn, qn, vg, v_qRn, v_qn);
+                qnormalize_vjp(qn, invq, v_qn, v_q);
+                reinterpret_cast<float4*>(v_quats)[n] = make_float4(v_q[0], v_q[1], v_q[2], v_q[3]);
+                qnormalize_vjp(qRn, invR, v_qRn, v_qR);
+                mat_to_quat_vjp(T, v_qR, v_m);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) vT[k] += v_m[k];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 12; ++k) s_vT[threadIdx.x][k] = vT[k];
+        s_vT[threadIdx.x][12] = 0.f;
+        for (int j = 0; j < SMPL_J; ++j) s_W[threadIdx.x][j] = (n < hi && vis) ? a.W[n * SMPL_J + j] : 0.f;
+        // v_trans contribution rides in slot 12.. via separate sums below
+        __syncthreads();
+        const int npts = (int)min((int64_t)SM_THREADS, hi - base);
+        // outputs 0..287: (j, k) -> sum_pt W[pt][j] * vT[pt][k];  288..290: sum_pt g[pt]
+        if (vis && o0 < SM_AOUT) {
+            const int j = o0 / 12, k = o0 - j * 12;
+            float s = 0.f;
+            for (int pt = 0; pt < npts; ++pt) s += s_W[pt][j] * s_vT[pt][k];
+            acc0 += s;
+        }
+        if (vis && o1 < SM_AOUT) {
+            const int j = o1 / 12, k = o1 - j * 12;
+            float s = 0.f;
+            for (int pt = 0; pt < npts; ++pt) s += s_W[pt][j] * s_vT[pt][k];
+            acc1 += s;
+        }
+        // v_trans: reuse s_vT slots 9..11 when visible; for invisible instances stash g there now
+        __syncthreads();
+        if (!vis) { s_vT[threadIdx.x][9] = gx; s_vT[threadIdx.x][10] = gy; s_vT[threadIdx.x][11] = gz; }
+        __syncthreads();
+        if (o1 >= SM_AOUT && o1 < SM_RED) {
+            const int k = o1 - SM_AOUT;
+            float s = 0.f;
+            for (int pt = 0; pt < npts; ++pt) s += s_vT[pt][9 + k];
+            acc1 += s;
+        }
+    }
+    float* out = red_partial + ((int64_t)b * a.max_chunks + chunk) * SM_RED;
+    if (o0 < SM_RED) out[o0] = acc0;
+    if (o1 < SM_RED) out[o1] = acc1;
+}
+
+__global__ void smpl_instance_bwd_kernel(SmplArgs a, const float* __restrict__ mean_emb,
+                                         const float* __restrict__ red_partial, float* __restrict__ v_theta,
+                                         float* __restrict__ v_trans, float* __restrict__ v_params_partial,
+                                         float* __restrict__ v_table, float* __restrict__ v_mean_emb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.I) return;
+    const int nch = (a.V + SM_CHUNK - 1) / SM_CHUNK;
+    float vA[SM_AOUT];
+    for (int k = 0; k < SM_AOUT; ++k) {
+        float s = 0.f;
+        for (int c = 0; c < nch; ++c) s += red_partial[((int64_t)i * a.max_chunks + c) * SM_RED + k];
+        vA[k] = s;
+    }
+    for (int k = 0; k < 3; ++k) {
+        float s = 0.f;
+        for (int c = 0; c < nch; ++c) s += red_partial[((int64_t)i * a.max_chunks + c) * SM_RED + SM_AOUT + k];
+        v_trans[i * 3 + k] = s;
+    }
+    const int pc = smpl_param_count(a.d + a.g);
+    float* vp = v_params_partial + (int64_t)i * pc;
+    if (!a.visible[i]) {
+        for (int k = 0; k < SMPL_J * 4; ++k) v_theta[(int64_t)i * SMPL_J * 4 + k] = 0.f;
+        for (int k = 0; k < pc; ++k) vp[k] = 0.f;
+        for (int k = 0; k < a.g; ++k) v_mean_emb[i * a.g + k] = 0.f;
+        return;
+    }
+    int par[SMPL_J];
+    for (int j = 0; j < SMPL_J; ++j) par[j] = a.parents[j];
+    smpl_instance_bwd(a.table + (int64_t)i * a.E * a.d, a.E, a.d, a.g, mean_emb + i * a.g, a.t, a.cur_c, a.cur_f, a.H,
+                      a.theta + (int64_t)i * SMPL_J * 4, a.J + (int64_t)i * SMPL_J * 3,
+                      a.A0inv + (int64_t)i * SMPL_J * 16, par, vA, v_theta + (int64_t)i * SMPL_J * 4, vp,
+                      v_table + (int64_t)i * a.E * a.d, v_mean_emb + i * a.g);
+}
+
+__global__ void smpl_params_reduce_kernel(const float* __restrict__ partial, int I, int pc, float* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= pc) return;
+    float s = 0.f;
+    for (int i = 0; i < I; ++i) s += partial[(int64_t)i * pc + k];
+    out[k] = s;
+}
+
+__global__ void smpl_embed_bwd_kernel(const float* __restrict__ v_mean_emb, int g, int V, int64_t N,
+                                      float* __restrict__ v_emb) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N * g) return;
+    const int64_t n = e / g;
+    const int k = (int)(e - n * g);
+    v_emb[e] = v_mean_emb[(n / V) * g + k] / (float)V;
+}
+
+int fill(SmplArgs& a, const float* table, int I, int E, int d, int g, int V, float t, int cur_c, int cur_f,
+         const float* const* heads, const float* theta, const float* trans, const uint8_t* visible, const float* J,
+         const float* A0inv, const float* W, const int* parents) {
+    EMD_CHECK_ARG(I >= 1 && E >= 2 && V >= 1, "smpl: need I >= 1, E >= 2, V >= 1");
+    EMD_CHECK_ARG(d >= 1 && d <= EMD_TDIM_MAX && g >= 0 && g <= EMD_GDIM_MAX, "smpl: temporal dim <= %d, embedding dim <= %d",
+                  EMD_TDIM_MAX, EMD_GDIM_MAX);
+    a.table = table; a.I = I; a.E = E; a.d = d; a.g = g; a.V = V; a.t = t; a.cur_c = cur_c; a.cur_f = cur_f;
+    a.H.c_w = heads[0]; a.H.c_b = heads[1]; a.H.f_w = heads[2]; a.H.f_b = heads[3];
+    a.theta = theta; a.trans = trans; a.visible = visible; a.J = J; a.A0inv = A0inv; a.W = W; a.parents = parents;
+    a.max_chunks = (V + SM_CHUNK - 1) / SM_CHUNK;
+    EMD_CHECK_ARG(a.max_chunks <= 65535, "smpl: too many points per instance");
+    return EMD_OK;
+}
+
+}  // namespace
+
+extern "C" int emd_smpl_param_count(int d, int g) { return smpl_param_count(d + g); }
+extern "C" int emd_smpl_max_chunks(int V) { return (V + SM_CHUNK - 1) / SM_CHUNK; }
+extern "C" int emd_smpl_reduce_width() { return SM_RED; }
+
+// heads: HOST array of 4 DEVICE pointers {track_smpl_c.weight[24,d+g], .bias[24], track_smpl_f.weight, .bias}.
+// scratch: seg_partial [I*max_chunks*g].  Saved for backward: mean_emb [I,g], A [I,24,12].
+extern "C" int emd_smpl_deform_fwd(const float* means, const float* quats, const float* embeddings, const float* table,
+                                   const float* const* heads, const float* theta, const float* trans,
+                                   const uint8_t* visible, const float* J, const float* A0inv, const float* W,
+                                   const int* parents, int I, int V, int E, int d, int g, float t, int cur_c,
+                                   int cur_f, float* seg_partial, float* mean_emb, float* A, float* world_means,
+                                   float* world_quats, cudaStream_t stream) {
+    SmplArgs a;
+    int rc = fill(a, table, I, E, d, g, V, t, cur_c, cur_f, heads, theta, trans, visible, J, A0inv, W, parents);
+    if (rc != EMD_OK) return rc;
+    if (!emd_aligned(quats, 16) || !emd_aligned(world_quats, 16)) { emd_set_error("smpl_fwd: quats must be 16-B aligned"); return EMD_ERR_ALIGN; }
+    const int64_t N = (int64_t)I * V;
+    dim3 sg(a.max_chunks, I);
+    smpl_segmean_kernel<<<sg, SM_THREADS, 0, stream>>>(embeddings, g, V, a.max_chunks, seg_partial);
+    smpl_instance_fwd_kernel<<<(I + 31) / 32, 32, 0, stream>>>(a, seg_partial, mean_emb, A);
+    smpl_points_fwd_kernel<<<(unsigned)emd_cdiv(N, SM_THREADS), SM_THREADS, 0, stream>>>(a, A, means, quats, N, world_means, world_quats);
+    EMD_CHECK_LAUNCH("smpl_deform_fwd");
+    return EMD_OK;
+}
+
+// scratch: red_partial [I*max_chunks*reduce_width], params_partial [I*param_count]; v_table zero-filled by the caller.
+extern "C" int emd_smpl_deform_bwd(const float* means, const float* quats, const float* table,
+                                   const float* const* heads, const float* theta, const float* trans,
+                                   const uint8_t* visible, const float* J, const float* A0inv, const float* W,
+                                   const int* parents, int I, int V, int E, int d, int g, float t, int cur_c,
+                                   int cur_f, const float* mean_emb, const float* A, const float* v_world_means,
+                                   const float* v_world_quats, float* red_partial, float* params_partial,
+                                   float* v_means, float* v_quats, float* v_embeddings, float* v_table,
+                                   float* v_params, float* v_theta, float* v_trans, float* v_mean_emb,
+                                   cudaStream_t stream) {
+    SmplArgs a;
+    int rc = fill(a, table, I, E, d, g, V, t, cur_c, cur_f, heads, theta, trans, visible, J, A0inv, W, parents);
+    if (rc != EMD_OK) return rc;
+    if (!emd_aligned(quats, 16) || !emd_aligned(v_world_quats, 16) || !emd_aligned(v_quats, 16)) {
+        emd_set_error("smpl_bwd: quats tensors must be 16-B aligned");
+        return EMD_ERR_ALIGN;
+    }
+    const int64_t N = (int64_t)I * V;
+    dim3 sg(a.max_chunks, I);
+    smpl_points_bwd_kernel<<<sg, SM_THREADS, 0, stream>>>(a, A, means, quats, v_world_means, v_world_quats, v_means,
+                                                          v_quats, red_partial);
+    smpl_instance_bwd_kernel<<<(I + 31) / 32, 32, 0, stream>>>(a, mean_emb, red_partial, v_theta, v_trans,
+                                                               params_partial, v_table, v_mean_emb);
+    const int pc = smpl_param_count(d + g);
+    smpl_params_reduce_kernel<<<(pc + 127) / 128, 128, 0, stream>>>(params_partial, I, pc, v_params);
+    if (g > 0) smpl_embed_bwd_kernel<<<(unsigned)emd_cdiv(N * g, 256), 256, 0, stream>>>(v_mean_emb, g, V, N, v_embeddings);
+    EMD_CHECK_LAUNCH("smpl_deform_bwd");
+    return EMD_OK;
+}

@@ -165,3 +165,103 @@ def simple_gaussians(n: int, g: torch.Generator, width: int = 960, height: int =
     scales = torch.exp(math.log(scale) + 0.7 * torch.randn(n, 3, generator=g))
     return dict(means=means, quats=random_quats(n, g), scales=scales,
                 opacities=torch.sigmoid(1.5 * torch.randn(n, generator=g)), colors=torch.rand(n, 3, generator=g))
+
+
+# --------------------------------------------------------------------------- SMPL-shaped nodes
+SMPL_PARENTS = (-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21)
+
+# a fixed 24-joint stick figure (metres, y up in the body frame), standard SMPL joint order
+_STICK = [
+    (0.00, 0.00, 0.00), (0.07, -0.09, 0.00), (-0.07, -0.09, 0.00), (0.00, 0.11, -0.01), (0.10, -0.47, 0.00),
+    (-0.10, -0.47, 0.00), (0.00, 0.25, 0.00), (0.09, -0.87, -0.03), (-0.09, -0.87, -0.03), (0.00, 0.30, 0.02),
+    (0.11, -0.93, 0.09), (-0.11, -0.93, 0.09), (0.00, 0.52, -0.01), (0.08, 0.42, -0.01), (-0.08, 0.42, -0.01),
+    (0.00, 0.60, 0.03), (0.17, 0.44, -0.01), (-0.17, 0.44, -0.01), (0.43, 0.43, -0.03), (-0.43, 0.43, -0.03),
+    (0.68, 0.43, -0.03), (-0.68, 0.43, -0.03), (0.76, 0.42, -0.04), (-0.76, 0.42, -0.04),
+]
+
+
+def _quat_to_mat(q: Tensor) -> Tensor:
+    q = q / q.norm(dim=-1, keepdim=True)
+    w, x, y, z = q.unbind(-1)
+    return torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+                        2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                        2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], -1).reshape(q.shape[:-1] + (3, 3))
+
+
+def _rigid_chain(rot: Tensor, joints: Tensor, parents=SMPL_PARENTS) -> Tensor:
+    """Relative joint transforms [B,24,4,4] of a pose (the SMPL linear-blend-skinning chain)."""
+    B = rot.shape[0]
+    G = []
+    for j in range(24):
+        T = torch.eye(4).repeat(B, 1, 1)
+        T[:, :3, :3] = rot[:, j]
+        T[:, :3, 3] = joints[:, j] - (joints[:, parents[j]] if parents[j] >= 0 else 0.0)
+        G.append(T if parents[j] < 0 else G[parents[j]] @ T)
+    G = torch.stack(G, 1)
+    A = G.clone()
+    A[..., :3, 3] = G[..., :3, 3] - torch.einsum("bjrc,bjc->bjr", G[..., :3, :3], joints)
+    return A
+
+
+@dataclass
+class SMPLScene:
+    means: Tensor
+    quats: Tensor
+    scales: Tensor
+    opacities: Tensor
+    features_dc: Tensor
+    features_rest: Tensor  # [N,3,3] (sh_degree 1)
+    embeddings: Tensor
+    point_ids: Tensor  # [N,1]
+    weight: Tensor
+    instances_quats: Tensor  # [F,I,1,4]
+    smpl_qauts: Tensor  # [F,I,23,4]
+    instances_trans: Tensor  # [F,I,3]
+    instances_fv: Tensor  # [F,I]
+    J_canonical: Tensor  # [I,24,3]
+    A0_inv: Tensor  # [I,24,4,4]
+    W: Tensor  # [I,V,24]
+    track: Dict[str, Tensor] = field(default_factory=dict)
+
+
+def smpl_nodes(num_instances: int, g: torch.Generator, V: int = 6890, num_frames: int = 150, g_dim: int = 4,
+               t_dim: int = 32, max_emb: int = 150) -> SMPLScene:
+    I, F = num_instances, num_frames
+    J = torch.tensor(_STICK).repeat(I, 1, 1) * (0.9 + 0.2 * torch.rand(I, 1, 1, generator=g))
+    # canonical ("da") pose: small fixed joint rotations; A0_inv = inverse of its chain
+    can_q = torch.cat([torch.ones(24, 1), 0.08 * torch.randn(24, 3, generator=g)], -1)
+    A0 = _rigid_chain(_quat_to_mat(can_q)[None].repeat(I, 1, 1, 1), J)
+    A0_inv = torch.linalg.inv(A0)
+    # body points: scattered around the bones
+    seg = torch.randint(1, 24, (I, V), generator=g)
+    par = torch.tensor(SMPL_PARENTS)[seg]
+    u = torch.rand(I, V, 1, generator=g)
+    Jb = J[torch.arange(I)[:, None], seg]
+    Jp = J[torch.arange(I)[:, None], par]
+    pts = Jp + u * (Jb - Jp) + 0.04 * torch.randn(I, V, 3, generator=g)
+    dist = (pts[:, :, None, :] - J[:, None, :, :]).norm(dim=-1)  # [I,V,24]
+    top = torch.topk(-dist, 4, dim=-1)
+    W = torch.zeros(I, V, 24).scatter(-1, top.indices, torch.softmax(8.0 * top.values, dim=-1))
+    n = I * V
+    dc = (torch.rand(n, 3, generator=g) - 0.5) / C0
+    rest = 0.05 * torch.randn(n, 3, 3, generator=g)
+    t = torch.linspace(0, 1, F)
+    x0 = 8 + 30 * torch.rand(I, generator=g)
+    y0 = 6 * torch.rand(I, generator=g) - 3
+    trans = torch.stack([x0[None, :] + 1.2 * t[:, None] * 5, y0[None, :].expand(F, I), torch.full((F, I), 0.95)], -1)
+    # body frame is y-up; rotate to world z-up with a global orientation about x by +90 deg, plus a walking yaw
+    base = torch.tensor([math.cos(math.pi / 4), math.sin(math.pi / 4), 0.0, 0.0])
+    iq = base.expand(F, I, 1, 4).clone() + 0.03 * torch.randn(F, I, 1, 4, generator=g)
+    sq = torch.cat([torch.ones(F, I, 23, 1), 0.15 * torch.randn(F, I, 23, 3, generator=g)], -1)
+    fv = torch.rand(F, I, generator=g) < 0.8
+    d_in = t_dim + g_dim
+    track = {"smpl_c_w": 0.05 * torch.randn(24, d_in, generator=g), "smpl_c_b": 0.05 * torch.randn(24, generator=g),
+             "smpl_f_w": 0.05 * torch.randn(24, d_in, generator=g), "smpl_f_b": 0.05 * torch.randn(24, generator=g)}
+    return SMPLScene(
+        means=pts.reshape(n, 3), quats=random_quats(n, g), scales=math.log(0.02) + 0.3 * torch.randn(n, 3, generator=g),
+        opacities=2.0 * torch.randn(n, 1, generator=g), features_dc=dc, features_rest=rest,
+        embeddings=0.1 * torch.randn(n, g_dim, generator=g),
+        point_ids=torch.arange(I).repeat_interleave(V)[:, None].contiguous(),
+        weight=torch.randn(I, max_emb, t_dim, generator=g) * (0.01 / math.sqrt(t_dim)),
+        instances_quats=iq, smpl_qauts=sq, instances_trans=trans, instances_fv=fv, J_canonical=J, A0_inv=A0_inv, W=W,
+        track=track)
