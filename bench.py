@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd megapixels/s of one EMD-OmniRe training step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          # our arm (one rank per GPU under torchrun for N > 1)
+    python bench.py --impl reference --gpus N ...          # the reference's algorithm on the host CPU (oracle)
+
+Workload (BASELINE.json configs[1]): synthetic Waymo-shaped street scene, 1.30 M background +
+30 x 5 000 rigid + 8 x 6 890 SMPL Gaussians (~1.505 M), 3 cameras 640x960 of one timestep per
+step.  A step = EMD deformation (rigid + SMPL) -> activations + SH colour per camera ->
+projection -> tile intersection + radix sort + tile ranges -> rasterization (RGB + expected
+depth + alpha), then the backward of all of it for seeded per-pixel cotangents.  With N GPUs
+every rank renders its own timestep (weak scaling) and the parameter gradients are
+all-reduced over NCCL inside the timed region.
+
+Prints ONE JSON line (see DESIGN.md section 7 for every field).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+W_IMG, H_IMG = 960, 640
+YAWS = (0.0, 45.0, -45.0)
+STEP0 = 20000  # training step fed to the c2f / SH-degree schedules (degree 3, full temporal table)
+METRIC = "fwd+bwd megapixels/s per train step"
+UNIT = "Mpix/s"
+
+# algorithmic work per unit
+FLOP_PER_PAIR_FWD = 42.0    # 21 FP32-pipe instructions, FMA counted as 2
+FLOP_PER_PAIR_BWD = 120.0   # 60 FP32-pipe instructions per blended pair
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal: MEASURED_PEAKS.json has no fp32 figure
+
+
+def workload_cfg(args):
+    return {
+        "workload": "OmniRe+EMD synthetic Waymo-shaped street scene, one training step (BASELINE.json configs[1])",
+        "gaussians": args.n_bg + args.rigid_instances * args.pts_per_rigid + args.smpl_instances * 6890,
+        "background": args.n_bg, "rigid": f"{args.rigid_instances}x{args.pts_per_rigid}",
+        "smpl": f"{args.smpl_instances}x6890", "cameras": len(YAWS), "height": H_IMG, "width": W_IMG,
+        "render_mode": "RGB+ED", "frames": 150, "train_step": STEP0, "seed": 0,
+        "parallelism": "view-sharded data parallel (one timestep per rank), NCCL all-reduce of parameter grads",
+        "l2_policy": "working set >> L2: 379 MB of parameters + 0.5 GB of per-step intermediates vs 126 MB L2; "
+                     "frame and cotangents change every step",
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, pw = [], [], set(), []
+        for ts, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed region"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+def build_inputs(args, rank, world):
+    """Scene (replicated, seed 0) + this rank's host-side per-step inputs in pinned memory."""
+    from emd_b200 import pipeline as P, scenes
+    bg, rigid, smpl = P.make_street_scene(args.n_bg, args.rigid_instances, args.pts_per_rigid, args.smpl_instances,
+                                          seed=0)
+    viewmats, Ks, c2w = scenes.cameras(YAWS, W_IMG, H_IMG)
+    C = len(YAWS)
+    g = torch.Generator().manual_seed(1234 + rank)
+    n_sets = 4  # cotangent sets cycled through so consecutive steps never reuse one
+    host = {
+        "c2w": c2w.pin_memory(), "viewmats": viewmats.pin_memory(), "Ks": Ks.pin_memory(),
+        "v_rgb": [(torch.randn(C, H_IMG, W_IMG, 3, generator=g) / (H_IMG * W_IMG)).pin_memory() for _ in range(n_sets)],
+        "v_depth": [(0.02 * torch.randn(C, H_IMG, W_IMG, 1, generator=g) / (H_IMG * W_IMG)).pin_memory() for _ in range(n_sets)],
+        "v_alpha": [(torch.randn(C, H_IMG, W_IMG, 1, generator=g) / (H_IMG * W_IMG)).pin_memory() for _ in range(n_sets)],
+    }
+    return (bg, rigid, smpl), host
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    from emd_b200 import _C, pipeline as P
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _C.check(_C.lib().emd_device_check(), "emd_device_check")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    (bg, rigid, smpl), host = build_inputs(args, rank, world)
+    scene = P.StreetScene(bg, rigid, smpl, dev)
+    params = scene.parameters()
+    C = len(YAWS)
+    cam_centers = host["c2w"][:, :3, 3].tolist()
+    n_frames = 150
+    n_sets = len(host["v_rgb"])
+
+    # device-resident copies for the `value` leg (inputs already in HBM)
+    dev_in = {k: (v.to(dev) if isinstance(v, torch.Tensor) else [x.to(dev) for x in v]) for k, v in host.items()}
+    loss_host = torch.zeros(1).pin_memory()
+    stats = {}
+
+    def step(i, e2e: bool):
+        frame = (7 + 13 * (i * world + rank)) % n_frames
+        s = i % n_sets
+        if e2e:  # host -> device copy of this step's inputs from pinned memory, inside the timed region
+            c2w = host["c2w"].to(dev, non_blocking=True)
+            Ks = host["Ks"].to(dev, non_blocking=True)
+            vm = host["viewmats"].to(dev, non_blocking=True)
+            v_rgb = host["v_rgb"][s].to(dev, non_blocking=True)
+            v_d = host["v_depth"][s].to(dev, non_blocking=True)
+            v_a = host["v_alpha"][s].to(dev, non_blocking=True)
+        else:
+            c2w, Ks, vm = dev_in["c2w"], dev_in["Ks"], dev_in["viewmats"]
+            v_rgb, v_d, v_a = dev_in["v_rgb"][s], dev_in["v_depth"][s], dev_in["v_alpha"][s]
+        for p in params:
+            p.grad = None
+        rgb, depth, alpha, info = scene.render(c2w, Ks, W_IMG, H_IMG, frame, STEP0, viewmats=vm, cam_centers=cam_centers)
+        loss = (rgb * v_rgb).sum() + (depth * v_d).sum() + (alpha * v_a).sum()
+        loss.backward()
+        if world > 1:
+            works = [dist.all_reduce(p.grad, async_op=True) for p in params if p.grad is not None]
+            for w in works:
+                w.wait()
+        if e2e:  # device -> host read of the step's result
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        stats["n_isects"] = info["isect_ids"].numel()
+        stats["info"] = info
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(k_steps, e2e, first_index):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _C.launch_count()
+        t0 = time.perf_counter()
+        a.record()
+        for i in range(k_steps):
+            step(first_index + i, e2e)
+        b.record()
+        barrier()
+        t1 = time.perf_counter()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, _C.launch_count() - l0, t0, t1
+
+    for i in range(args.warmup):
+        step(i, False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ms_dev, launches, t0, t1 = timed(args.steps, False, args.warmup)
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    step(0, True)  # warm the pinned-copy path
+    ms_e2e, _, _, _ = timed(args.steps, True, args.warmup + args.steps)
+
+    # per-kernel durations over K more steps, each library kernel bracketed by CUDA events on its stream
+    with _C.profile() as prof:
+        barrier()
+        for i in range(args.steps):
+            step(args.warmup + 2 * args.steps + i, False)
+        barrier()
+    kern = prof.result()
+
+    pix = C * H_IMG * W_IMG
+    ms_step = ms_dev / args.steps
+    value = world * pix / (ms_step * 1e-3) / 1e6
+    e2e_value = world * pix / (ms_e2e / args.steps * 1e-3) / 1e6
+    h2d = sum(host[k].numel() * 4 for k in ("c2w", "Ks", "viewmats")) + sum(host[k][0].numel() * 4 for k in ("v_rgb", "v_depth", "v_alpha"))
+
+    # dominant kernel: raster backward.  Algorithmic work = blended-or-tested pixel-Gaussian pairs.
+    info = stats["info"]
+    with torch.no_grad():
+        offs = info["isect_offsets"]  # [C,th,tw]
+        last = info["last_ids"].to(torch.int64)  # [C,H,W]
+        th, tw = offs.shape[1:]
+        ty = (torch.arange(H_IMG, device=dev) // 16)[:, None].expand(H_IMG, W_IMG)
+        tx = (torch.arange(W_IMG, device=dev) // 16)[None, :].expand(H_IMG, W_IMG)
+        start = offs[:, ty, tx].to(torch.int64)
+        pairs_bwd = int(torch.clamp(last - start + 1, min=0).sum().item())
+    k_steps = args.steps
+    rb_ms = kern.get("raster_bwd", (0.0, 1))[0] / max(1, kern.get("raster_bwd", (0.0, 1))[1])
+    rf_ms = kern.get("raster_fwd", (0.0, 1))[0] / max(1, kern.get("raster_fwd", (0.0, 1))[1])
+    achieved = pairs_bwd * FLOP_PER_PAIR_BWD / (rb_ms * 1e-3) / 1e12 if rb_ms > 0 else 0.0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    P_is = stats["n_isects"]
+    N = scene.num_gaussians
+    stage_bytes = {  # algorithmic bytes per launch
+        "projection_fwd": 40.0 * N + 32.0 * C * N, "projection_bwd": 40.0 * N + C * N * (4 + 24) + 40.0 * N,
+        "sort_hist": 8.0 * P_is, "sort_scatter": 24.0 * P_is, "isect_emit": 12.0 * P_is + 24.0 * C * N,
+        "activate_fwd": None, "raster_gather": 49.0 * P_is + 36.0 * C * N,
+    }
+    per_kernel = {}
+    step_kernel_ms = sum(v[0] for v in kern.values()) / k_steps
+    for name, (ms_total, cnt) in sorted(kern.items(), key=lambda kv: -kv[1][0]):
+        ent = {"ms_per_step": round(ms_total / k_steps, 4), "launches_per_step": cnt / k_steps,
+               "share": round(ms_total / k_steps / step_kernel_ms, 4)}
+        b = stage_bytes.get(name)
+        if b:
+            gbs = b / (ms_total / cnt * 1e-3) / 1e9
+            ent.update({"bound": "hbm", "achieved_gbs": round(gbs, 1), "frac_of_measured_hbm": round(gbs / hbm_peak, 4)})
+        per_kernel[name] = ent
+    roofline = {
+        "kernel": "raster_bwd", "bound": "fp32", "achieved": round(achieved, 3), "peak": round(FP32_PEAK_TFLOPS, 2),
+        "unit": "TFLOP/s", "frac": round(achieved / FP32_PEAK_TFLOPS, 4), "traffic": None,
+        "peak_source": "nominal 148 SM x 128 FMA lanes x 1.965 GHz (MEASURED_PEAKS.json holds HBM and bf16 only)",
+        "algorithmic": f"{pairs_bwd} pixel-Gaussian pairs x {FLOP_PER_PAIR_BWD:.0f} flop per launch (3 cameras)",
+        "avg_launch_ms": round(rb_ms, 4), "pairs_per_launch": pairs_bwd,
+        "raster_fwd": {"avg_launch_ms": round(rf_ms, 4)},
+        "hbm_peak_gbs_measured": hbm_peak, "per_kernel": per_kernel,
+    }
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_cfg(args),
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e2e / args.steps, 4),
+                "note": "per step: H2D of camera matrices + per-pixel RGB/depth/alpha cotangents from pinned memory, "
+                        "D2H of the loss; Gaussian parameters are model state resident in HBM"},
+        "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+        "n_isects_per_step": P_is, "fwd_ms_per_frame": None, "clocks": clocks, "roofline": roofline,
+    }
+    if rank == 0:
+        # forward-only render time (the second headline metric: ms per frame = per camera image)
+        with torch.no_grad():
+            for _ in range(3):
+                scene.render(dev_in["c2w"], dev_in["Ks"], W_IMG, H_IMG, 11, STEP0, viewmats=dev_in["viewmats"], cam_centers=cam_centers)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(args.steps):
+                scene.render(dev_in["c2w"], dev_in["Ks"], W_IMG, H_IMG, (11 + 7 * i) % n_frames, STEP0, viewmats=dev_in["viewmats"], cam_centers=cam_centers)
+            b.record()
+            torch.cuda.synchronize()
+            line["fwd_ms_per_frame"] = round(a.elapsed_time(b) / args.steps / C, 4)
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, steps=1, warmup=0)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_baseline(args, steps=1, warmup=0):
+    """The reference's algorithm (pure-PyTorch CPU oracle) on a bounded sample of the same workload:
+    same scene, camera 0, the full per-Gaussian front end (EMD, SH, projection, keys, sort) and the
+    compositing + backward of a band of tile rows; value = band pixels / time."""
+    from emd_b200 import pipeline as P, scenes
+    from oracle import pipeline_ref as PR
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    bg, rigid, smpl = P.make_street_scene(args.n_bg, args.rigid_instances, args.pts_per_rigid, args.smpl_instances, seed=0)
+    _, Ks, c2w = scenes.cameras(YAWS, W_IMG, H_IMG)
+    L = PR.leaves(bg, rigid, smpl)
+    r0 = max(0, min(40 - args.cpu_tile_rows, 20 - args.cpu_tile_rows // 2))
+    rows = (r0, r0 + args.cpu_tile_rows)
+    g = torch.Generator().manual_seed(99)
+    band_pix = (rows[1] - rows[0]) * 16 * W_IMG
+    v_rgb = torch.randn(H_IMG, W_IMG, 3, generator=g) / band_pix
+    v_a = torch.randn(H_IMG, W_IMG, 1, generator=g) / band_pix
+    times = []
+    for i in range(warmup + steps):
+        for t in L.values():
+            t.grad = None
+        t0 = time.perf_counter()
+        rgb, depth, alpha, info = PR.render(L, rigid, smpl, c2w[0], Ks[0], W_IMG, H_IMG, (7 + 13 * i) % 150, STEP0, tile_rows=rows)
+        ((rgb * v_rgb).sum() + 0.02 * (depth * v_a).sum() + (alpha * v_a).sum()).backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return {"value": round(band_pix / sec / 1e6, 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "seconds_per_sample": round(sec, 2),
+            "sample": f"same scene ({L['bg.means'].shape[0]} bg + rigid + SMPL Gaussians), camera 0 only: full EMD/SH/"
+                      f"projection/keys/sort front end on all Gaussians + compositing fwd+bwd of tile rows "
+                      f"{rows[0]}..{rows[1] - 1} of 40 ({band_pix} pixels); oracle = pure-PyTorch CPU restatement "
+                      f"(reference's gsplat CUDA source is an absent third-party dependency)"}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own algorithm for this path on the host cores (the oracle port;
+    the rasterizer's real source, gsplat, is not in the reference tree and cannot be installed offline)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_all = time.perf_counter()
+    cb = cpu_baseline(args, steps=max(1, min(args.steps, 3)), warmup=1 if args.warmup > 0 else 0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": max(1, min(args.steps, 3)),
+        "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": cb["seconds_per_sample"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_cfg(args), "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": round(time.perf_counter() - t_all, 1),
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-bg", dest="n_bg", type=int, default=1_300_000)
+    ap.add_argument("--rigid-instances", type=int, default=30)
+    ap.add_argument("--pts-per-rigid", type=int, default=5000)
+    ap.add_argument("--smpl-instances", type=int, default=8)
+    ap.add_argument("--cpu-tile-rows", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,11 @@ _SIGS = {
     "emd_last_error_string": (ctypes.c_char_p, []),
     "emd_abi_version": (c_int, []),
     "emd_device_check": (c_int, []),
+    "emd_launch_count": (ctypes.c_longlong, []),
+    "emd_kernel_id_count": (c_int, []),
+    "emd_kernel_name": (ctypes.c_char_p, [c_int]),
+    "emd_profile_enable": (None, [c_int]),
+    "emd_profile_collect": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),
     "emd_projection_fwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int, c_int, c_float, c_float, c_float, c_float,
                                    c_int, c_int, P, P, P, P, P, P, P]),
     "emd_projection_bwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int, c_int, c_float, c_float, c_float, c_float,
@@ -38,8 +43,8 @@ _SIGS = {
     "emd_rasterize_bwd_workspace_bytes": (c_size_t, [c_int64]),
     "emd_sh_fwd": (c_int, [c_int, P, P, c_int64, c_int, P, P]),
     "emd_sh_bwd": (c_int, [c_int, P, c_int64, c_int, P, P, P]),
-    "emd_activate_fwd": (c_int, [P] * 8 + [ctypes.POINTER(c_float), c_int64, c_int, c_int] + [P] * 5 + [P]),
-    "emd_activate_bwd": (c_int, [P] * 8 + [ctypes.POINTER(c_float), c_int64, c_int, c_int] + [P] * 11 + [P]),
+    "emd_activate_fwd": (c_int, [P] * 8 + [ctypes.POINTER(c_float), c_int, c_int64, c_int, c_int] + [P] * 5 + [P]),
+    "emd_activate_bwd": (c_int, [P] * 8 + [ctypes.POINTER(c_float), c_int, c_int64, c_int, c_int] + [P] * 11 + [P]),
     "emd_rigid_chunk_size": (c_int, []),
     "emd_rigid_param_count": (c_int, [c_int, c_int]),
     "emd_rigid_deform_fwd": (c_int, [P] * 11 + [c_int64, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int]
@@ -113,3 +118,36 @@ def ptr(t: Optional[torch.Tensor], dtype=None, name: str = "tensor") -> Optional
 
 def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    """Kernels launched by the library so far in this process."""
+    return int(lib().emd_launch_count())
+
+
+class profile:
+    """``with _C.profile() as prof: ...`` brackets every library kernel with CUDA events on
+    its own stream; ``prof.result()`` -> {kernel: (total_ms, launches)}."""
+
+    def __enter__(self):
+        L = lib()
+        n = L.emd_kernel_id_count()
+        self._ms = (ctypes.c_double * n)()
+        self._cnt = (ctypes.c_longlong * n)()
+        L.emd_profile_collect(self._ms, self._cnt)  # drop stale records
+        for i in range(n):
+            self._ms[i] = 0.0
+            self._cnt[i] = 0
+        L.emd_profile_enable(1)
+        return self
+
+    def __exit__(self, *exc):
+        L = lib()
+        L.emd_profile_enable(0)
+        L.emd_profile_collect(self._ms, self._cnt)
+        return False
+
+    def result(self):
+        L = lib()
+        return {L.emd_kernel_name(i).decode(): (float(self._ms[i]), int(self._cnt[i]))
+                for i in range(L.emd_kernel_id_count()) if self._cnt[i] > 0}

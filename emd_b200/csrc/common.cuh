@@ -35,6 +35,23 @@ static inline bool emd_aligned(const void* p, size_t a) { return (reinterpret_ca
 
 static inline int64_t emd_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// ---- launch accounting / optional per-kernel CUDA-event timing (api.cu) ----------------------
+enum EmdKernelId {
+    EK_PROJ_FWD = 0, EK_PROJ_BWD, EK_SCAN, EK_ISECT_EMIT, EK_SORT_HIST, EK_SORT_SCATTER, EK_ISECT_OFFSETS,
+    EK_RASTER_PACK, EK_RASTER_FWD, EK_RASTER_BWD, EK_RASTER_GATHER, EK_SH_FWD, EK_SH_BWD, EK_ACT_FWD, EK_ACT_BWD,
+    EK_RIGID_FWD, EK_RIGID_BWD, EK_SMPL_FWD, EK_SMPL_BWD, EK_MLP_FWD, EK_MLP_BWD, EK_DG_PREP_FWD, EK_DG_PREP_BWD,
+    EK_MISC, EK_COUNT
+};
+void emd_prof_begin(int id, cudaStream_t stream);
+void emd_prof_end(int id, cudaStream_t stream);
+// every kernel launch of the library goes through this: counts it, and times it when profiling is on
+#define EMD_LAUNCH(ID, STREAM, ...)  \
+    do {                             \
+        emd_prof_begin(ID, STREAM);  \
+        __VA_ARGS__;                 \
+        emd_prof_end(ID, STREAM);    \
+    } while (0)
+
 constexpr int EMD_TILE = 16;          // raster tile edge (pixels)
 constexpr int EMD_NUM_SMS = 148;      // B200
 

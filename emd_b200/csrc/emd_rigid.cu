@@ -239,11 +239,11 @@ extern "C" int emd_rigid_deform_fwd(const float* means, const float* quats, cons
     if (rc != EMD_OK) return rc;
     if (!emd_aligned(quats, 16) || !emd_aligned(world_quats, 16)) { emd_set_error("rigid_fwd: quats must be 16-B aligned"); return EMD_ERR_ALIGN; }
     dim3 sg(max_chunks, I);
-    rigid_segmean_kernel<<<sg, RG_THREADS, 0, stream>>>(embeddings, g, order, seg_start, max_chunks, seg_partial);
-    rigid_instance_fwd_kernel<<<(I + 63) / 64, 64, 0, stream>>>(a, seg_partial, mean_emb, inst_out);
+    EMD_LAUNCH(EK_RIGID_FWD, stream, rigid_segmean_kernel<<<sg, RG_THREADS, 0, stream>>>(embeddings, g, order, seg_start, max_chunks, seg_partial));
+    EMD_LAUNCH(EK_RIGID_FWD, stream, rigid_instance_fwd_kernel<<<(I + 63) / 64, 64, 0, stream>>>(a, seg_partial, mean_emb, inst_out));
     if (N > 0)
-        rigid_points_fwd_kernel<<<(unsigned)emd_cdiv(N, RG_THREADS), RG_THREADS, 0, stream>>>(
-            means, quats, point_ids, inst_out, N, world_means, world_quats);
+        EMD_LAUNCH(EK_RIGID_FWD, stream, rigid_points_fwd_kernel<<<(unsigned)emd_cdiv(N, RG_THREADS), RG_THREADS, 0, stream>>>(
+            means, quats, point_ids, inst_out, N, world_means, world_quats));
     EMD_CHECK_LAUNCH("rigid_deform_fwd");
     return EMD_OK;
 }
@@ -266,14 +266,14 @@ extern "C" int emd_rigid_deform_bwd(const float* means, const float* quats, cons
         return EMD_ERR_ALIGN;
     }
     dim3 sg(max_chunks, I);
-    rigid_points_bwd_kernel<<<sg, RG_THREADS, 0, stream>>>(means, quats, order, seg_start, inst_out, max_chunks,
-                                                           v_world_means, v_world_quats, v_means, v_quats, pose_partial);
-    rigid_instance_bwd_kernel<<<(I + 63) / 64, 64, 0, stream>>>(a, mean_emb, pose_partial, v_pose_q_means,
-                                                                v_pose_q_quats, v_pose_t, params_partial, v_table, v_mean_emb);
+    EMD_LAUNCH(EK_RIGID_BWD, stream, rigid_points_bwd_kernel<<<sg, RG_THREADS, 0, stream>>>(means, quats, order, seg_start, inst_out, max_chunks,
+                                                           v_world_means, v_world_quats, v_means, v_quats, pose_partial));
+    EMD_LAUNCH(EK_RIGID_BWD, stream, rigid_instance_bwd_kernel<<<(I + 63) / 64, 64, 0, stream>>>(a, mean_emb, pose_partial, v_pose_q_means,
+                                                                v_pose_q_quats, v_pose_t, params_partial, v_table, v_mean_emb));
     const int pc = rigid_param_count(d + g);
-    params_reduce_kernel<<<(pc + 127) / 128, 128, 0, stream>>>(params_partial, I, pc, v_params);
+    EMD_LAUNCH(EK_RIGID_BWD, stream, params_reduce_kernel<<<(pc + 127) / 128, 128, 0, stream>>>(params_partial, I, pc, v_params));
     if (N > 0 && g > 0)
-        embed_bwd_kernel<<<(unsigned)emd_cdiv(N * g, 256), 256, 0, stream>>>(v_mean_emb, point_ids, seg_start, g, N, v_embeddings);
+        EMD_LAUNCH(EK_RIGID_BWD, stream, embed_bwd_kernel<<<(unsigned)emd_cdiv(N * g, 256), 256, 0, stream>>>(v_mean_emb, point_ids, seg_start, g, N, v_embeddings));
     EMD_CHECK_LAUNCH("rigid_deform_bwd");
     return EMD_OK;
 }

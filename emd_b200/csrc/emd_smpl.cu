@@ -305,9 +305,9 @@ extern "C" int emd_smpl_deform_fwd(const float* means, const float* quats, const
     if (!emd_aligned(quats, 16) || !emd_aligned(world_quats, 16)) { emd_set_error("smpl_fwd: quats must be 16-B aligned"); return EMD_ERR_ALIGN; }
     const int64_t N = (int64_t)I * V;
     dim3 sg(a.max_chunks, I);
-    smpl_segmean_kernel<<<sg, SM_THREADS, 0, stream>>>(embeddings, g, V, a.max_chunks, seg_partial);
-    smpl_instance_fwd_kernel<<<(I + 31) / 32, 32, 0, stream>>>(a, seg_partial, mean_emb, A);
-    smpl_points_fwd_kernel<<<(unsigned)emd_cdiv(N, SM_THREADS), SM_THREADS, 0, stream>>>(a, A, means, quats, N, world_means, world_quats);
+    EMD_LAUNCH(EK_SMPL_FWD, stream, smpl_segmean_kernel<<<sg, SM_THREADS, 0, stream>>>(embeddings, g, V, a.max_chunks, seg_partial));
+    EMD_LAUNCH(EK_SMPL_FWD, stream, smpl_instance_fwd_kernel<<<(I + 31) / 32, 32, 0, stream>>>(a, seg_partial, mean_emb, A));
+    EMD_LAUNCH(EK_SMPL_FWD, stream, smpl_points_fwd_kernel<<<(unsigned)emd_cdiv(N, SM_THREADS), SM_THREADS, 0, stream>>>(a, A, means, quats, N, world_means, world_quats));
     EMD_CHECK_LAUNCH("smpl_deform_fwd");
     return EMD_OK;
 }
@@ -331,12 +331,12 @@ extern "C" int emd_smpl_deform_bwd(const float* means, const float* quats, const
     }
     const int64_t N = (int64_t)I * V;
     dim3 sg(a.max_chunks, I);
-    smpl_points_bwd_kernel<<<sg, SM_THREADS, 0, stream>>>(a, A, means, quats, v_world_means, v_world_quats, v_means,
-                                                          v_quats, red_partial);
-    smpl_instance_bwd_kernel<<<(I + 31) / 32, 32, 0, stream>>>(a, mean_emb, red_partial, v_theta, v_trans,
-                                                               params_partial, v_table, v_mean_emb);
+    EMD_LAUNCH(EK_SMPL_BWD, stream, smpl_points_bwd_kernel<<<sg, SM_THREADS, 0, stream>>>(a, A, means, quats, v_world_means, v_world_quats, v_means,
+                                                          v_quats, red_partial));
+    EMD_LAUNCH(EK_SMPL_BWD, stream, smpl_instance_bwd_kernel<<<(I + 31) / 32, 32, 0, stream>>>(a, mean_emb, red_partial, v_theta, v_trans,
+                                                               params_partial, v_table, v_mean_emb));
     const int pc = smpl_param_count(d + g);
-    smpl_params_reduce_kernel<<<(pc + 127) / 128, 128, 0, stream>>>(params_partial, I, pc, v_params);
+    EMD_LAUNCH(EK_SMPL_BWD, stream, smpl_params_reduce_kernel<<<(pc + 127) / 128, 128, 0, stream>>>(params_partial, I, pc, v_params));
     if (g > 0) smpl_embed_bwd_kernel<<<(unsigned)emd_cdiv(N * g, 256), 256, 0, stream>>>(v_mean_emb, g, V, N, v_embeddings);
     EMD_CHECK_LAUNCH("smpl_deform_bwd");
     return EMD_OK;

@@ -114,9 +114,9 @@ int scan_impl(const TIn* in, TOut* out, int64_t n, TOut* total_out, void* worksp
         if (total_out) cudaMemsetAsync(total_out, 0, sizeof(TOut), stream);
         return EMD_OK;
     }
-    scan_reduce_kernel<TIn, TOut><<<(unsigned)nb, SCAN_THREADS, 0, stream>>>(in, n, sums);
-    scan_spine_kernel<TOut><<<1, SCAN_THREADS, 0, stream>>>(sums, nb, total_out);
-    scan_down_kernel<TIn, TOut, INCLUSIVE><<<(unsigned)nb, SCAN_THREADS, 0, stream>>>(in, n, sums, out);
+    EMD_LAUNCH(EK_SCAN, stream, scan_reduce_kernel<TIn, TOut><<<(unsigned)nb, SCAN_THREADS, 0, stream>>>(in, n, sums));
+    EMD_LAUNCH(EK_SCAN, stream, scan_spine_kernel<TOut><<<1, SCAN_THREADS, 0, stream>>>(sums, nb, total_out));
+    EMD_LAUNCH(EK_SCAN, stream, scan_down_kernel<TIn, TOut, INCLUSIVE><<<(unsigned)nb, SCAN_THREADS, 0, stream>>>(in, n, sums, out));
     EMD_CHECK_LAUNCH("scan");
     return EMD_OK;
 }
@@ -200,8 +200,8 @@ extern "C" int emd_isect_emit(const float* means2d, const int32_t* radii, const 
     EMD_CHECK_ARG(tile_n_bits >= 1 && tile_n_bits < 31, "isect_emit: bad tile_n_bits %d", tile_n_bits);
     const int64_t CN = C * N;
     if (CN == 0) return EMD_OK;
-    isect_emit_kernel<<<(unsigned)emd_cdiv(CN, EMIT_THREADS), EMIT_THREADS, 0, stream>>>(
-        means2d, radii, depths, cum_tiles, N, CN, tile_w, tile_h, tile_n_bits, isect_ids, flatten_ids);
+    EMD_LAUNCH(EK_ISECT_EMIT, stream, isect_emit_kernel<<<(unsigned)emd_cdiv(CN, EMIT_THREADS), EMIT_THREADS, 0, stream>>>(
+        means2d, radii, depths, cum_tiles, N, CN, tile_w, tile_h, tile_n_bits, isect_ids, flatten_ids));
     EMD_CHECK_LAUNCH("isect_emit");
     return EMD_OK;
 }
@@ -212,8 +212,8 @@ extern "C" int emd_isect_offsets(const int64_t* sorted_ids, int64_t P, int64_t C
     const int64_t n_cam_tiles = C * n_tiles;
     EMD_CHECK_ARG(P >= 0 && n_cam_tiles > 0, "isect_offsets: bad sizes");
     const int64_t threads = P > 0 ? P : n_cam_tiles;
-    isect_offsets_kernel<<<(unsigned)emd_cdiv(threads, 256), 256, 0, stream>>>(sorted_ids, P, n_cam_tiles, n_tiles,
-                                                                                tile_n_bits, offsets);
+    EMD_LAUNCH(EK_ISECT_OFFSETS, stream, isect_offsets_kernel<<<(unsigned)emd_cdiv(threads, 256), 256, 0, stream>>>(sorted_ids, P, n_cam_tiles, n_tiles,
+                                                                                tile_n_bits, offsets));
     EMD_CHECK_LAUNCH("isect_offsets");
     return EMD_OK;
 }

@@ -172,9 +172,9 @@ extern "C" int emd_projection_fwd(const float* means, const float* quats, const 
         return EMD_ERR_ALIGN;
     }
     const int64_t blocks = emd_cdiv(N, PROJ_THREADS);
-    projection_fwd_kernel<<<(unsigned)blocks, PROJ_THREADS, 0, stream>>>(
+    EMD_LAUNCH(EK_PROJ_FWD, stream, projection_fwd_kernel<<<(unsigned)blocks, PROJ_THREADS, 0, stream>>>(
         means, quats, scales, viewmats, Ks, N, (int)C, width, height, eps2d, near_plane, far_plane, radius_clip,
-        tile_w, tile_h, radii, means2d, depths, conics, comps, tiles_per_gauss);
+        tile_w, tile_h, radii, means2d, depths, conics, comps, tiles_per_gauss));
     EMD_CHECK_LAUNCH("projection_fwd");
     return EMD_OK;
 }
@@ -191,9 +191,9 @@ extern "C" int emd_projection_bwd(const float* means, const float* quats, const 
         return EMD_ERR_ALIGN;
     }
     const int64_t blocks = emd_cdiv(N, PROJ_THREADS);
-    projection_bwd_kernel<<<(unsigned)blocks, PROJ_THREADS, 0, stream>>>(
+    EMD_LAUNCH(EK_PROJ_BWD, stream, projection_bwd_kernel<<<(unsigned)blocks, PROJ_THREADS, 0, stream>>>(
         means, quats, scales, viewmats, Ks, N, (int)C, width, height, eps2d, near_plane, far_plane, radius_clip,
-        radii, v_means2d, v_depths, v_conics, v_means, v_quats, v_scales);
+        radii, v_means2d, v_depths, v_conics, v_means, v_quats, v_scales));
     EMD_CHECK_LAUNCH("projection_bwd");
     return EMD_OK;
 }

@@ -131,10 +131,10 @@ extern "C" int emd_radix_sort_pairs(uint64_t* keys0, uint32_t* vals0, uint64_t* 
     for (int shift = begin_bit; shift < end_bit; shift += 8) {
         const int bits = end_bit - shift < 8 ? end_bit - shift : 8;
         const uint32_t mask = (1u << bits) - 1u;
-        rs_hist_kernel<<<(unsigned)nb, RS_THREADS, 0, stream>>>(kin, n, shift, mask, table, nb);
+        EMD_LAUNCH(EK_SORT_HIST, stream, rs_hist_kernel<<<(unsigned)nb, RS_THREADS, 0, stream>>>(kin, n, shift, mask, table, nb));
         int rc = emd_exclusive_scan_u32(table, table, nb * RS_BINS, scan_ws, scan_ws_bytes, stream);
         if (rc != EMD_OK) return rc;
-        rs_scatter_kernel<<<(unsigned)nb, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, n, shift, mask, table, nb);
+        EMD_LAUNCH(EK_SORT_SCATTER, stream, rs_scatter_kernel<<<(unsigned)nb, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, n, shift, mask, table, nb));
         uint64_t* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
         cur ^= 1;

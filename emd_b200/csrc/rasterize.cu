@@ -356,9 +356,9 @@ extern "C" int emd_raster_pack(const float* means2d, const float* conics, const 
     }
     const int64_t CN = C * N;
     if (CN == 0) return EMD_OK;
-    raster_pack_kernel<<<(unsigned)emd_cdiv(CN, 256), 256, 0, stream>>>(
+    EMD_LAUNCH(EK_RASTER_PACK, stream, raster_pack_kernel<<<(unsigned)emd_cdiv(CN, 256), 256, 0, stream>>>(
         means2d, conics, opacities, opac_per_cam, colors, colors_per_cam, d_color, depths, with_depth, radii, N, CN,
-        reinterpret_cast<float4*>(recs));
+        reinterpret_cast<float4*>(recs)));
     EMD_CHECK_LAUNCH("raster_pack");
     return EMD_OK;
 }
@@ -376,9 +376,9 @@ extern "C" int emd_rasterize_fwd(const float* recs, const int32_t* tile_offsets,
         return EMD_ERR_ALIGN;
     }
     dim3 grid(tile_w, tile_h, (unsigned)C), block(EMD_TILE, EMD_TILE, 1);
-    raster_fwd_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, P,
+    EMD_LAUNCH(EK_RASTER_FWD, stream, raster_fwd_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, P,
                                                   (int)C, width, height, tile_w, tile_h, channels, ed_mode,
-                                                  backgrounds, out_colors, out_alphas, last_ids);
+                                                  backgrounds, out_colors, out_alphas, last_ids));
     EMD_CHECK_LAUNCH("rasterize_fwd");
     return EMD_OK;
 }
@@ -416,14 +416,14 @@ extern "C" int emd_rasterize_bwd(const float* recs, const int32_t* tile_offsets,
     if (P > 0) {
         cudaMemsetAsync(touched, 0, (size_t)P, stream);
         dim3 grid(tile_w, tile_h, (unsigned)C), block(EMD_TILE, EMD_TILE, 1);
-        raster_bwd_kernel<<<grid, block, 0, stream>>>(
+        EMD_LAUNCH(EK_RASTER_BWD, stream, raster_bwd_kernel<<<grid, block, 0, stream>>>(
             reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, radii, cum_tiles, P, (int)C, width,
             height, tile_w, tile_h, channels, ed_mode, backgrounds, out_colors, out_alphas, last_ids, v_out_colors,
-            v_out_alphas, partials, touched);
+            v_out_alphas, partials, touched));
     }
-    raster_gather_kernel<<<(unsigned)emd_cdiv(CN, 256), 256, 0, stream>>>(partials, touched, cum_tiles, CN, d_color,
+    EMD_LAUNCH(EK_RASTER_GATHER, stream, raster_gather_kernel<<<(unsigned)emd_cdiv(CN, 256), 256, 0, stream>>>(partials, touched, cum_tiles, CN, d_color,
                                                                            with_depth, v_means2d, v_means2d_abs,
-                                                                           v_conics, v_colors, v_depths, v_opacities);
+                                                                           v_conics, v_colors, v_depths, v_opacities));
     EMD_CHECK_LAUNCH("rasterize_bwd");
     return EMD_OK;
 }

@@ -139,7 +139,8 @@ struct ActArgs {
     const float* quats;      // [N,4]
     const int64_t* point_ids;  // [N] or null
     const uint8_t* inst_valid; // [I] (frame-valid flag per instance) or null
-    float cam[3];
+    float cam[8][3];       // camera centres: colours are produced per camera, coefficients read once
+    int C;
     int64_t N;
     int K;          // total bases stored (1 + rest rows)
     int deg;        // degree to use
@@ -159,27 +160,9 @@ __global__ void __launch_bounds__(SH_THREADS) activate_fwd_kernel(ActArgs a, flo
     if (a.K > 1 && nb > 1) warp_load_rows(a.rest, row0, a.N, (a.K - 1) * 3, tile, 3, lane);
     __syncwarp();
     const int64_t n = row0 + lane;
-    float col[3] = {0.f, 0.f, 0.f};
+    float mx = 0.f, my = 0.f, mz = 0.f;
     if (n < a.N) {
-        float x = a.means[n * 3 + 0] - a.cam[0], y = a.means[n * 3 + 1] - a.cam[1], z = a.means[n * 3 + 2] - a.cam[2];
-        const float inv = 1.0f / sqrtf(x * x + y * y + z * z);
-        x *= inv; y *= inv; z *= inv;
-        float b[16];
-        sh_bases(a.deg, x, y, z, b);
-        const float* row = tile + lane * SH_STRIDE;
-        for (int k = 0; k < nb; ++k) {
-            col[0] += b[k] * row[k * 3 + 0];
-            col[1] += b[k] * row[k * 3 + 1];
-            col[2] += b[k] * row[k * 3 + 2];
-        }
-        // torch.clamp passes the gradient on the closed interval [0,1]; remember which channels do
-        uint32_t pass = 0;
-        for (int c = 0; c < 3; ++c) {
-            const float pre = col[c] + 0.5f;
-            if (pre >= 0.f && pre <= 1.f) pass |= 1u << c;
-            col[c] = fminf(fmaxf(pre, 0.f), 1.f);
-        }
-        clamp_pass[n] = (uint8_t)pass;
+        mx = a.means[n * 3 + 0]; my = a.means[n * 3 + 1]; mz = a.means[n * 3 + 2];
         float valid = 1.f;
         if (a.inst_valid) valid = a.inst_valid[a.point_ids[n]] ? 1.f : 0.f;
         opac[n] = valid / (1.0f + expf(-a.opac_logit[n]));
@@ -187,14 +170,50 @@ __global__ void __launch_bounds__(SH_THREADS) activate_fwd_kernel(ActArgs a, flo
         const float qi = 1.0f / sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
         reinterpret_cast<float4*>(quats_n)[n] = make_float4(q.x * qi, q.y * qi, q.z * qi, q.w * qi);
     }
+    // colours: one pass per camera over the staged coefficients (read from HBM once); each camera's
+    // colours leave through a small second tile so the stores stay coalesced.
+    __shared__ float s_rgb[SH_WARPS][32 * 3];
+    for (int c = 0; c < a.C; ++c) {
+        float col[3] = {0.f, 0.f, 0.f};
+        if (n < a.N) {
+            float x = mx - a.cam[c][0], y = my - a.cam[c][1], z = mz - a.cam[c][2];
+            const float inv = 1.0f / sqrtf(x * x + y * y + z * z);
+            x *= inv; y *= inv; z *= inv;
+            float b[16];
+            sh_bases(a.deg, x, y, z, b);
+            const float* row = tile + lane * SH_STRIDE;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (k < nb) {
+                    col[0] += b[k] * row[k * 3 + 0];
+                    col[1] += b[k] * row[k * 3 + 1];
+                    col[2] += b[k] * row[k * 3 + 2];
+                }
+            }
+            // torch.clamp passes the gradient on the closed interval [0,1]; remember which channels do
+            uint32_t pass = 0;
+            for (int ch = 0; ch < 3; ++ch) {
+                const float pre = col[ch] + 0.5f;
+                if (pre >= 0.f && pre <= 1.f) pass |= 1u << ch;
+                col[ch] = fminf(fmaxf(pre, 0.f), 1.f);
+            }
+            clamp_pass[(int64_t)c * a.N + n] = (uint8_t)pass;
+        }
+        __syncwarp();
+        s_rgb[warp][lane * 3 + 0] = col[0]; s_rgb[warp][lane * 3 + 1] = col[1]; s_rgb[warp][lane * 3 + 2] = col[2];
+        __syncwarp();
+        {
+            const int64_t rows = min((int64_t)32, a.N - row0);
+            float* dst = rgbs + ((int64_t)c * a.N + row0) * 3;
+            for (int i = lane; i < (int)rows * 3; i += 32) dst[i] = s_rgb[warp][i];
+        }
+    }
     __syncwarp();
     if (n < a.N) {
         float* row = tile + lane * SH_STRIDE;
-        row[0] = col[0]; row[1] = col[1]; row[2] = col[2];
         row[3] = expf(a.log_scales[n * 3 + 0]); row[4] = expf(a.log_scales[n * 3 + 1]); row[5] = expf(a.log_scales[n * 3 + 2]);
     }
     __syncwarp();
-    warp_store_rows(rgbs, row0, a.N, 3, tile, 0, lane);
     warp_store_rows(scales, row0, a.N, 3, tile, 3, lane);
 }
 
@@ -211,18 +230,24 @@ __global__ void __launch_bounds__(SH_THREADS) activate_bwd_kernel(
     float* tile = s_tile[warp];
     const int64_t n = row0 + lane;
     if (n < a.N) {
-        float x = a.means[n * 3 + 0] - a.cam[0], y = a.means[n * 3 + 1] - a.cam[1], z = a.means[n * 3 + 2] - a.cam[2];
-        const float inv = 1.0f / sqrtf(x * x + y * y + z * z);
-        x *= inv; y *= inv; z *= inv;
-        float b[16];
-        sh_bases(a.deg, x, y, z, b);
-        float v[3];
-        const uint32_t pass = clamp_pass[n];
-        for (int c = 0; c < 3; ++c) v[c] = ((pass >> c) & 1u) ? v_rgbs[n * 3 + c] : 0.f;
         float* row = tile + lane * SH_STRIDE;
-        for (int k = 0; k < a.K; ++k) {
-            const float bk = k < nb ? b[k] : 0.f;
-            row[k * 3 + 0] = bk * v[0]; row[k * 3 + 1] = bk * v[1]; row[k * 3 + 2] = bk * v[2];
+        for (int k = 0; k < a.K * 3; ++k) row[k] = 0.f;
+        const float mx = a.means[n * 3 + 0], my = a.means[n * 3 + 1], mz = a.means[n * 3 + 2];
+        for (int c = 0; c < a.C; ++c) {
+            float x = mx - a.cam[c][0], y = my - a.cam[c][1], z = mz - a.cam[c][2];
+            const float inv = 1.0f / sqrtf(x * x + y * y + z * z);
+            x *= inv; y *= inv; z *= inv;
+            float b[16];
+            sh_bases(a.deg, x, y, z, b);
+            float v[3];
+            const uint32_t pass = clamp_pass[(int64_t)c * a.N + n];
+            for (int ch = 0; ch < 3; ++ch) v[ch] = ((pass >> ch) & 1u) ? v_rgbs[((int64_t)c * a.N + n) * 3 + ch] : 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (k < nb) {
+                    row[k * 3 + 0] += b[k] * v[0]; row[k * 3 + 1] += b[k] * v[1]; row[k * 3 + 2] += b[k] * v[2];
+                }
+            }
         }
         // sigmoid * mask
         float valid = 1.f;
@@ -257,7 +282,7 @@ extern "C" int emd_sh_fwd(int degree, const float* dirs, const float* coeffs, in
     EMD_CHECK_ARG(degree >= 0 && degree <= 3, "sh_fwd: degree must be 0..3");
     EMD_CHECK_ARG(K >= (degree + 1) * (degree + 1) && K <= 16, "sh_fwd: K=%d too small for degree %d or > 16", K, degree);
     if (N == 0) return EMD_OK;
-    sh_fwd_kernel<<<(unsigned)emd_cdiv(N, SH_WARPS * 32), SH_THREADS, 0, stream>>>(degree, dirs, coeffs, N, K, out);
+    EMD_LAUNCH(EK_SH_FWD, stream, sh_fwd_kernel<<<(unsigned)emd_cdiv(N, SH_WARPS * 32), SH_THREADS, 0, stream>>>(degree, dirs, coeffs, N, K, out));
     EMD_CHECK_LAUNCH("sh_fwd");
     return EMD_OK;
 }
@@ -267,54 +292,56 @@ extern "C" int emd_sh_bwd(int degree, const float* dirs, int64_t N, int K, const
     EMD_CHECK_ARG(degree >= 0 && degree <= 3, "sh_bwd: degree must be 0..3");
     EMD_CHECK_ARG(K >= (degree + 1) * (degree + 1) && K <= 16, "sh_bwd: bad K");
     if (N == 0) return EMD_OK;
-    sh_bwd_kernel<<<(unsigned)emd_cdiv(N, SH_WARPS * 32), SH_THREADS, 0, stream>>>(degree, dirs, N, K, v_out, v_coeffs);
+    EMD_LAUNCH(EK_SH_BWD, stream, sh_bwd_kernel<<<(unsigned)emd_cdiv(N, SH_WARPS * 32), SH_THREADS, 0, stream>>>(degree, dirs, N, K, v_out, v_coeffs));
     EMD_CHECK_LAUNCH("sh_bwd");
     return EMD_OK;
 }
 
 static int make_act_args(ActArgs& a, const float* means, const float* dc, const float* rest, const float* opac_logit,
                          const float* log_scales, const float* quats, const int64_t* point_ids,
-                         const uint8_t* inst_valid, const float* cam_pos_host, int64_t N, int K, int degree) {
+                         const uint8_t* inst_valid, const float* cam_pos_host, int C, int64_t N, int K, int degree) {
     EMD_CHECK_ARG(degree >= 0 && degree <= 3, "activate: degree must be 0..3");
     EMD_CHECK_ARG(K >= 1 && K <= 16 && K >= (degree + 1) * (degree + 1), "activate: bad K=%d for degree %d", K, degree);
     EMD_CHECK_ARG((point_ids == nullptr) == (inst_valid == nullptr), "activate: point_ids and inst_valid go together");
     if (!emd_aligned(quats, 16)) { emd_set_error("activate: quats must be 16-B aligned"); return EMD_ERR_ALIGN; }
     a.means = means; a.dc = dc; a.rest = rest; a.opac_logit = opac_logit; a.log_scales = log_scales; a.quats = quats;
     a.point_ids = point_ids; a.inst_valid = inst_valid;
-    a.cam[0] = cam_pos_host[0]; a.cam[1] = cam_pos_host[1]; a.cam[2] = cam_pos_host[2];
-    a.N = N; a.K = K; a.deg = degree;
+    EMD_CHECK_ARG(C >= 1 && C <= 8, "activate: 1..8 cameras per call (got %d)", C);
+    for (int c = 0; c < C; ++c)
+        for (int k = 0; k < 3; ++k) a.cam[c][k] = cam_pos_host[c * 3 + k];
+    a.C = C; a.N = N; a.K = K; a.deg = degree;
     return EMD_OK;
 }
 
-// cam_pos is a HOST pointer to 3 floats (it is a per-call scalar triple, like the image size).
+// cam_pos_host is a HOST pointer to C x 3 floats (per-call scalars, like the image size).  rgbs / clamp_pass are [C,N,.].
 extern "C" int emd_activate_fwd(const float* means, const float* dc, const float* rest, const float* opac_logit,
                                 const float* log_scales, const float* quats, const int64_t* point_ids,
-                                const uint8_t* inst_valid, const float* cam_pos_host, int64_t N, int K, int degree,
+                                const uint8_t* inst_valid, const float* cam_pos_host, int C, int64_t N, int K, int degree,
                                 float* rgbs, float* opac, float* scales, float* quats_n, uint8_t* clamp_pass,
                                 cudaStream_t stream) {
     ActArgs a;
-    int rc = make_act_args(a, means, dc, rest, opac_logit, log_scales, quats, point_ids, inst_valid, cam_pos_host, N, K, degree);
+    int rc = make_act_args(a, means, dc, rest, opac_logit, log_scales, quats, point_ids, inst_valid, cam_pos_host, C, N, K, degree);
     if (rc != EMD_OK) return rc;
     if (N == 0) return EMD_OK;
-    activate_fwd_kernel<<<(unsigned)emd_cdiv(N, SH_WARPS * 32), SH_THREADS, 0, stream>>>(a, rgbs, opac, scales, quats_n, clamp_pass);
+    EMD_LAUNCH(EK_ACT_FWD, stream, activate_fwd_kernel<<<(unsigned)emd_cdiv(N, SH_WARPS * 32), SH_THREADS, 0, stream>>>(a, rgbs, opac, scales, quats_n, clamp_pass));
     EMD_CHECK_LAUNCH("activate_fwd");
     return EMD_OK;
 }
 
 extern "C" int emd_activate_bwd(const float* means, const float* dc, const float* rest, const float* opac_logit,
                                 const float* log_scales, const float* quats, const int64_t* point_ids,
-                                const uint8_t* inst_valid, const float* cam_pos_host, int64_t N, int K, int degree,
+                                const uint8_t* inst_valid, const float* cam_pos_host, int C, int64_t N, int K, int degree,
                                 const uint8_t* clamp_pass, const float* scales, const float* v_rgbs,
                                 const float* v_opac, const float* v_scales, const float* v_quats_n, float* v_dc,
                                 float* v_rest, float* v_opac_logit, float* v_log_scales, float* v_quats,
                                 cudaStream_t stream) {
     ActArgs a;
-    int rc = make_act_args(a, means, dc, rest, opac_logit, log_scales, quats, point_ids, inst_valid, cam_pos_host, N, K, degree);
+    int rc = make_act_args(a, means, dc, rest, opac_logit, log_scales, quats, point_ids, inst_valid, cam_pos_host, C, N, K, degree);
     if (rc != EMD_OK) return rc;
     if (N == 0) return EMD_OK;
     if (!emd_aligned(v_quats, 16) || !emd_aligned(v_quats_n, 16)) { emd_set_error("activate_bwd: quats grads must be 16-B aligned"); return EMD_ERR_ALIGN; }
-    activate_bwd_kernel<<<(unsigned)emd_cdiv(N, SH_WARPS * 32), SH_THREADS, 0, stream>>>(
-        a, clamp_pass, scales, v_rgbs, v_opac, v_scales, v_quats_n, v_dc, v_rest, v_opac_logit, v_log_scales, v_quats);
+    EMD_LAUNCH(EK_ACT_BWD, stream, activate_bwd_kernel<<<(unsigned)emd_cdiv(N, SH_WARPS * 32), SH_THREADS, 0, stream>>>(
+        a, clamp_pass, scales, v_rgbs, v_opac, v_scales, v_quats_n, v_dc, v_rest, v_opac_logit, v_log_scales, v_quats));
     EMD_CHECK_LAUNCH("activate_bwd");
     return EMD_OK;
 }

@@ -70,36 +70,37 @@ class _Activate(torch.autograd.Function):
         rest = rest.float().contiguous() if K > 1 else None
         opac_logit = opac_logit.float().contiguous().reshape(-1)
         log_scales = log_scales.float().contiguous()
-        cam = (_c.c_float * 3)(*[float(v) for v in cam_pos])
-        rgbs = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        C = len(cam_pos) // 3
+        cam = (_c.c_float * (3 * C))(*[float(v) for v in cam_pos])
+        rgbs = torch.empty(C, N, 3, dtype=torch.float32, device=dev)
         opac = torch.empty(N, dtype=torch.float32, device=dev)
         scales = torch.empty(N, 3, dtype=torch.float32, device=dev)
         quats_n = torch.empty(N, 4, dtype=torch.float32, device=dev)
-        clamp_pass = torch.empty(N, dtype=torch.uint8, device=dev)
+        clamp_pass = torch.empty(C, N, dtype=torch.uint8, device=dev)
         pid = point_ids.contiguous() if point_ids is not None else None
         iv = inst_valid.to(torch.uint8).contiguous() if inst_valid is not None else None
         _C.check(L.emd_activate_fwd(_C.ptr(means_world), _C.ptr(dc), _C.ptr(rest), _C.ptr(opac_logit),
                                     _C.ptr(log_scales), _C.ptr(quats), _C.ptr(pid, torch.int64, "point_ids"),
-                                    _C.ptr(iv), cam, N, K, degree, _C.ptr(rgbs), _C.ptr(opac), _C.ptr(scales),
+                                    _C.ptr(iv), cam, C, N, K, degree, _C.ptr(rgbs), _C.ptr(opac), _C.ptr(scales),
                                     _C.ptr(quats_n), _C.ptr(clamp_pass), _C.stream()), "emd_activate_fwd")
         ctx.save_for_backward(means_world, dc, rest if rest is not None else torch.empty(0, device=dev), opac_logit,
                               log_scales, quats, pid if pid is not None else torch.empty(0, device=dev),
                               iv if iv is not None else torch.empty(0, device=dev), clamp_pass, scales)
-        ctx.cfg = (N, K, degree, tuple(float(v) for v in cam_pos), pid is not None)
+        ctx.cfg = (N, K, degree, tuple(float(v) for v in cam_pos), pid is not None, C)
         return rgbs, opac, scales, quats_n
 
     @staticmethod
     def backward(ctx, v_rgbs, v_opac, v_scales, v_quats_n):
         L = _C.lib()
         means_world, dc, rest, opac_logit, log_scales, quats, pid, iv, clamp_pass, scales = ctx.saved_tensors
-        N, K, degree, cam_pos, has_ids = ctx.cfg
+        N, K, degree, cam_pos, has_ids, C = ctx.cfg
         dev = dc.device
-        cam = (_c.c_float * 3)(*cam_pos)
+        cam = (_c.c_float * (3 * C))(*cam_pos)
 
         def z(g, shape):
             return g.float().contiguous() if g is not None else torch.zeros(shape, dtype=torch.float32, device=dev)
 
-        v_rgbs, v_opac = z(v_rgbs, (N, 3)), z(v_opac, (N,))
+        v_rgbs, v_opac = z(v_rgbs, (C, N, 3)), z(v_opac, (N,))
         v_scales, v_quats_n = z(v_scales, (N, 3)), z(v_quats_n, (N, 4))
         v_dc = torch.empty(N, 3, dtype=torch.float32, device=dev)
         v_rest = torch.empty(N, K - 1, 3, dtype=torch.float32, device=dev) if K > 1 else None
@@ -108,7 +109,7 @@ class _Activate(torch.autograd.Function):
         v_q = torch.empty(N, 4, dtype=torch.float32, device=dev)
         _C.check(L.emd_activate_bwd(_C.ptr(means_world), _C.ptr(dc), _C.ptr(rest) if K > 1 else None,
                                     _C.ptr(opac_logit), _C.ptr(log_scales), _C.ptr(quats),
-                                    _C.ptr(pid) if has_ids else None, _C.ptr(iv) if has_ids else None, cam, N, K,
+                                    _C.ptr(pid) if has_ids else None, _C.ptr(iv) if has_ids else None, cam, C, N, K,
                                     degree, _C.ptr(clamp_pass), _C.ptr(scales), _C.ptr(v_rgbs), _C.ptr(v_opac),
                                     _C.ptr(v_scales), _C.ptr(v_quats_n), _C.ptr(v_dc), _C.ptr(v_rest), _C.ptr(v_logit),
                                     _C.ptr(v_ls), _C.ptr(v_q), _C.stream()), "emd_activate_bwd")
@@ -118,11 +119,16 @@ class _Activate(torch.autograd.Function):
 def activate_gaussians(means_world: Tensor, features_dc: Tensor, features_rest: Optional[Tensor], opacities: Tensor,
                        scales: Tensor, quats: Tensor, cam_pos, sh_degree_to_use: int,
                        point_ids: Optional[Tensor] = None, inst_valid: Optional[Tensor] = None):
-    """-> rgbs[N,3] in [0,1], opacities[N] (sigmoid x frame-valid), scales[N,3] (exp), quats[N,4] (unit).
+    """-> rgbs in [0,1], opacities[N] (sigmoid x frame-valid), scales[N,3] (exp), quats[N,4] (unit).
 
-    ``opacities`` are logits ``[N,1]`` or ``[N]``; the gradient w.r.t. them keeps that shape."""
-    shape = opacities.shape
+    ``cam_pos`` is one camera centre (3 numbers -> rgbs[N,3]) or a list of up to 8
+    (-> rgbs[C,N,3]; the SH coefficients are read once for all cameras).
+    ``opacities`` are logits ``[N,1]`` or ``[N]``."""
+    if isinstance(cam_pos, Tensor):
+        cam_pos = cam_pos.detach().cpu().tolist()
+    multi = len(cam_pos) > 0 and isinstance(cam_pos[0], (list, tuple))
+    flat = [float(v) for cp in cam_pos for v in cp] if multi else [float(v) for v in cam_pos]
+    assert len(flat) % 3 == 0 and 3 <= len(flat) <= 24, "cam_pos: 1..8 camera centres"
     rgbs, opac, sc, qn = _Activate.apply(means_world, features_dc, features_rest, opacities.reshape(-1), scales, quats,
-                                         point_ids, inst_valid, [float(v) for v in cam_pos], int(sh_degree_to_use))
-    del shape
-    return rgbs, opac, sc, qn
+                                         point_ids, inst_valid, flat, int(sh_degree_to_use))
+    return (rgbs if multi else rgbs[0]), opac, sc, qn

@@ -12,8 +12,8 @@ rectangles, sort keys) are written as explicit elementwise expressions in a
 fixed association order -- the "canonical op order" that DESIGN.md section 4
 documents -- so that the CUDA kernels, which evaluate the same expressions with
 un-contracted IEEE round-to-nearest intrinsics, reproduce them bit for bit.
-torch CPU elementwise ``*`` ``+`` ``-`` ``/`` ``sqrt`` are IEEE-correct and are
-never fused, which is what makes this possible.
+torch CPU elementwise ``*`` ``+`` ``-`` ``/`` are IEEE-correct and are never
+fused, which is what makes this possible (``sqrt`` is not -- see ``c_sqrt``).
 
 Backward values come from ``torch.autograd`` on these functions.
 """
@@ -268,8 +268,12 @@ def rasterize_to_pixels(
     max_alpha: float = MAX_ALPHA,
     t_stop_inclusive: bool = True,
     pixel_center: float = 0.5,
+    tile_rows: Optional[Tuple[int, int]] = None,
 ):
     """Front-to-back alpha compositing per 16x16 tile.
+
+    ``tile_rows=(r0, r1)`` composites only tile rows r0 <= ty < r1 (a bounded
+    sample for the CPU baseline); other pixels stay zero.
 
     -> render_colors[C,H,W,D], render_alphas[C,H,W,1], last_ids[C,H,W] (i32, index
     into the sorted list of the last blended Gaussian; 0 if none).
@@ -297,6 +301,8 @@ def rasterize_to_pixels(
     chunks_c, chunks_a = {}, {}
     for c in range(C):
         for ty in range(th):
+            if tile_rows is not None and not (tile_rows[0] <= ty < tile_rows[1]):
+                continue
             for tx in range(tw):
                 t = (c * th + ty) * tw + tx
                 s, e = int(offs[t]), int(offs[t + 1])
@@ -422,6 +428,7 @@ def rasterization(
     render_mode: str = "RGB",
     rasterize_mode: str = "classic",
     return_unstable: bool = False,
+    tile_rows: Optional[Tuple[int, int]] = None,
 ) -> Tuple[Tensor, Tensor, Dict]:
     """Restates ``gsplat.rendering.rasterization`` for the arguments the
     reference passes (``OmniRe/models/trainers/base.py:393-408``)."""
@@ -451,7 +458,7 @@ def rasterization(
     isect_offsets = isect_offset_encode(isect_ids, C, tile_width, tile_height, tile_n_bits)
     res = rasterize_to_pixels(
         means2d, conics, colors, opac, width, height, tile_size, isect_offsets, flatten_ids, backgrounds,
-        return_unstable=return_unstable,
+        return_unstable=return_unstable, tile_rows=tile_rows,
     )
     render_colors, render_alphas, last_ids = res[:3]
     if render_mode in ("ED", "RGB+ED"):
