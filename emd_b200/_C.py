@@ -39,7 +39,8 @@ _SIGS = {
     "emd_radix_sort_workspace_bytes": (c_size_t, [c_int64]),
     "emd_radix_sort_pairs": (c_int, [P, P, P, P, c_int64, c_int, c_int, P, c_size_t, ctypes.POINTER(c_int), P]),
     "emd_raster_pack": (c_int, [P, P, P, c_int, P, c_int, c_int, P, c_int, P, c_int64, c_int64, P, P]),
-    "emd_rasterize_fwd": (c_int, [P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
+    "emd_tile_order": (c_int, [P, c_int64, c_int64, P, P]),
+    "emd_rasterize_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "emd_rasterize_bwd_workspace_bytes": (c_size_t, [c_int64]),
     "emd_sh_fwd": (c_int, [c_int, P, P, c_int64, c_int, P, P]),
     "emd_sh_bwd": (c_int, [c_int, P, c_int64, c_int, P, P, P]),
@@ -56,7 +57,7 @@ _SIGS = {
     "emd_smpl_reduce_width": (c_int, []),
     "emd_smpl_deform_fwd": (c_int, [P] * 12 + [c_int] * 5 + [c_float, c_int, c_int] + [P] * 5 + [P]),
     "emd_smpl_deform_bwd": (c_int, [P] * 11 + [c_int] * 5 + [c_float, c_int, c_int] + [P] * 14 + [P]),
-    "emd_rasterize_bwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
+    "emd_rasterize_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
                                   P, P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
 }
 

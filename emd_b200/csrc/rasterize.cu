@@ -58,18 +58,22 @@ __global__ void raster_pack_kernel(const float* __restrict__ means2d, const floa
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(RB) raster_fwd_kernel(
     const float4* __restrict__ recs, const int32_t* __restrict__ tile_offsets, const int32_t* __restrict__ flatten_ids,
-    int64_t P, int C, int width, int height, int tile_w, int tile_h, int CH, int ed_mode,
-    const float* __restrict__ backgrounds, float* __restrict__ out_colors, float* __restrict__ out_alphas,
-    int32_t* __restrict__ last_ids) {
+    const int32_t* __restrict__ tile_order, int64_t P, int C, int width, int height, int tile_w, int tile_h, int CH,
+    int ed_mode, const float* __restrict__ backgrounds, float* __restrict__ out_colors,
+    float* __restrict__ out_alphas, int32_t* __restrict__ last_ids) {
     __shared__ float4 s_r0[RB];
     __shared__ float4 s_r1[RB];
     __shared__ float2 s_r2[RB];
 
-    const int cam = blockIdx.z;
-    const int tile_id = (cam * tile_h + blockIdx.y) * tile_w + blockIdx.x;
+    // heaviest tiles first (longest-processing-time-first): the long horizon tiles then overlap
+    // with the many short ones instead of running alone at the tail of the grid
+    const int tile_id = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;
+    const int cam = tile_id / (tile_w * tile_h);
+    const int tile_y = (tile_id - cam * tile_w * tile_h) / tile_w;
+    const int tile_x = tile_id - (cam * tile_h + tile_y) * tile_w;
     const int tr = threadIdx.y * EMD_TILE + threadIdx.x;
-    const int i = blockIdx.y * EMD_TILE + threadIdx.y;
-    const int j = blockIdx.x * EMD_TILE + threadIdx.x;
+    const int i = tile_y * EMD_TILE + threadIdx.y;
+    const int j = tile_x * EMD_TILE + threadIdx.x;
     const float px = (float)j + 0.5f, py = (float)i + 0.5f;
     const bool inside = i < height && j < width;
     bool done = !inside;
@@ -151,8 +155,9 @@ __device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
 
 __global__ void __launch_bounds__(RB) raster_bwd_kernel(
     const float4* __restrict__ recs, const int32_t* __restrict__ tile_offsets, const int32_t* __restrict__ flatten_ids,
-    const int32_t* __restrict__ radii, const int64_t* __restrict__ cum_tiles, int64_t P, int C, int width, int height,
-    int tile_w, int tile_h, int CH, int ed_mode, const float* __restrict__ backgrounds,
+    const int32_t* __restrict__ tile_order, const int32_t* __restrict__ radii, const int64_t* __restrict__ cum_tiles,
+    int64_t P, int C, int width, int height, int tile_w, int tile_h, int CH, int ed_mode,
+    const float* __restrict__ backgrounds,
     const float* __restrict__ out_colors, const float* __restrict__ out_alphas, const int32_t* __restrict__ last_ids,
     const float* __restrict__ v_out_colors, const float* __restrict__ v_out_alphas, float* __restrict__ partials,
     uint8_t* __restrict__ touched) {
@@ -164,12 +169,14 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
     __shared__ uint32_t s_tmask[RB / 32];
     __shared__ int s_red[RB / 32];
 
-    const int cam = blockIdx.z;
-    const int tile_id = (cam * tile_h + blockIdx.y) * tile_w + blockIdx.x;
+    const int tile_id = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;
+    const int cam = tile_id / (tile_w * tile_h);
+    const int tile_y = (tile_id - cam * tile_w * tile_h) / tile_w;
+    const int tile_x = tile_id - (cam * tile_h + tile_y) * tile_w;
     const int tr = threadIdx.y * EMD_TILE + threadIdx.x;
     const int lane = tr & 31, warp = tr >> 5;
-    const int i = blockIdx.y * EMD_TILE + threadIdx.y;
-    const int j = blockIdx.x * EMD_TILE + threadIdx.x;
+    const int i = tile_y * EMD_TILE + threadIdx.y;
+    const int j = tile_x * EMD_TILE + threadIdx.x;
     const float px = (float)j + 0.5f, py = (float)i + 0.5f;
     const bool inside = i < height && j < width;
     const int64_t pix = ((int64_t)cam * height + min(i, height - 1)) * width + min(j, width - 1);
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
             int x0, y0, x1, y1;
             tile_rect_c(r0.x, r0.y, radii[g], tile_w, tile_h, x0, y0, x1, y1);
             const int64_t base = g == 0 ? 0 : cum_tiles[g - 1];
-            s_slot[tr] = (uint32_t)(base + (int64_t)((int)blockIdx.y - y0) * (x1 - x0) + ((int)blockIdx.x - x0));
+            s_slot[tr] = (uint32_t)(base + (int64_t)(tile_y - y0) * (x1 - x0) + (tile_x - x0));
         }
         __syncthreads();
         for (int sub = 0; sub < batch_size; sub += 32) {
@@ -313,6 +320,32 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
     }
 }
 
+// Heavy-first tile order: bucket tiles by floor(log2(list length)) (coarse LPT is enough) and emit
+// bucket 31 (longest) first.  One CTA; order within a bucket is arbitrary (it only affects scheduling).
+__global__ void __launch_bounds__(1024) tile_order_kernel(const int32_t* __restrict__ tile_offsets, int64_t P,
+                                                          int n_cam_tiles, int32_t* __restrict__ order) {
+    __shared__ int s_cnt[33];
+    __shared__ int s_base[33];
+    if (threadIdx.x < 33) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_cam_tiles; t += blockDim.x) {
+        const int64_t e = t == n_cam_tiles - 1 ? P : (int64_t)tile_offsets[t + 1];
+        const int len = (int)(e - tile_offsets[t]);
+        atomicAdd(&s_cnt[len > 0 ? 32 - __clz(len) : 0], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int b = 32; b >= 0; --b) { s_base[b] = run; run += s_cnt[b]; }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_cam_tiles; t += blockDim.x) {
+        const int64_t e = t == n_cam_tiles - 1 ? P : (int64_t)tile_offsets[t + 1];
+        const int len = (int)(e - tile_offsets[t]);
+        order[atomicAdd(&s_base[len > 0 ? 32 - __clz(len) : 0], 1)] = t;
+    }
+}
+
 // Sum each Gaussian's contiguous run of slots -> dense per-(camera,Gaussian) grads.
 __global__ void raster_gather_kernel(const float* __restrict__ partials, const uint8_t* __restrict__ touched,
                                      const int64_t* __restrict__ cum_tiles, int64_t CN, int d_color, int with_depth,
@@ -363,20 +396,29 @@ extern "C" int emd_raster_pack(const float* means2d, const float* conics, const 
     return EMD_OK;
 }
 
+// order[C*tile_h*tile_w]: tile ids, longest Gaussian list first (optional input of rasterize_fwd/bwd)
+extern "C" int emd_tile_order(const int32_t* tile_offsets, int64_t P, int64_t n_cam_tiles, int32_t* order,
+                              cudaStream_t stream) {
+    EMD_CHECK_ARG(n_cam_tiles >= 1 && n_cam_tiles < (1 << 30), "tile_order: bad tile count");
+    EMD_LAUNCH(EK_MISC, stream, tile_order_kernel<<<1, 1024, 0, stream>>>(tile_offsets, P, (int)n_cam_tiles, order));
+    EMD_CHECK_LAUNCH("tile_order");
+    return EMD_OK;
+}
+
 extern "C" int emd_rasterize_fwd(const float* recs, const int32_t* tile_offsets, const int32_t* flatten_ids,
-                                 int64_t P, int64_t C, int width, int height, int tile_w, int tile_h, int channels,
+                                 const int32_t* tile_order, int64_t P, int64_t C, int width, int height, int tile_w, int tile_h, int channels,
                                  int ed_mode, const float* backgrounds, float* out_colors, float* out_alphas,
                                  int32_t* last_ids, cudaStream_t stream) {
     EMD_CHECK_ARG(channels >= 1 && channels <= 4, "rasterize_fwd: channels must be 1..4");
-    EMD_CHECK_ARG(C >= 1 && C <= 65535 && tile_h <= 65535, "rasterize_fwd: grid too large");
+    EMD_CHECK_ARG(C >= 1 && C * tile_w * tile_h < ((int64_t)1 << 31), "rasterize_fwd: grid too large");
     EMD_CHECK_ARG(tile_w == (width + EMD_TILE - 1) / EMD_TILE && tile_h == (height + EMD_TILE - 1) / EMD_TILE,
                   "rasterize_fwd: tile grid does not match image size (tile size is 16)");
     if (!emd_aligned(recs, 16) || (channels == 4 && !emd_aligned(out_colors, 16))) {
         emd_set_error("rasterize_fwd: recs/out_colors must be 16-B aligned");
         return EMD_ERR_ALIGN;
     }
-    dim3 grid(tile_w, tile_h, (unsigned)C), block(EMD_TILE, EMD_TILE, 1);
-    EMD_LAUNCH(EK_RASTER_FWD, stream, raster_fwd_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, P,
+    dim3 grid((unsigned)(C * tile_w * tile_h)), block(EMD_TILE, EMD_TILE, 1);
+    EMD_LAUNCH(EK_RASTER_FWD, stream, raster_fwd_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, tile_order, P,
                                                   (int)C, width, height, tile_w, tile_h, channels, ed_mode,
                                                   backgrounds, out_colors, out_alphas, last_ids));
     EMD_CHECK_LAUNCH("rasterize_fwd");
@@ -390,7 +432,7 @@ extern "C" size_t emd_rasterize_bwd_workspace_bytes(int64_t P) {
 }
 
 extern "C" int emd_rasterize_bwd(const float* recs, const int32_t* tile_offsets, const int32_t* flatten_ids,
-                                 const int32_t* radii, const int64_t* cum_tiles, int64_t P, int64_t N, int64_t C,
+                                 const int32_t* tile_order, const int32_t* radii, const int64_t* cum_tiles, int64_t P, int64_t N, int64_t C,
                                  int width, int height, int tile_w, int tile_h, int channels, int ed_mode,
                                  const float* backgrounds, const float* out_colors, const float* out_alphas,
                                  const int32_t* last_ids, const float* v_out_colors, const float* v_out_alphas,
@@ -415,9 +457,9 @@ extern "C" int emd_rasterize_bwd(const float* recs, const int32_t* tile_offsets,
     uint8_t* touched = reinterpret_cast<uint8_t*>(workspace) + part;
     if (P > 0) {
         cudaMemsetAsync(touched, 0, (size_t)P, stream);
-        dim3 grid(tile_w, tile_h, (unsigned)C), block(EMD_TILE, EMD_TILE, 1);
+        dim3 grid((unsigned)(C * tile_w * tile_h)), block(EMD_TILE, EMD_TILE, 1);
         EMD_LAUNCH(EK_RASTER_BWD, stream, raster_bwd_kernel<<<grid, block, 0, stream>>>(
-            reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, radii, cum_tiles, P, (int)C, width,
+            reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, tile_order, radii, cum_tiles, P, (int)C, width,
             height, tile_w, tile_h, channels, ed_mode, backgrounds, out_colors, out_alphas, last_ids, v_out_colors,
             v_out_alphas, partials, touched));
     }

@@ -212,12 +212,15 @@ class _Rasterize(torch.autograd.Function):
         out_alphas = torch.empty(C, height, width, 1, dtype=torch.float32, device=dev)
         last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
         bg = _f32c(backgrounds) if backgrounds is not None else None
+        tile_order = torch.empty(C * th * tw, dtype=torch.int32, device=dev)
+        _C.check(L.emd_tile_order(_C.ptr(isect_offsets, torch.int32), P, C * th * tw, _C.ptr(tile_order), _C.stream()),
+                 "emd_tile_order")
         _C.check(L.emd_rasterize_fwd(_C.ptr(recs), _C.ptr(isect_offsets, torch.int32), _C.ptr(flatten_ids, torch.int32),
-                                     P, C, width, height, tw, th, CH, 1 if ed_mode else 0, _C.ptr(bg),
+                                     _C.ptr(tile_order), P, C, width, height, tw, th, CH, 1 if ed_mode else 0, _C.ptr(bg),
                                      _C.ptr(out_colors), _C.ptr(out_alphas), _C.ptr(last_ids), _C.stream()),
                  "emd_rasterize_fwd")
         ctx.save_for_backward(recs, isect_offsets, flatten_ids, radii, cum_tiles, bg if bg is not None else torch.empty(0, device=dev),
-                              out_colors, out_alphas, last_ids)
+                              out_colors, out_alphas, last_ids, tile_order)
         ctx.cfg = (width, height, CH, d_color, bool(with_depth), bool(ed_mode), bool(absgrad), colors_per_cam,
                    opac_per_cam, bg is not None)
         ctx.means2d_ref = means2d if absgrad else None
@@ -227,7 +230,7 @@ class _Rasterize(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_colors_out, v_alphas_out, _v_last):
         L = _C.lib()
-        recs, isect_offsets, flatten_ids, radii, cum_tiles, bg, out_colors, out_alphas, last_ids = ctx.saved_tensors
+        recs, isect_offsets, flatten_ids, radii, cum_tiles, bg, out_colors, out_alphas, last_ids, tile_order = ctx.saved_tensors
         width, height, CH, d_color, with_depth, ed_mode, absgrad, colors_per_cam, opac_per_cam, has_bg = ctx.cfg
         C, N = radii.shape
         dev = radii.device
@@ -244,7 +247,7 @@ class _Rasterize(torch.autograd.Function):
         ws_bytes = L.emd_rasterize_bwd_workspace_bytes(P)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _C.check(L.emd_rasterize_bwd(
-            _C.ptr(recs), _C.ptr(isect_offsets), _C.ptr(flatten_ids), _C.ptr(radii), _C.ptr(cum_tiles), P, N, C,
+            _C.ptr(recs), _C.ptr(isect_offsets), _C.ptr(flatten_ids), _C.ptr(tile_order), _C.ptr(radii), _C.ptr(cum_tiles), P, N, C,
             width, height, tw, th, CH, 1 if ed_mode else 0, _C.ptr(bg) if has_bg else None, _C.ptr(out_colors),
             _C.ptr(out_alphas), _C.ptr(last_ids), _C.ptr(v_colors_out), _C.ptr(v_alphas_out), d_color,
             1 if with_depth else 0, _C.ptr(v_means2d), _C.ptr(v_abs), _C.ptr(v_conics), _C.ptr(v_colors),
