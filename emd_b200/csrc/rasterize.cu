@@ -99,20 +99,34 @@ __global__ void __launch_bounds__(RB) raster_fwd_kernel(
         }
         __syncthreads();
         const int batch_size = (int)min((int64_t)RB, range_end - batch_start);
-        for (int t = 0; t < batch_size && !done; ++t) {
-            const float4 r0 = s_r0[t];
-            const float4 r1 = s_r1[t];
-            const float dx = r0.x - px, dy = r0.y - py;
-            const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
-            const float alpha = fminf(0.999f, r0.z * __expf(-sigma));
-            if (sigma < 0.f || alpha < ALPHA_MIN) continue;
-            const float next_T = T * (1.0f - alpha);
-            if (next_T <= 1e-4f) { done = true; break; }
-            const float vis = alpha * T;
-            const float2 r2 = s_r2[t];
-            acc[0] += r1.z * vis; acc[1] += r1.w * vis; acc[2] += r2.x * vis; acc[3] += r2.y * vis;
-            cur_idx = (int32_t)(batch_start + t);
-            T = next_T;
+        // Groups of 4: the alphas (sigma, exp) do not depend on the running transmittance, so four are
+        // evaluated with full ILP before the short sequential T / accumulate chain.  This matters for
+        // the long horizon tiles, whose CTA ends up alone on its SM and is latency-bound otherwise.
+        for (int t = 0; t < batch_size && !done; t += 4) {
+            float alpha[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int tt = min(t + u, RB - 1);
+                const float4 r0 = s_r0[tt];
+                const float4 r1 = s_r1[tt];
+                const float dx = r0.x - px, dy = r0.y - py;
+                const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
+                alpha[u] = fminf(0.999f, r0.z * __expf(-sigma));
+                ok[u] = (t + u < batch_size) && !(sigma < 0.f || alpha[u] < ALPHA_MIN);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!ok[u] || done) continue;
+                const float next_T = T * (1.0f - alpha[u]);
+                if (next_T <= 1e-4f) { done = true; continue; }
+                const float vis = alpha[u] * T;
+                const float4 r1 = s_r1[t + u];
+                const float2 r2 = s_r2[t + u];
+                acc[0] += r1.z * vis; acc[1] += r1.w * vis; acc[2] += r2.x * vis; acc[3] += r2.y * vis;
+                cur_idx = (int32_t)(batch_start + t + u);
+                T = next_T;
+            }
         }
     }
     if (inside) {
@@ -120,14 +134,23 @@ __global__ void __launch_bounds__(RB) raster_fwd_kernel(
         const float alpha_out = 1.0f - T;
         out_alphas[pix] = alpha_out;
         if (backgrounds) {
-            for (int k = 0; k < CH; ++k) acc[k] += T * backgrounds[cam * CH + k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < CH) acc[k] += T * backgrounds[cam * CH + k];
         }
-        if (ed_mode) acc[CH - 1] = acc[CH - 1] / fmaxf(alpha_out, 1e-10f);
+        if (ed_mode) {
+            const float inv = 1.0f / fmaxf(alpha_out, 1e-10f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k == CH - 1) acc[k] *= inv;
+        }
         float* o = out_colors + pix * CH;
         if (CH == 4) {
             *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         } else {
-            for (int k = 0; k < CH; ++k) o[k] = acc[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < CH) o[k] = acc[k];
         }
         last_ids[pix] = cur_idx;
     }
