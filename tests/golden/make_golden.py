@@ -1,0 +1,184 @@
+"""Generate the golden fixtures in tests/golden/ by running the REFERENCE's own Python
+(/root/reference, read-only) on the CPU.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The reference cannot be imported as is -- it needs open3d / omegaconf / pytorch3d / gsplat /
+nvdiffrast (absent) and hard-codes .cuda() -- so the missing third-party modules are stubbed with
+MagicMock, ``Tensor.cuda`` becomes the identity and ``device="cuda"`` arguments are dropped.  Only
+in-tree reference code produces the numbers: RigidNodes / SMPLNodes methods
+(OmniRe/models/nodes/{rigid,smpl}.py), the quaternion helpers (OmniRe/models/gaussians/basics.py,
+S3Gaussian/utils/graphics_utils.py), eval_sh (S3Gaussian/utils/sh_utils.py) and the S3Gaussian
+deformation network (S3Gaussian/scene/deformation.py).  gsplat's ``spherical_harmonics`` (stubbed
+module) is replaced by the reference's own ``eval_sh`` on normalised directions.
+"""
+import importlib
+import importlib.util
+import math
+import os
+import sys
+import types
+from unittest.mock import MagicMock
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+
+def _stub(names):
+    for n in names:
+        parts = n.split(".")
+        for i in range(1, len(parts) + 1):
+            sub = ".".join(parts[:i])
+            if sub not in sys.modules:
+                m = MagicMock(name=sub)
+                m.__path__ = []
+                m.__spec__ = None
+                sys.modules[sub] = m
+
+
+def _cpuify():
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    for fn in ("zeros", "ones", "tensor", "arange", "full", "eye", "empty", "rand", "randn"):
+        orig = getattr(torch, fn)
+
+        def wrap(*a, __orig=orig, **k):
+            if str(k.get("device", "")).startswith("cuda"):
+                k.pop("device")
+            return __orig(*a, **k)
+
+        setattr(torch, fn, wrap)
+
+
+def load_file(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def main():
+    _stub(["open3d", "omegaconf", "pytorch3d", "pytorch3d.transforms", "pytorch3d.ops", "gsplat", "gsplat.rendering",
+           "gsplat.cuda", "gsplat.cuda._wrapper", "nvdiffrast", "nvdiffrast.torch", "imageio", "matplotlib",
+           "matplotlib.pyplot", "trimesh", "kornia", "third_party", "third_party.smplx", "third_party.smplx.smplx",
+           "third_party.smplx.smplx.lbs", "third_party.smplx.smplx.utils", "smplx", "tinycudann", "simple_knn",
+           "simple_knn._C", "diff_gauss", "plyfile", "lpips", "wandb", "pytorch_msssim", "mmcv"])
+    _cpuify()
+    g = torch.Generator().manual_seed(20240917)
+
+    # ---------------------------------------------------------------- SH (S3Gaussian/utils/sh_utils.py:57-112)
+    sh_utils = load_file("ref_sh_utils", f"{REF}/S3Gaussian/utils/sh_utils.py")
+    N = 64
+    dirs = torch.randn(N, 3, generator=g)
+    dirs_n = dirs / dirs.norm(dim=-1, keepdim=True)
+    coeffs = torch.randn(N, 16, 3, generator=g)  # [N,K,3] gsplat layout
+    sh_out = {f"deg{d}": sh_utils.eval_sh(d, coeffs.transpose(1, 2), dirs_n).numpy() for d in range(4)}
+    np.savez(f"{HERE}/sh_eval.npz", dirs=dirs.numpy(), coeffs=coeffs.numpy(), **sh_out)
+
+    # ---------------------------------------------------------------- quaternions
+    sys.path.insert(0, f"{REF}/OmniRe")
+    basics = importlib.import_module("models.gaussians.basics")
+    gu = load_file("ref_graphics_utils", f"{REF}/S3Gaussian/utils/graphics_utils.py")
+    q1 = torch.randn(50, 4, generator=g); q2 = torch.randn(50, 4, generator=g)
+    q2[:5] = q1[:5] + 1e-3 * torch.randn(5, 4, generator=g)       # near-parallel branch
+    q2[5:10] = -q1[5:10] + 0.3 * torch.randn(5, 4, generator=g)   # negative-dot branch
+    np.savez(f"{HERE}/quat.npz", q1=q1.numpy(), q2=q2.numpy(),
+             rotmat=basics.quat_to_rotmat(q1.clone()).numpy(),
+             mult=basics.quat_mult(q1.clone(), q2.clone()).numpy(),
+             slerp=basics.interpolate_quats(q1.clone(), q2.clone()).numpy(),
+             bqm=gu.batch_quaternion_multiply(q1.clone(), q2.clone()).numpy())
+
+    # ---------------------------------------------------------------- EMD rigid (OmniRe/models/nodes/rigid.py)
+    basics.spherical_harmonics = lambda deg, d, c: sh_utils.eval_sh(deg, c.transpose(1, 2), d / d.norm(dim=-1, keepdim=True))
+    rigid_mod = importlib.import_module("models.nodes.rigid")
+    rigid_mod.spherical_harmonics = basics.spherical_harmonics
+    from emd_b200 import scenes
+    rs = scenes.rigid_nodes(3, 40, g, num_frames=12)
+    rs.instances_quats = rs.instances_quats + 0.05 * torch.randn(rs.instances_quats.shape, generator=g)
+    rs.point_ids[rs.point_ids == 2] = 1  # instance 2 owns no points: the NaN-skip path (rigid.py:528, :559)
+    node = object.__new__(rigid_mod.RigidNodes)
+    torch.nn.Module.__init__(node)
+    P = torch.nn.Parameter
+    node._means, node._quats, node._scales = P(rs.means.clone()), P(rs.quats.clone()), P(rs.scales.clone())
+    node._opacities, node._features_dc, node._features_rest = P(rs.opacities.clone()), P(rs.features_dc.clone()), P(rs.features_rest.clone())
+    node._embeddings, node.weight = P(rs.embeddings.clone()), P(rs.weight.clone())
+    node.point_ids = rs.point_ids.clone()
+    node.instances_quats, node.instances_trans = P(rs.instances_quats.clone()), P(rs.instances_trans.clone())
+    node.instances_fv = rs.instances_fv.clone()
+    node.instances_size = torch.tensor([[4.6, 2.0, 1.6]]).repeat(3, 1)
+    for nm, out in (("rot_c", 1), ("rot_f", 1), ("trans_c", 3), ("trans_f", 3)):
+        lin = torch.nn.Linear(36, out)
+        lin.weight.data.copy_(rs.track[nm + "_w"]); lin.bias.data.copy_(rs.track[nm + "_b"])
+        setattr(node, "track_" + nm, lin)
+    node.temporal_embedding_dim, node.gaussian_embedding_dim = 32, 4
+    node.max_embeddings, node.min_embeddings, node.c2f_temporal_iter = 150, 30, 20000
+    for flag in ("no_temporal_embedding_dim", "no_gaussian_embedding_dim", "no_coarse_deform", "no_fine_deform",
+                 "no_c2f_temporal_embedding", "no_apply_embed_shs", "no_apply_embed_track"):
+        setattr(node, flag, False)
+    node.ball_gaussians, node.gaussian_2d = False, False
+    node.ctrl_cfg = types.SimpleNamespace(sh_degree_interval=1000, sh_degree=3)
+    node.device = torch.device("cpu")
+    out = dict(means=rs.means, quats=rs.quats, scales=rs.scales, opacities=rs.opacities, features_dc=rs.features_dc,
+               features_rest=rs.features_rest, embeddings=rs.embeddings, point_ids=rs.point_ids, weight=rs.weight,
+               instances_quats=rs.instances_quats, instances_trans=rs.instances_trans,
+               instances_fv=rs.instances_fv, **{"track_" + k: v for k, v in rs.track.items()})
+    out = {k: v.numpy() for k, v in out.items()}
+    cam = types.SimpleNamespace(camtoworlds=torch.eye(4))
+    cam.camtoworlds[:3, 3] = torch.tensor([0.3, -0.2, 1.6])
+    cases = [(0, 0, False), (5, 3500, False), (11, 20000, False), (6, 12000, True), (3, 31000, False)]
+    out["cases"] = np.array([(f, s, int(t)) for f, s, t in cases])
+    with torch.no_grad():
+        for ci, (frame, step, test_set) in enumerate(cases):
+            node.cur_frame, node.step, node.in_test_set = frame, step, test_set
+            tnorm = torch.tensor([[frame / (12 - 1)]]).float()
+            out[f"c{ci}_temb_coarse"] = node.get_temporal_embed(tnorm, 30, weight=node.weight[0]).numpy()
+            cur = node.int_lininterp(step, 30, 150, 20000)
+            out[f"c{ci}_temb_fine"] = node.get_temporal_embed(tnorm, cur, weight=node.weight[0]).numpy()
+            for ins in (0, 1):
+                emb = node._embeddings[(node.point_ids == ins).squeeze(1), :]
+                out[f"c{ci}_rot_off_{ins}"] = node.embedding_track_rot_offset(frame, 0, 11, emb, node.weight[ins]).numpy()
+                out[f"c{ci}_trans_off_{ins}"] = node.embedding_track_trans_offset(frame, 0, 11, emb, node.weight[ins]).numpy()
+            out[f"c{ci}_world_means"] = node.transform_means(node._means).numpy()
+            out[f"c{ci}_world_quats"] = node.transform_quats(node._quats).numpy()
+            gs = node.get_gaussians(cam)
+            for k, v in gs.items():
+                out[f"c{ci}_gs{k}"] = v.numpy()
+    np.savez(f"{HERE}/emd_rigid.npz", cam_pos=cam.camtoworlds[:3, 3].numpy(), **out)
+
+    # ---------------------------------------------------------------- EMD SMPL joint offsets (smpl.py:401-436)
+    # (the skinning half needs SMPL_NEUTRAL.pkl + smplx, absent: only the EMD head is pinned here)
+    try:
+        smpl_mod = importlib.import_module("models.nodes.smpl")
+        snode = object.__new__(smpl_mod.SMPLNodes)
+        torch.nn.Module.__init__(snode)
+        for flag in ("no_temporal_embedding_dim", "no_gaussian_embedding_dim", "no_coarse_deform", "no_fine_deform",
+                     "no_c2f_temporal_embedding"):
+            setattr(snode, flag, False)
+        snode.temporal_embedding_dim, snode.max_embeddings, snode.c2f_temporal_iter = 32, 150, 20000
+        cw, cb = 0.05 * torch.randn(24, 36, generator=g), 0.05 * torch.randn(24, generator=g)
+        fw, fb = 0.05 * torch.randn(24, 36, generator=g), 0.05 * torch.randn(24, generator=g)
+        snode.track_smpl_c, snode.track_smpl_f = torch.nn.Linear(36, 24), torch.nn.Linear(36, 24)
+        snode.track_smpl_c.weight.data.copy_(cw); snode.track_smpl_c.bias.data.copy_(cb)
+        snode.track_smpl_f.weight.data.copy_(fw); snode.track_smpl_f.bias.data.copy_(fb)
+        emb = 0.1 * torch.randn(77, 4, generator=g)
+        table = torch.randn(150, 32, generator=g) * (0.01 / math.sqrt(32))
+        res = {}
+        with torch.no_grad():
+            for ci, (frame, step) in enumerate([(0, 0), (4, 9000), (9, 25000)]):
+                snode.step = step
+                res[f"c{ci}"] = snode.embedding_track_smpl_offset(frame, 0, 9, emb, table).numpy()
+        np.savez(f"{HERE}/emd_smpl_offsets.npz", c_w=cw.numpy(), c_b=cb.numpy(), f_w=fw.numpy(), f_b=fb.numpy(),
+                 embeddings=emb.numpy(), table=table.numpy(), cases=np.array([(0, 0), (4, 9000), (9, 25000)]), **res)
+    except Exception as e:  # noqa: BLE001
+        print("SMPL offsets golden skipped:", repr(e))
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,83 @@
+"""CPU: pin the oracle against golden vectors produced by the REFERENCE's own Python
+(tests/golden/make_golden.py ran OmniRe/models/nodes/{rigid,smpl}.py, models/gaussians/basics.py,
+S3Gaussian/utils/{sh_utils,graphics_utils}.py in the build container)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def test_sh_eval_golden():
+    from oracle import sh as SH
+    z = np.load(f"{G}/sh_eval.npz")
+    for d in range(4):
+        out = SH.spherical_harmonics(d, _t(z["dirs"]), _t(z["coeffs"]))
+        assert torch.allclose(out, _t(z[f"deg{d}"]), rtol=1e-5, atol=1e-6), d
+
+
+def test_quaternion_golden():
+    from oracle import quat as Q
+    z = np.load(f"{G}/quat.npz")
+    q1, q2 = _t(z["q1"]), _t(z["q2"])
+    assert torch.allclose(Q.quat_to_rotmat(q1), _t(z["rotmat"]), atol=1e-6)
+    assert torch.allclose(Q.quat_mult(q1, q2), _t(z["mult"]), atol=1e-6)
+    assert torch.allclose(Q.interpolate_quats(q1, q2), _t(z["slerp"]), atol=2e-6)
+    assert torch.allclose(Q.batch_quaternion_multiply(q1, q2), _t(z["bqm"]), atol=1e-6)
+
+
+def _rigid_from_golden(z):
+    from oracle import emd_rigid as ER
+    return ER.RigidEMD(point_ids=_t(z["point_ids"])[:, 0], embeddings=_t(z["embeddings"]), weight=_t(z["weight"]),
+                       instances_quats=_t(z["instances_quats"]), instances_trans=_t(z["instances_trans"]),
+                       instances_fv=_t(z["instances_fv"]),
+                       **{k: _t(z["track_" + k]) for k in ("rot_c_w", "rot_c_b", "rot_f_w", "rot_f_b", "trans_c_w",
+                                                           "trans_c_b", "trans_f_w", "trans_f_b")})
+
+
+def test_emd_rigid_golden():
+    """get_temporal_embed, track offsets, transform_means/quats, get_gaussians of RigidNodes (incl. the
+    coarse-to-fine schedule, the eval-time neighbour interpolation and the empty-instance NaN skip)."""
+    from oracle import emd_rigid as ER
+    z = np.load(f"{G}/emd_rigid.npz")
+    p = _rigid_from_golden(z)
+    F = p.num_frames
+    for ci, (frame, step, test_set) in enumerate(z["cases"].tolist()):
+        t = frame / (F - 1)
+        assert torch.allclose(ER.get_temporal_embed(t, 30, p.weight[0]), _t(z[f"c{ci}_temb_coarse"]), atol=1e-7)
+        cur = ER.int_lininterp(step, 30, 150, 20000)
+        assert torch.allclose(ER.get_temporal_embed(t, cur, p.weight[0]), _t(z[f"c{ci}_temb_fine"]), atol=1e-7)
+        dtrans, qoff, ok_t, ok_q = ER.track_offsets(p, frame, step)
+        for ins in (0, 1):
+            assert torch.allclose(dtrans[ins], _t(z[f"c{ci}_trans_off_{ins}"]), atol=1e-6)
+            assert torch.allclose(qoff[ins], _t(z[f"c{ci}_rot_off_{ins}"]), atol=1e-6)
+        assert not bool(ok_t[2]) and not bool(ok_q[2])  # instance 2 owns no points
+        wm = ER.transform_means(p, _t(z["means"]), frame, step, in_test_set=bool(test_set))
+        wq = ER.transform_quats(p, _t(z["quats"]), frame, step)
+        assert torch.allclose(wm, _t(z[f"c{ci}_world_means"]), rtol=1e-5, atol=1e-5), ci
+        assert torch.allclose(wq, _t(z[f"c{ci}_world_quats"]), atol=2e-6), ci
+        gs = ER.get_gaussians(p, _t(z["means"]), _t(z["quats"]), _t(z["scales"]), _t(z["opacities"]),
+                              _t(z["features_dc"]), _t(z["features_rest"]), frame, step, _t(z["cam_pos"]),
+                              in_test_set=bool(test_set))
+        for k, v in gs.items():
+            assert torch.allclose(v, _t(z[f"c{ci}_gs{k}"]), rtol=1e-5, atol=2e-5), (ci, k)
+
+
+def test_emd_smpl_offsets_golden():
+    from oracle import emd_smpl as ES
+    z = np.load(f"{G}/emd_smpl_offsets.npz")
+    n = z["embeddings"].shape[0]
+    p = ES.SMPLEMD(point_ids=torch.zeros(n, dtype=torch.long), embeddings=_t(z["embeddings"]),
+                   weight=_t(z["table"])[None], instances_quats=None, smpl_quats=None,
+                   instances_trans=torch.zeros(10, 1, 3), instances_fv=None, smpl_c_w=_t(z["c_w"]),
+                   smpl_c_b=_t(z["c_b"]), smpl_f_w=_t(z["f_w"]), smpl_f_b=_t(z["f_b"]), J_canonical=None, A0_inv=None,
+                   W=torch.zeros(1, n, 24))
+    for ci, (frame, step) in enumerate(z["cases"].tolist()):
+        off = ES.track_smpl_offset(p, 0, frame, step)
+        assert torch.allclose(off, _t(z[f"c{ci}"]), atol=1e-6), ci

@@ -1,0 +1,165 @@
+"""Write include/emd_b200.h from the `extern "C"` definitions in emd_b200/csrc/*.cu plus the
+hand-written per-function documentation below (what each entry point replaces in the reference,
+file:line).  `python tools/gen_header.py --write`; tests/test_cpu_abi.py checks the header is current."""
+import re
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+GROUPS = [
+    ("Library plumbing", ["emd_abi_version", "emd_device_check", "emd_last_error_string", "emd_launch_count",
+                          "emd_kernel_id_count", "emd_kernel_name", "emd_profile_enable", "emd_profile_collect"]),
+    ("K1a  EMD motion-embedding deformation, rigid nodes", ["emd_rigid_chunk_size", "emd_rigid_param_count",
+                                                          "emd_rigid_deform_fwd", "emd_rigid_deform_bwd"]),
+    ("K1c  EMD motion-embedding deformation, SMPL nodes", ["emd_smpl_param_count", "emd_smpl_max_chunks",
+                                                         "emd_smpl_reduce_width", "emd_smpl_deform_fwd",
+                                                         "emd_smpl_deform_bwd"]),
+    ("K1b  spherical harmonics + node activations", ["emd_sh_fwd", "emd_sh_bwd", "emd_activate_fwd", "emd_activate_bwd"]),
+    ("K1d  S3Gaussian EMD deformation MLP", ["emd_mlp_workspace_bytes", "emd_s3g_mlp_fwd", "emd_s3g_mlp_bwd"]),
+    ("K2   projection", ["emd_projection_fwd", "emd_projection_bwd", "emd_dg_preprocess_fwd", "emd_dg_preprocess_bwd"]),
+    ("K3   tile intersection", ["emd_scan_workspace_bytes", "emd_cumsum_i32_i64", "emd_exclusive_scan_u32",
+                                "emd_isect_emit", "emd_dg_isect_emit"]),
+    ("K4   radix sort", ["emd_radix_sort_workspace_bytes", "emd_radix_sort_pairs"]),
+    ("K5   tile ranges", ["emd_isect_offsets", "emd_tile_order"]),
+    ("K6/K7 rasterization", ["emd_raster_pack", "emd_rasterize_fwd", "emd_rasterize_bwd_workspace_bytes",
+                             "emd_rasterize_bwd"]),
+]
+
+DOC = {
+    "emd_abi_version": "ABI revision of this header (bumped on any signature change).",
+    "emd_device_check": "0 iff the current CUDA device can run this library (compute capability 10.x).",
+    "emd_last_error_string": "Text of the last error raised on the calling thread (thread-local).",
+    "emd_launch_count": "Number of kernels the library has launched in this process (bench.py's gpu_launches).",
+    "emd_kernel_id_count": "Number of kernel ids the profiler distinguishes.",
+    "emd_kernel_name": "Name of kernel id `id`.",
+    "emd_profile_enable": "When on, every kernel launch is bracketed by CUDA events on its own stream.",
+    "emd_profile_collect": "Synchronise recorded events; ADD durations (ms) / launch counts into the [emd_kernel_id_count()] arrays.",
+    "emd_rigid_chunk_size": "Points per (instance, chunk) block of the rigid kernels (sizes the scratch buffers).",
+    "emd_rigid_param_count": "Floats in the flat track_* gradient: 2*(d+g+1) + 2*(3*(d+g)+3).",
+    "emd_rigid_deform_fwd": "Replaces RigidNodes.transform_means + transform_quats incl. the per-instance Python loops "
+                            "(OmniRe/models/nodes/rigid.py:478-568; embedding_track_{rot,trans}_offset :203-246; "
+                            "get_temporal_embed/query_time :150-201).  heads = HOST array of 8 DEVICE pointers "
+                            "{rot_c_w, rot_c_b, rot_f_w, rot_f_b, trans_c_w, trans_c_b, trans_f_w, trans_f_b}.  "
+                            "order/seg_start: points stably sorted by instance + the I+1 boundaries.",
+    "emd_rigid_deform_bwd": "VJP of emd_rigid_deform_fwd (what torch.autograd derives from rigid.py:478-568).  "
+                            "v_table must be zero-filled by the caller.",
+    "emd_smpl_param_count": "Floats in the flat track_smpl_{c,f} gradient: 2*(24*(d+g)+24).",
+    "emd_smpl_max_chunks": "Chunks per SMPL instance of V points.",
+    "emd_smpl_reduce_width": "Floats per (instance, chunk) backward partial (24x12 + 3).",
+    "emd_smpl_deform_fwd": "Replaces SMPLNodes.transform_means_and_quats (OmniRe/models/nodes/smpl.py:438-532; "
+                           "embedding_track_smpl_offset :401-436) + SMPLTemplate.forward's chain "
+                           "(OmniRe/models/human_body.py:158-172) + pytorch3d matrix_to_quaternion (smpl.py:522).  "
+                           "heads = HOST array of 4 DEVICE pointers {smpl_c_w, smpl_c_b, smpl_f_w, smpl_f_b}.",
+    "emd_smpl_deform_bwd": "VJP of emd_smpl_deform_fwd.  v_table must be zero-filled by the caller.",
+    "emd_sh_fwd": "gsplat.cuda._wrapper.spherical_harmonics (OmniRe/models/gaussians/basics.py:16; calls vanilla.py:388, "
+                  "rigid.py:584, smpl.py:555): dirs[N,3] (normalised inside), coeffs[N,K,3] -> out[N,3].",
+    "emd_sh_bwd": "VJP of emd_sh_fwd w.r.t. the coefficients (the reference passes detached directions).",
+    "emd_activate_fwd": "Tail of {VanillaGaussians,RigidNodes,SMPLNodes}.get_gaussians (vanilla.py:378-414, rigid.py:578-603, "
+                        "smpl.py:549-576): view dir, SH -> clamp(+0.5,0,1) for C cameras, sigmoid(opacity) x frame-valid "
+                        "mask, exp(scale), normalize(quat).  cam_pos_host = HOST pointer to C x 3 floats.",
+    "emd_activate_bwd": "VJP of emd_activate_fwd.",
+    "emd_projection_fwd": "gsplat fully_fused_projection (pinhole, quats+scales) as reached from "
+                          "OmniRe/models/trainers/base.py:393; also writes tiles_per_gauss (first pass of isect_tiles).",
+    "emd_projection_bwd": "VJP of emd_projection_fwd w.r.t. means, quats, scales.",
+    "emd_scan_workspace_bytes": "Workspace bytes of the scans for n elements.",
+    "emd_cumsum_i32_i64": "Inclusive cumulative sum (torch.cumsum of tiles_per_gauss in gsplat's isect_tiles); total -> device scalar.",
+    "emd_exclusive_scan_u32": "Exclusive scan (radix-sort tables); in-place allowed.",
+    "emd_isect_emit": "gsplat isect_tiles second pass: key = cam << (32+tile_n_bits) | tile << 32 | float_bits(depth), value = cam*N+gid.",
+    "emd_radix_sort_workspace_bytes": "Workspace bytes of emd_radix_sort_pairs for n pairs.",
+    "emd_radix_sort_pairs": "cub::DeviceRadixSort::SortPairs as gsplat/diff_gauss call it: stable, ascending, bits [begin,end). "
+                            "*result_buffer = 0/1 tells which buffer holds the result.",
+    "emd_isect_offsets": "gsplat isect_offset_encode / diff_gauss identifyTileRanges: first sorted index of every (camera, tile).",
+    "emd_tile_order": "Tile ids ordered longest-list-first (scheduling hint for rasterize_fwd/bwd; results do not depend on it).",
+    "emd_raster_pack": "Packs per-(camera,Gaussian) mean2d/conic/opacity/colour(+depth) into three float4 records for the compositor.",
+    "emd_rasterize_fwd": "gsplat rasterize_to_pixels forward (RGB / +depth / expected depth, alpha, last_ids) "
+                         "(reference call OmniRe/models/trainers/base.py:393-408).",
+    "emd_rasterize_bwd_workspace_bytes": "Workspace bytes of emd_rasterize_bwd for P intersections.",
+    "emd_rasterize_bwd": "gsplat rasterize_to_pixels backward: v_means2d (+abs), v_conics, v_colors, v_depths, v_opacities; "
+                         "deterministic (no float atomics).",
+}
+
+
+def prototypes():
+    out = {}
+    for f in sorted((ROOT / "emd_b200" / "csrc").glob("*.cu")):
+        src = f.read_text()
+        for m in re.finditer(r'^extern "C" ([^{;]*?)\s*\{', src, re.S | re.M):
+            p = " ".join(m.group(1).split())
+            name = re.search(r"(\w+)\s*\(", p).group(1)
+            out[name] = (p, f.name)
+    return out
+
+
+def wrap(text, width=100, indent=" * "):
+    words, lines, cur = text.split(), [], ""
+    for w in words:
+        if len(cur) + len(w) + 1 > width:
+            lines.append(cur)
+            cur = w
+        else:
+            cur = (cur + " " + w).strip()
+    if cur:
+        lines.append(cur)
+    return "\n".join(indent + ln for ln in lines)
+
+
+def render():
+    protos = prototypes()
+    out = ['''/* emd_b200.h -- C ABI of libemd_b200.so (sm_100a).  GENERATED by tools/gen_header.py from the
+ * extern "C" definitions in emd_b200/csrc; do not edit the prototypes by hand.
+ *
+ * Boundary contract (SURVEY.md section 8b):
+ *  - plain pointers and sizes only; every buffer (inputs, outputs, workspace) is device memory owned by the
+ *    caller (PyTorch in the reference-side bindings); the library never allocates, frees or retains pointers;
+ *  - every function returns 0 on success or a negative code (EMD_ERR_*); the text is emd_last_error_string();
+ *    no exception crosses the boundary;
+ *  - re-entrant, no implicit device synchronisation; kernels are enqueued on the cudaStream_t passed last
+ *    (backward runs on autograd's thread -- pass torch.cuda.current_stream().cuda_stream);
+ *  - tensors are dense row-major fp32 unless stated; [N,4] quaternion arrays must be 16-byte aligned;
+ *  - there is no CPU implementation behind these symbols.
+ */
+#ifndef EMD_B200_H
+#define EMD_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#include <cuda_runtime_api.h>
+
+#define EMD_OK 0
+#define EMD_ERR_BAD_ARG -1
+#define EMD_ERR_ALIGN -2
+#define EMD_ERR_WORKSPACE -3
+#define EMD_ERR_CUDA -4
+#define EMD_ERR_UNSUPPORTED -5
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+''']
+    seen = set()
+    for title, names in GROUPS:
+        have = [n for n in names if n in protos]
+        if not have:
+            continue
+        out.append(f"/* ---- {title} {'-' * max(4, 90 - len(title))} */\n")
+        for n in have:
+            seen.add(n)
+            if n not in DOC:
+                raise SystemExit(f"tools/gen_header.py: no DOC entry for {n}")
+            out.append("/*\n" + wrap(DOC[n]) + f"\n * (defined in emd_b200/csrc/{protos[n][1]})\n */")
+            out.append(protos[n][0] + ";\n")
+    missing = sorted(set(protos) - seen)
+    if missing:
+        raise SystemExit(f"tools/gen_header.py: exported but not listed in GROUPS: {missing}")
+    out.append("#ifdef __cplusplus\n}\n#endif\n#endif /* EMD_B200_H */\n")
+    return "\n".join(out)
+
+
+if __name__ == "__main__":
+    text = render()
+    if "--write" in sys.argv:
+        (ROOT / "include").mkdir(exist_ok=True)
+        (ROOT / "include" / "emd_b200.h").write_text(text)
+        print("wrote include/emd_b200.h")
+    else:
+        print(text)
