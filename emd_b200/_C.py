@@ -40,7 +40,12 @@ _SIGS = {
     "emd_radix_sort_pairs": (c_int, [P, P, P, P, c_int64, c_int, c_int, P, c_size_t, ctypes.POINTER(c_int), P]),
     "emd_raster_pack": (c_int, [P, P, P, c_int, P, c_int, c_int, P, c_int, P, c_int64, c_int64, P, P]),
     "emd_tile_order": (c_int, [P, c_int64, c_int64, P, P]),
-    "emd_rasterize_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
+    "emd_rasterize_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
+    "emd_dg_preprocess_fwd": (c_int, [P] * 4 + [ctypes.POINTER(c_float)] * 3 + [c_float, c_float, c_int, c_int, c_float,
+                                                                              c_int, c_int, c_int64] + [P] * 7 + [P]),
+    "emd_dg_preprocess_bwd": (c_int, [P] * 4 + [ctypes.POINTER(c_float)] * 3 + [c_float, c_float, c_int, c_int, c_float,
+                                                                              c_int, c_int, c_int64] + [P] * 10 + [P]),
+    "emd_dg_isect_emit": (c_int, [P, P, P, P, c_int64, c_int, c_int, P, P, P]),
     "emd_rasterize_bwd_workspace_bytes": (c_size_t, [c_int64]),
     "emd_sh_fwd": (c_int, [c_int, P, P, c_int64, c_int, P, P]),
     "emd_sh_bwd": (c_int, [c_int, P, c_int64, c_int, P, P, P]),
@@ -58,7 +63,7 @@ _SIGS = {
     "emd_smpl_deform_fwd": (c_int, [P] * 12 + [c_int] * 5 + [c_float, c_int, c_int] + [P] * 5 + [P]),
     "emd_smpl_deform_bwd": (c_int, [P] * 11 + [c_int] * 5 + [c_float, c_int, c_int] + [P] * 14 + [P]),
     "emd_rasterize_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
-                                  P, P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
+                                  c_int, P, P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
 }
 
 

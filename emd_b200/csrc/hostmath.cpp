@@ -110,3 +110,29 @@ extern "C" void emd_host_rigid_instance_bwd(const float* table, int I, int E, in
     }
     delete[] part;
 }
+
+// ---- diff_gauss preprocess (dg_math.cuh) ---------------------------------------------------------
+#include "dg_math.cuh"
+
+extern "C" void emd_host_dg_preprocess_fwd(const float* means, const float* scales, const float* rots,
+                                           const float* viewmatrix, const float* projmatrix, float tanfovx,
+                                           float tanfovy, int W, int H, float mod, int64_t N, int32_t* radii,
+                                           float* means2d, float* depths, float* conics, int32_t* rects) {
+    DgCam cam;
+    make_dg_cam(viewmatrix, projmatrix, tanfovx, tanfovy, W, H, mod, cam);
+    for (int64_t n = 0; n < N; ++n) {
+        float s_mod[3], R[9], M[9], S[6];
+        for (int k = 0; k < 3; ++k) s_mod[k] = c_mul(mod, scales[n * 3 + k]);
+        dg_quat_to_rotmat_c(rots + n * 4, R);
+        covar_world_c(R, s_mod, M, S);
+        DgFwd o;
+        memset(&o, 0, sizeof(o));
+        dg_project_c(means + n * 3, S, cam, o);
+        const bool vis = o.f.radius > 0;
+        radii[n] = vis ? o.f.radius : 0;
+        means2d[n * 2] = vis ? o.f.m2x : 0.f; means2d[n * 2 + 1] = vis ? o.f.m2y : 0.f;
+        depths[n] = vis ? o.f.z : 0.f;
+        conics[n * 3] = vis ? o.f.conic_a : 0.f; conics[n * 3 + 1] = vis ? o.f.conic_b : 0.f; conics[n * 3 + 2] = vis ? o.f.conic_c : 0.f;
+        rects[n * 4] = vis ? o.x0 : 0; rects[n * 4 + 1] = vis ? o.y0 : 0; rects[n * 4 + 2] = vis ? o.x1 : 0; rects[n * 4 + 3] = vis ? o.y1 : 0;
+    }
+}

@@ -16,6 +16,16 @@
 // contiguous run.  No global float atomics anywhere; results are bit-reproducible.
 #include "common.cuh"
 #include "proj_math.cuh"
+#include "dg_math.cuh"
+
+// flavour of the compositing rule: gsplat (pixel centre +0.5, alpha cap 0.999, stop at T <= 1e-4, gsplat tile
+// rect) or diff_gauss / Inria (integer pixel coordinates, cap 0.99, stop at T < 1e-4, getRect)
+struct RasterCfg {
+    float px_off;
+    float alpha_max;
+    int strict_stop;
+    int dg_rect;
+};
 
 namespace {
 
@@ -59,7 +69,7 @@ __global__ void raster_pack_kernel(const float* __restrict__ means2d, const floa
 __global__ void __launch_bounds__(RB) raster_fwd_kernel(
     const float4* __restrict__ recs, const int32_t* __restrict__ tile_offsets, const int32_t* __restrict__ flatten_ids,
     const int32_t* __restrict__ tile_order, int64_t P, int C, int width, int height, int tile_w, int tile_h, int CH,
-    int ed_mode, const float* __restrict__ backgrounds, float* __restrict__ out_colors,
+    int ed_mode, RasterCfg cfg, const float* __restrict__ backgrounds, float* __restrict__ out_colors,
     float* __restrict__ out_alphas, int32_t* __restrict__ last_ids) {
     __shared__ float4 s_r0[RB];
     __shared__ float4 s_r1[RB];
@@ -74,7 +84,7 @@ __global__ void __launch_bounds__(RB) raster_fwd_kernel(
     const int tr = threadIdx.y * EMD_TILE + threadIdx.x;
     const int i = tile_y * EMD_TILE + threadIdx.y;
     const int j = tile_x * EMD_TILE + threadIdx.x;
-    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const float px = (float)j + cfg.px_off, py = (float)i + cfg.px_off;
     const bool inside = i < height && j < width;
     bool done = !inside;
 
@@ -112,14 +122,14 @@ __global__ void __launch_bounds__(RB) raster_fwd_kernel(
                 const float4 r1 = s_r1[tt];
                 const float dx = r0.x - px, dy = r0.y - py;
                 const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
-                alpha[u] = fminf(0.999f, r0.z * __expf(-sigma));
+                alpha[u] = fminf(cfg.alpha_max, r0.z * __expf(-sigma));
                 ok[u] = (t + u < batch_size) && !(sigma < 0.f || alpha[u] < ALPHA_MIN);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (!ok[u] || done) continue;
                 const float next_T = T * (1.0f - alpha[u]);
-                if (next_T <= 1e-4f) { done = true; continue; }
+                if (cfg.strict_stop ? (next_T < 1e-4f) : (next_T <= 1e-4f)) { done = true; continue; }
                 const float vis = alpha[u] * T;
                 const float4 r1 = s_r1[t + u];
                 const float2 r2 = s_r2[t + u];
@@ -179,7 +189,7 @@ __device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
 __global__ void __launch_bounds__(RB) raster_bwd_kernel(
     const float4* __restrict__ recs, const int32_t* __restrict__ tile_offsets, const int32_t* __restrict__ flatten_ids,
     const int32_t* __restrict__ tile_order, const int32_t* __restrict__ radii, const int64_t* __restrict__ cum_tiles,
-    int64_t P, int C, int width, int height, int tile_w, int tile_h, int CH, int ed_mode,
+    int64_t P, int C, int width, int height, int tile_w, int tile_h, int CH, int ed_mode, RasterCfg cfg,
     const float* __restrict__ backgrounds,
     const float* __restrict__ out_colors, const float* __restrict__ out_alphas, const int32_t* __restrict__ last_ids,
     const float* __restrict__ v_out_colors, const float* __restrict__ v_out_alphas, float* __restrict__ partials,
@@ -200,7 +210,7 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
     const int lane = tr & 31, warp = tr >> 5;
     const int i = tile_y * EMD_TILE + threadIdx.y;
     const int j = tile_x * EMD_TILE + threadIdx.x;
-    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const float px = (float)j + cfg.px_off, py = (float)i + cfg.px_off;
     const bool inside = i < height && j < width;
     const int64_t pix = ((int64_t)cam * height + min(i, height - 1)) * width + min(j, width - 1);
 
@@ -260,7 +270,8 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
             const float4 r2 = __ldg(recs + g * 3 + 2);
             s_r2[tr] = make_float2(r2.x, r2.y);
             int x0, y0, x1, y1;
-            tile_rect_c(r0.x, r0.y, radii[g], tile_w, tile_h, x0, y0, x1, y1);
+            if (cfg.dg_rect) tile_rect_dg(r0.x, r0.y, radii[g], tile_w, tile_h, x0, y0, x1, y1);
+            else tile_rect_c(r0.x, r0.y, radii[g], tile_w, tile_h, x0, y0, x1, y1);
             const int64_t base = g == 0 ? 0 : cum_tiles[g - 1];
             s_slot[tr] = (uint32_t)(base + (int64_t)(tile_y - y0) * (x1 - x0) + (tile_x - x0));
         }
@@ -280,7 +291,7 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
                     dx = r0.x - px; dy = r0.y - py;
                     const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
                     vis = __expf(-sigma);
-                    alpha = fminf(0.999f, r0.z * vis);
+                    alpha = fminf(cfg.alpha_max, r0.z * vis);
                     if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
                 }
                 if (!__any_sync(0xffffffffu, valid)) continue;
@@ -302,7 +313,7 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
                     v_alpha += T_final * ra * v_a;
                     v_alpha -= T_final * ra * bg_dot;
                     const float opac = r0.z;
-                    if (opac * vis <= 0.999f) {
+                    if (opac * vis <= cfg.alpha_max) {
                         const float v_sigma = -opac * vis * v_alpha;
                         v[4] = 0.5f * v_sigma * dx * dx;
                         v[5] = v_sigma * dx * dy;
@@ -430,8 +441,9 @@ extern "C" int emd_tile_order(const int32_t* tile_offsets, int64_t P, int64_t n_
 
 extern "C" int emd_rasterize_fwd(const float* recs, const int32_t* tile_offsets, const int32_t* flatten_ids,
                                  const int32_t* tile_order, int64_t P, int64_t C, int width, int height, int tile_w, int tile_h, int channels,
-                                 int ed_mode, const float* backgrounds, float* out_colors, float* out_alphas,
-                                 int32_t* last_ids, cudaStream_t stream) {
+                                 int ed_mode, int flavour, const float* backgrounds, float* out_colors,
+                                 float* out_alphas, int32_t* last_ids, cudaStream_t stream) {
+    const RasterCfg cfg = flavour == 1 ? RasterCfg{0.0f, 0.99f, 1, 1} : RasterCfg{0.5f, 0.999f, 0, 0};
     EMD_CHECK_ARG(channels >= 1 && channels <= 4, "rasterize_fwd: channels must be 1..4");
     EMD_CHECK_ARG(C >= 1 && C * tile_w * tile_h < ((int64_t)1 << 31), "rasterize_fwd: grid too large");
     EMD_CHECK_ARG(tile_w == (width + EMD_TILE - 1) / EMD_TILE && tile_h == (height + EMD_TILE - 1) / EMD_TILE,
@@ -442,7 +454,7 @@ extern "C" int emd_rasterize_fwd(const float* recs, const int32_t* tile_offsets,
     }
     dim3 grid((unsigned)(C * tile_w * tile_h)), block(EMD_TILE, EMD_TILE, 1);
     EMD_LAUNCH(EK_RASTER_FWD, stream, raster_fwd_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, tile_order, P,
-                                                  (int)C, width, height, tile_w, tile_h, channels, ed_mode,
+                                                  (int)C, width, height, tile_w, tile_h, channels, ed_mode, cfg,
                                                   backgrounds, out_colors, out_alphas, last_ids));
     EMD_CHECK_LAUNCH("rasterize_fwd");
     return EMD_OK;
@@ -456,7 +468,7 @@ extern "C" size_t emd_rasterize_bwd_workspace_bytes(int64_t P) {
 
 extern "C" int emd_rasterize_bwd(const float* recs, const int32_t* tile_offsets, const int32_t* flatten_ids,
                                  const int32_t* tile_order, const int32_t* radii, const int64_t* cum_tiles, int64_t P, int64_t N, int64_t C,
-                                 int width, int height, int tile_w, int tile_h, int channels, int ed_mode,
+                                 int width, int height, int tile_w, int tile_h, int channels, int ed_mode, int flavour,
                                  const float* backgrounds, const float* out_colors, const float* out_alphas,
                                  const int32_t* last_ids, const float* v_out_colors, const float* v_out_alphas,
                                  int d_color, int with_depth, float* v_means2d, float* v_means2d_abs, float* v_conics,
@@ -464,6 +476,7 @@ extern "C" int emd_rasterize_bwd(const float* recs, const int32_t* tile_offsets,
                                  size_t ws_bytes, cudaStream_t stream) {
     EMD_CHECK_ARG(channels >= 1 && channels <= 4, "rasterize_bwd: channels must be 1..4");
     EMD_CHECK_ARG(d_color + (with_depth ? 1 : 0) == channels, "rasterize_bwd: channel bookkeeping mismatch");
+    const RasterCfg cfg = flavour == 1 ? RasterCfg{0.0f, 0.99f, 1, 1} : RasterCfg{0.5f, 0.999f, 0, 0};
     EMD_CHECK_ARG(P < ((int64_t)1 << 32), "rasterize_bwd: too many intersections");
     if (ws_bytes < emd_rasterize_bwd_workspace_bytes(P)) {
         emd_set_error("rasterize_bwd: workspace too small");
@@ -483,7 +496,7 @@ extern "C" int emd_rasterize_bwd(const float* recs, const int32_t* tile_offsets,
         dim3 grid((unsigned)(C * tile_w * tile_h)), block(EMD_TILE, EMD_TILE, 1);
         EMD_LAUNCH(EK_RASTER_BWD, stream, raster_bwd_kernel<<<grid, block, 0, stream>>>(
             reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, tile_order, radii, cum_tiles, P, (int)C, width,
-            height, tile_w, tile_h, channels, ed_mode, backgrounds, out_colors, out_alphas, last_ids, v_out_colors,
+            height, tile_w, tile_h, channels, ed_mode, cfg, backgrounds, out_colors, out_alphas, last_ids, v_out_colors,
             v_out_alphas, partials, touched));
     }
     EMD_LAUNCH(EK_RASTER_GATHER, stream, raster_gather_kernel<<<(unsigned)emd_cdiv(CN, 256), 256, 0, stream>>>(partials, touched, cum_tiles, CN, d_color,

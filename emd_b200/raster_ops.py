@@ -188,7 +188,7 @@ class _Rasterize(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, conics, colors, opacities, depths, backgrounds, radii, cum_tiles, isect_offsets,
-                flatten_ids, width, height, with_depth, ed_mode, absgrad):
+                flatten_ids, width, height, with_depth, ed_mode, absgrad, flavour=0):
         L = _C.lib()
         C, N = radii.shape
         dev = radii.device
@@ -216,13 +216,13 @@ class _Rasterize(torch.autograd.Function):
         _C.check(L.emd_tile_order(_C.ptr(isect_offsets, torch.int32), P, C * th * tw, _C.ptr(tile_order), _C.stream()),
                  "emd_tile_order")
         _C.check(L.emd_rasterize_fwd(_C.ptr(recs), _C.ptr(isect_offsets, torch.int32), _C.ptr(flatten_ids, torch.int32),
-                                     _C.ptr(tile_order), P, C, width, height, tw, th, CH, 1 if ed_mode else 0, _C.ptr(bg),
+                                     _C.ptr(tile_order), P, C, width, height, tw, th, CH, 1 if ed_mode else 0, int(flavour), _C.ptr(bg),
                                      _C.ptr(out_colors), _C.ptr(out_alphas), _C.ptr(last_ids), _C.stream()),
                  "emd_rasterize_fwd")
         ctx.save_for_backward(recs, isect_offsets, flatten_ids, radii, cum_tiles, bg if bg is not None else torch.empty(0, device=dev),
                               out_colors, out_alphas, last_ids, tile_order)
         ctx.cfg = (width, height, CH, d_color, bool(with_depth), bool(ed_mode), bool(absgrad), colors_per_cam,
-                   opac_per_cam, bg is not None)
+                   opac_per_cam, bg is not None, int(flavour))
         ctx.means2d_ref = means2d if absgrad else None
         ctx.mark_non_differentiable(last_ids)
         return out_colors, out_alphas, last_ids
@@ -231,7 +231,7 @@ class _Rasterize(torch.autograd.Function):
     def backward(ctx, v_colors_out, v_alphas_out, _v_last):
         L = _C.lib()
         recs, isect_offsets, flatten_ids, radii, cum_tiles, bg, out_colors, out_alphas, last_ids, tile_order = ctx.saved_tensors
-        width, height, CH, d_color, with_depth, ed_mode, absgrad, colors_per_cam, opac_per_cam, has_bg = ctx.cfg
+        width, height, CH, d_color, with_depth, ed_mode, absgrad, colors_per_cam, opac_per_cam, has_bg, flavour = ctx.cfg
         C, N = radii.shape
         dev = radii.device
         tw, th, _ = tile_grid(width, height)
@@ -248,7 +248,7 @@ class _Rasterize(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _C.check(L.emd_rasterize_bwd(
             _C.ptr(recs), _C.ptr(isect_offsets), _C.ptr(flatten_ids), _C.ptr(tile_order), _C.ptr(radii), _C.ptr(cum_tiles), P, N, C,
-            width, height, tw, th, CH, 1 if ed_mode else 0, _C.ptr(bg) if has_bg else None, _C.ptr(out_colors),
+            width, height, tw, th, CH, 1 if ed_mode else 0, flavour, _C.ptr(bg) if has_bg else None, _C.ptr(out_colors),
             _C.ptr(out_alphas), _C.ptr(last_ids), _C.ptr(v_colors_out), _C.ptr(v_alphas_out), d_color,
             1 if with_depth else 0, _C.ptr(v_means2d), _C.ptr(v_abs), _C.ptr(v_conics), _C.ptr(v_colors),
             _C.ptr(v_depths), _C.ptr(v_opac), _C.ptr(ws), ws_bytes, _C.stream()), "emd_rasterize_bwd")
@@ -265,10 +265,12 @@ class _Rasterize(torch.autograd.Function):
         if has_bg and ctx.needs_input_grad[5]:
             T_final = 1.0 - out_alphas  # [C,H,W,1]
             g_bg = (v_colors_out * T_final).sum(dim=(1, 2))
-        return (v_means2d, v_conics, g_colors, g_opac, v_depths, g_bg) + (None,) * 9
+        return (v_means2d, v_conics, g_colors, g_opac, v_depths, g_bg) + (None,) * 10
 
 
 def rasterize_to_pixels(means2d, conics, colors, opacities, depths, backgrounds, radii, cum_tiles, isect_offsets,
-                        flatten_ids, width, height, with_depth=False, ed_mode=False, absgrad=False):
+                        flatten_ids, width, height, with_depth=False, ed_mode=False, absgrad=False, flavour=0):
+    """flavour 0 = gsplat compositing rule, 1 = diff_gauss / Inria rule (see RasterCfg in rasterize.cu)."""
     return _Rasterize.apply(means2d, conics, colors, opacities, depths, backgrounds, radii, cum_tiles, isect_offsets,
-                            flatten_ids, int(width), int(height), bool(with_depth), bool(ed_mode), bool(absgrad))
+                            flatten_ids, int(width), int(height), bool(with_depth), bool(ed_mode), bool(absgrad),
+                            int(flavour))

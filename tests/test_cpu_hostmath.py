@@ -147,3 +147,29 @@ def test_rigid_instance_heads(hostlib, seed, step, empty):
     cnt = torch.stack([(p.point_ids == i).sum() for i in range(I)]).float()
     per_point = torch.nan_to_num(torch.from_numpy(v_me))[p.point_ids] / cnt[p.point_ids][:, None]
     close(per_point.numpy(), p.embeddings.grad, "embeddings")
+
+
+def test_dg_preprocess_bit_exact(hostlib):
+    """dg_math.cuh (diff_gauss front end) vs oracle/diff_gauss_ref.preprocess: radii, means, depth bits, tile rects."""
+    from oracle import diff_gauss_ref as DG
+    from tests.dg_util import s3g_camera
+    g = torch.Generator().manual_seed(4)
+    W, H, N = 960, 640, 50000
+    sc = scenes.simple_gaussians(N, g, W, H, depth=(0.05, 60.0))
+    rots = (sc["quats"] / sc["quats"].norm(dim=-1, keepdim=True)).contiguous()
+    cam = s3g_camera(15.0, W, H)
+    s = DG.Settings(H, W, cam["tanfovx"], cam["tanfovy"], torch.zeros(3), 0.9, cam["viewmatrix"], cam["projmatrix"], 0,
+                    cam["campos"])
+    radii, m2d, depths, conics, rect = DG.preprocess(sc["means"], sc["scales"], rots, s)
+    r2 = np.zeros(N, np.int32); m2 = np.zeros((N, 2), np.float32); d2 = np.zeros(N, np.float32)
+    c2 = np.zeros((N, 3), np.float32); rc = np.zeros((N, 4), np.int32)
+    f = hostlib.emd_host_dg_preprocess_fwd
+    f.argtypes = [P] * 5 + [ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int64] + [P] * 5
+    f(_fp(sc["means"]), _fp(sc["scales"]), _fp(rots), _fp(cam["viewmatrix"]), _fp(cam["projmatrix"]), cam["tanfovx"],
+      cam["tanfovy"], W, H, 0.9, N, *[a.ctypes.data_as(P) for a in (r2, m2, d2, c2, rc)])
+    assert (radii > 0).sum() > N // 4
+    assert np.array_equal(r2, radii.numpy())
+    assert np.array_equal(m2.view(np.int32), m2d.numpy().view(np.int32))
+    assert np.array_equal(d2.view(np.int32), depths.numpy().view(np.int32))
+    assert np.array_equal(c2.view(np.int32), conics.numpy().view(np.int32))
+    assert np.array_equal(rc, torch.stack(rect, -1).numpy().astype(np.int32))

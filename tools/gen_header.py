@@ -62,6 +62,14 @@ DOC = {
     "emd_projection_fwd": "gsplat fully_fused_projection (pinhole, quats+scales) as reached from "
                           "OmniRe/models/trainers/base.py:393; also writes tiles_per_gauss (first pass of isect_tiles).",
     "emd_projection_bwd": "VJP of emd_projection_fwd w.r.t. means, quats, scales.",
+    "emd_dg_preprocess_fwd": "diff_gauss preprocessCUDA (Inria-derived) as called from "
+                             "S3Gaussian/gaussian_renderer/__init__.py:145 with the settings of :49-62: frustum cull, "
+                             "cov3D/cov2D, conic, radius, getRect tile count, SH -> RGB.  viewmatrix/projmatrix/campos are "
+                             "HOST pointers (row-vector convention of S3Gaussian/scene/cameras.py:55-66).  K = SH bases "
+                             "stored per Gaussian, 0 when colours are precomputed.",
+    "emd_dg_preprocess_bwd": "VJP of emd_dg_preprocess_fwd w.r.t. means3D, scales, rotations, shs (incl. the view-direction "
+                             "term of the SH colour); v_means2d is the gradient w.r.t. the pixel-space mean.",
+    "emd_dg_isect_emit": "diff_gauss duplicateWithKeys: key = tile << 32 | float_bits(view depth), value = Gaussian index.",
     "emd_scan_workspace_bytes": "Workspace bytes of the scans for n elements.",
     "emd_cumsum_i32_i64": "Inclusive cumulative sum (torch.cumsum of tiles_per_gauss in gsplat's isect_tiles); total -> device scalar.",
     "emd_exclusive_scan_u32": "Exclusive scan (radix-sort tables); in-place allowed.",
