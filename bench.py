@@ -127,7 +127,7 @@ def build_inputs(args, rank, world):
 def run_ours(args):
     import torch.distributed as dist
 
-    from emd_b200 import _C, pipeline as P
+    from emd_b200 import _C, dist as D, pipeline as P
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -173,9 +173,7 @@ def run_ours(args):
         loss = (rgb * v_rgb).sum() + (depth * v_d).sum() + (alpha * v_a).sum()
         loss.backward()
         if world > 1:
-            works = [dist.all_reduce(p.grad, async_op=True) for p in params if p.grad is not None]
-            for w in works:
-                w.wait()
+            stats["allreduce_bytes"] = D.allreduce_grads(params)
         if e2e:  # device -> host read of the step's result
             loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         stats["n_isects"] = info["isect_ids"].numel()
@@ -285,7 +283,7 @@ def run_ours(args):
                 "note": "per step: H2D of camera matrices + per-pixel RGB/depth/alpha cotangents from pinned memory, "
                         "D2H of the loss; Gaussian parameters are model state resident in HBM"},
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
-        "n_isects_per_step": P_is, "fwd_ms_per_frame": None, "clocks": clocks, "roofline": roofline,
+        "n_isects_per_step": P_is, "allreduce_bytes_per_step": stats.get("allreduce_bytes", 0), "fwd_ms_per_frame": None, "clocks": clocks, "roofline": roofline,
     }
     if rank == 0:
         # forward-only render time (the second headline metric: ms per frame = per camera image)

@@ -1,0 +1,64 @@
+"""CPU, world_size 2, gloo: the N > 1 host logic (view sharding, bucketed gradient all-reduce,
+densification-statistics reduction) -- the data path itself has no collective besides this one."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from emd_b200 import dist as D
+        g = torch.Generator().manual_seed(100 + rank)
+        shapes = [(300000, 3), (300000, 4), (7, 36), (3,), (150, 32), (1,), (12, 5, 4)]
+        params = [torch.zeros(s, requires_grad=True) for s in shapes]
+        for p in params:
+            p.grad = torch.randn(p.shape, generator=g)
+        params.append(torch.zeros(5, requires_grad=True))  # no grad on this one
+        local = [p.grad.clone() if p.grad is not None else None for p in params]
+        nbytes = D.allreduce_grads(params)
+        # reference: plain per-tensor all_reduce
+        for p, l in zip(params, local):
+            if l is None:
+                assert p.grad is None
+                continue
+            ref = l.clone()
+            dist.all_reduce(ref)
+            assert torch.equal(p.grad, ref), "bucketed all-reduce differs from per-tensor all-reduce"
+        assert nbytes == sum(l.numel() * 4 for l in local if l is not None)
+        a, b, c = torch.full((4,), float(rank + 1)), torch.full((4,), 2.0), torch.tensor([1.0 + rank, 5.0 - rank])
+        D.allreduce_densify_stats(a, b, c)
+        assert torch.equal(a, torch.full((4,), 3.0)) and torch.equal(b, torch.full((4,), 4.0))
+        assert torch.equal(c, torch.tensor([2.0, 5.0]))
+        views = D.shard_views(11, rank, world)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, views)
+        assert sorted(sum(gathered, [])) == list(range(11))
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo():
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_single_process_is_noop():
+    from emd_b200 import dist as D
+    p = torch.zeros(3, requires_grad=True)
+    p.grad = torch.ones(3)
+    assert D.allreduce_grads([p]) == 0 and torch.equal(p.grad, torch.ones(3))
