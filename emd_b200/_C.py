@@ -39,6 +39,11 @@ _SIGS = {
     "emd_radix_sort_workspace_bytes": (c_size_t, [c_int64]),
     "emd_radix_sort_pairs": (c_int, [P, P, P, P, c_int64, c_int, c_int, P, c_size_t, ctypes.POINTER(c_int), P]),
     "emd_raster_pack": (c_int, [P, P, P, c_int, P, c_int, c_int, P, c_int, P, c_int64, c_int64, P, P]),
+    "emd_linear_bwd_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "emd_linear_fwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P]),
+    "emd_linear_bwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),
+    "emd_temb_fwd": (c_int, [P, c_int, c_int, P, c_int, P, P]),
+    "emd_temb_bwd": (c_int, [P, c_int, c_int, P, c_int, P, P, P, P]),
     "emd_tile_order": (c_int, [P, c_int64, c_int64, P, P]),
     "emd_rasterize_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "emd_dg_preprocess_fwd": (c_int, [P] * 4 + [ctypes.POINTER(c_float)] * 3 + [c_float, c_float, c_int, c_int, c_float,

@@ -277,3 +277,70 @@ extern "C" int emd_rigid_deform_bwd(const float* means, const float* quats, cons
     EMD_CHECK_LAUNCH("rigid_deform_bwd");
     return EMD_OK;
 }
+
+// ---- stand-alone temporal embedding (S3Gaussian: one shared table, per-call scalar time on the device) ----
+namespace {
+__global__ void temb_fwd_kernel(const float* __restrict__ table, int E, int d, const float* __restrict__ t_dev, int cur,
+                                float* __restrict__ emb) {
+    TembTaps taps;
+    temb_taps(*t_dev, cur, E, taps);
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < 4; ++k) s += taps.w[k] * table[taps.row[k] * d + j];
+        emb[j] = s;
+    }
+}
+// d emb / d t: the taps are piecewise linear in the (reflected) row coordinate iy = t * (cur-1):
+//   emb = (1-wy1) Wc[y0] + wy1 Wc[y0+1]  =>  d emb/d iy = Wc[y0+1] - Wc[y0]
+__global__ void temb_bwd_kernel(const float* __restrict__ table, int E, int d, const float* __restrict__ t_dev, int cur,
+                                const float* __restrict__ v_emb, float* __restrict__ v_table, float* __restrict__ v_t) {
+    __shared__ float s_red[32];
+    const float t = *t_dev;
+    TembTaps taps;
+    temb_taps(t, cur, E, taps);
+    const float wy0 = taps.w[0] + taps.w[1], wy1 = taps.w[2] + taps.w[3];
+    float local = 0.f;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        const float g = v_emb[j];
+        for (int k = 0; k < 4; ++k)
+            if (taps.w[k] != 0.f) v_table[taps.row[k] * d + j] += taps.w[k] * g;  // one thread per column: no race
+        // resized rows: Wc0 = (w0 T[r0] + w1 T[r1]) / wy0 etc.; guard the degenerate weights
+        const float a = wy0 > 0.f ? (taps.w[0] * table[taps.row[0] * d + j] + taps.w[1] * table[taps.row[1] * d + j]) / wy0 : 0.f;
+        const float b = wy1 > 0.f ? (taps.w[2] * table[taps.row[2] * d + j] + taps.w[3] * table[taps.row[3] * d + j]) / wy1 : a;
+        local += g * (b - a);
+    }
+    for (int o = 16; o >= 1; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0 && v_t) {
+        float s = 0.f;
+        for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) s += s_red[w];
+        // iy = reflect(t * (cur-1)): slope +-(cur-1) depending on the reflection parity
+        const float span = (float)(cur - 1);
+        float sign = 1.f;
+        if (span > 0.f) {
+            const float iy = t * span;
+            const int flips = (int)floorf(fabsf(iy) / span);
+            sign = (flips % 2 == 0) ? 1.f : -1.f;
+            if (iy < 0.f) sign = -sign;
+        }
+        *v_t = s * sign * span;
+    }
+}
+}  // namespace
+
+extern "C" int emd_temb_fwd(const float* table, int E, int d, const float* t_dev, int cur, float* emb,
+                            cudaStream_t stream) {
+    EMD_CHECK_ARG(E >= 2 && d >= 1 && cur >= 1, "temb_fwd: bad sizes");
+    EMD_LAUNCH(EK_MISC, stream, temb_fwd_kernel<<<1, 64, 0, stream>>>(table, E, d, t_dev, cur, emb));
+    EMD_CHECK_LAUNCH("temb_fwd");
+    return EMD_OK;
+}
+
+extern "C" int emd_temb_bwd(const float* table, int E, int d, const float* t_dev, int cur, const float* v_emb,
+                            float* v_table, float* v_t, cudaStream_t stream) {
+    EMD_CHECK_ARG(E >= 2 && d >= 1 && cur >= 1, "temb_bwd: bad sizes");
+    EMD_LAUNCH(EK_MISC, stream, temb_bwd_kernel<<<1, 64, 0, stream>>>(table, E, d, t_dev, cur, v_emb, v_table, v_t));
+    EMD_CHECK_LAUNCH("temb_bwd");
+    return EMD_OK;
+}

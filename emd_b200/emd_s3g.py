@@ -1,0 +1,73 @@
+"""EMD deformation network of S3Gaussian (K1d) -- host-side mirror of ``deform_network``
+(``S3Gaussian/scene/deformation.py:405-527``) for the flag set the reference's run scripts use
+(``--no_ds --no_dr --no_fine_hexplane_features``; ``feat_head``, ``defor_depth 1``, ``net_width 64``).
+
+Weights keep their ``state_dict`` names (below ``deformation_net.``), so a checkpoint of the reference
+loads by key.  The HexPlane features of the coarse pass are passed in (``hex_feat[N,128]``, produced by the
+reference's own ``HexPlaneField`` in PyTorch -- SURVEY.md 8f-1); everything after them runs in the
+C-ABI kernels: temporal embedding, the 22 Linear layers with their ReLUs, residual application.
+
+The temporal embedding is the same for every Gaussian, so its columns of the first layers are folded into
+the bias (``b' = b + W[:, temb] @ temb``): the per-Gaussian GEMM input shrinks from 164 to 132 (coarse) and
+from 36 to 4 (fine).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from .emd_rigid import int_lininterp
+from .mlp_ops import linear, temporal_embed
+
+
+class S3GDeformation:
+    def __init__(self, weights: Dict[str, Tensor], min_embeddings: int = 30, max_embeddings: int = 150,
+                 c2f_temporal_iter: int = 25000, temporal_dim: int = 32, hex_dim: int = 128):
+        self.w = weights
+        self.min_embeddings, self.max_embeddings, self.c2f = min_embeddings, max_embeddings, c2f_temporal_iter
+        self.td, self.hd = temporal_dim, hex_dim
+
+    def _head(self, name: str, hidden: Tensor) -> Tensor:
+        w = self.w
+        h1 = linear(hidden, w[name + ".1.weight"], w[name + ".1.bias"], relu_in=True, relu_out=True)
+        return linear(h1, w[name + ".3.weight"], w[name + ".3.bias"])
+
+    def _dino(self, hidden: Tensor) -> Tensor:
+        w = self.w
+        h1 = linear(hidden, w["dino_head.0.weight"], w["dino_head.0.bias"], relu_out=True)
+        h2 = linear(h1, w["dino_head.2.weight"], w["dino_head.2.bias"], relu_out=True)
+        return linear(h2, w["dino_head.4.weight"], w["dino_head.4.bias"])
+
+    def _branch(self, sfx: str, hidden: Tensor, N: int):
+        return dict(dx=self._head("pos_deform" + sfx, hidden), ds=None, dr=None,
+                    do=self._head("opacity_deform" + sfx, hidden),
+                    dshs=self._head("shs_deform" + sfx, hidden).reshape(N, 16, 3), feat=self._dino(hidden))
+
+    def forward(self, point: Tensor, scales: Tensor, rotations: Tensor, opacity: Tensor, shs: Tensor, time,
+                embeddings: Tensor, iteration: int, cam_no: int, hex_feat: Tensor):
+        """-> (means3D, scales, rotations, opacity, shs, ddict) as ``deform_network.forward`` returns them.
+        ``time`` is the normalised timestamp (python float or 0-d tensor)."""
+        w, td, hd = self.w, self.td, self.hd
+        N = point.shape[0]
+        t = torch.as_tensor(time, dtype=torch.float32, device=point.device) + w["time_offset"][cam_no, 0]
+        temb_c = temporal_embed(w["weight"], t, self.min_embeddings)
+        cur = int_lininterp(iteration, self.min_embeddings, self.max_embeddings, self.c2f)
+        temb_f = temporal_embed(w["weight"], t, cur)
+        W0, b0 = w["feature_out.0.weight"], w["feature_out.0.bias"]          # [64, 128+32+4]
+        W0f, b0f = w["feature_out_f.0.weight"], w["feature_out_f.0.bias"]    # [64, 32+4]
+        # fold the (row-constant) temporal embedding into the bias
+        b0_eff = b0 + W0[:, hd:hd + td] @ temb_c
+        b0f_eff = b0f + W0f[:, :td] @ temb_f
+        x_c = torch.cat([hex_feat, embeddings], dim=-1)                      # [N,132]
+        W0_eff = torch.cat([W0[:, :hd], W0[:, hd + td:]], dim=1)
+        h_c = linear(x_c, W0_eff, b0_eff)
+        h_f = linear(embeddings, W0f[:, td:], b0f_eff)
+        ddict = {"coarse": self._branch("", h_c, N), "fine": self._branch("_f", h_f, N)}
+        means = point + ddict["coarse"]["dx"] + ddict["fine"]["dx"]
+        opac = opacity + ddict["coarse"]["do"] + ddict["fine"]["do"]
+        shs_f = shs + ddict["coarse"]["dshs"] + ddict["fine"]["dshs"]
+        return means, scales, rotations, opac, shs_f, ddict
+
+    __call__ = forward

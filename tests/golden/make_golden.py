@@ -180,5 +180,65 @@ def main():
     print("golden fixtures written to", HERE)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--s3g" not in sys.argv:
     main()
+
+
+def make_s3g_golden():
+    """S3Gaussian deformation network (S3Gaussian/scene/deformation.py) run on the CPU with the flags of
+    scripts/dynamic/run_dynamic_*.sh (--no_ds --no_dr --no_fine_hexplane_features) -> tests/golden/emd_s3g.npz."""
+    _stub(["tkinter", "tinycudann", "open3d", "plyfile", "simple_knn", "simple_knn._C", "diff_gauss", "nvdiffrast",
+           "nvdiffrast.torch", "lpips", "matplotlib", "matplotlib.pyplot", "imageio", "mmcv"])
+    _cpuify()
+    for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.") or k == "scene" or k.startswith("scene.")
+              or k == "arguments" or k.startswith("arguments.")]:
+        del sys.modules[k]
+    sys.path.insert(0, f"{REF}/S3Gaussian")
+    if f"{REF}/OmniRe" in sys.path:
+        sys.path.remove(f"{REF}/OmniRe")
+    # scene/__init__.py pulls the whole training stack; load the three modules we need directly
+    pkg = types.ModuleType("scene"); pkg.__path__ = [f"{REF}/S3Gaussian/scene"]; sys.modules["scene"] = pkg
+    upkg = types.ModuleType("utils"); upkg.__path__ = [f"{REF}/S3Gaussian/utils"]; sys.modules["utils"] = upkg
+    apkg = types.ModuleType("arguments"); apkg.__path__ = [f"{REF}/S3Gaussian/arguments"]; sys.modules["arguments"] = apkg
+    sys.modules["scene.encodings"] = MagicMock()
+    opts = importlib.import_module("arguments.gaussian_options")
+    deformation = importlib.import_module("scene.deformation")
+    args = opts.BaseOptions()
+    args.no_ds, args.no_dr, args.no_fine_hexplane_features = True, True, True
+    torch.manual_seed(7)
+    net = deformation.deform_network(args)
+    net.deformation_net.time_offset.data = torch.tensor([[0.0], [0.013], [-0.02]])
+    g = torch.Generator().manual_seed(11)
+    N = 257
+    point = (torch.rand(N, 3, generator=g) - 0.5) * 2.4
+    scales = 0.1 * torch.randn(N, 3, generator=g); rots = torch.randn(N, 4, generator=g)
+    opacity = torch.randn(N, 1, generator=g); shs = 0.3 * torch.randn(N, 16, 3, generator=g)
+    emb = 0.1 * torch.randn(N, 4, generator=g)
+    out = {"point": point, "scales": scales, "rotations": rots, "opacity": opacity, "shs": shs, "embeddings": emb}
+    for k, v in net.state_dict().items():
+        if "grid.grids" in k or "poc" in k or "aabb" in k:
+            continue
+        out["w." + k] = v.clone()
+    cases = [(0.25, 6000, 0), (0.8, 17000, 1), (1.0, 40000, 2)]
+    out["cases"] = torch.tensor([[t, it, c] for t, it, c in cases])
+    grabbed = {}
+    hook = net.deformation_net.grid.register_forward_hook(lambda m, i, o: grabbed.setdefault("hex", []).append(o.detach().clone()))
+    with torch.no_grad():
+        for ci, (t, it, cam_no) in enumerate(cases):
+            grabbed.clear()
+            times = torch.full((N, 1), t)
+            m, s, r, o, sh, dd = net(point, scales, rots, opacity, shs, times, emb, it, cam_no, 1.0, is_train=False)
+            out[f"c{ci}_hex"] = grabbed["hex"][0]   # hexplane features of the coarse pass (at `point`)
+            out[f"c{ci}_means"], out[f"c{ci}_opacity"], out[f"c{ci}_shs"] = m, o, sh
+            assert torch.equal(s, scales) and torch.equal(r, rots)
+            for br in ("coarse", "fine"):
+                for key in ("dx", "do", "dshs", "feat"):
+                    out[f"c{ci}_{br}_{key}"] = dd[br][key]
+                assert dd[br]["ds"] is None and dd[br]["dr"] is None
+    hook.remove()
+    np.savez(f"{HERE}/emd_s3g.npz", **{k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in out.items()})
+    print("wrote emd_s3g.npz with", len(out), "arrays")
+
+
+if __name__ == "__main__" and "--s3g" in sys.argv:
+    make_s3g_golden()

@@ -81,3 +81,19 @@ def test_emd_smpl_offsets_golden():
     for ci, (frame, step) in enumerate(z["cases"].tolist()):
         off = ES.track_smpl_offset(p, 0, frame, step)
         assert torch.allclose(off, _t(z[f"c{ci}"]), atol=1e-6), ci
+
+
+def test_emd_s3g_golden():
+    """The S3Gaussian deformation network (coarse + fine heads, c2f schedule, per-camera time offset)."""
+    from oracle import emd_s3g as S
+    z = np.load(f"{G}/emd_s3g.npz")
+    w = {k[len("w.deformation_net."):]: _t(z[k]) for k in z.files if k.startswith("w.deformation_net.")}
+    for ci, (t, it, cam) in enumerate(z["cases"].tolist()):
+        means, opac, shs, dd = S.deform(w, _t(z["point"]), _t(z["opacity"]), _t(z["shs"]), _t(z["embeddings"]),
+                                        _t(z[f"c{ci}_hex"]), float(np.float32(t)), int(it), int(cam))
+        assert torch.allclose(means, _t(z[f"c{ci}_means"]), atol=2e-6), ci
+        assert torch.allclose(opac, _t(z[f"c{ci}_opacity"]), atol=2e-6), ci
+        assert torch.allclose(shs, _t(z[f"c{ci}_shs"]), atol=2e-6), ci
+        for br in ("coarse", "fine"):
+            for key in ("dx", "do", "dshs", "feat"):
+                assert torch.allclose(dd[br][key], _t(z[f"c{ci}_{br}_{key}"]), atol=2e-6), (ci, br, key)
