@@ -44,8 +44,10 @@ _SIGS = {
     "emd_linear_bwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),
     "emd_temb_fwd": (c_int, [P, c_int, c_int, P, c_int, P, P]),
     "emd_temb_bwd": (c_int, [P, c_int, c_int, P, c_int, P, P, P, P]),
-    "emd_tile_order": (c_int, [P, c_int64, c_int64, P, P]),
-    "emd_rasterize_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
+    "emd_tile_order": (c_int, [P, c_int64, c_int64, P, P, P, P]),
+    "emd_raster_segment_size": (c_int, []),
+    "emd_raster_checkpoint_floats": (c_int, []),
+    "emd_rasterize_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "emd_dg_preprocess_fwd": (c_int, [P] * 4 + [ctypes.POINTER(c_float)] * 3 + [c_float, c_float, c_int, c_int, c_float,
                                                                               c_int, c_int, c_int64] + [P] * 7 + [P]),
     "emd_dg_preprocess_bwd": (c_int, [P] * 4 + [ctypes.POINTER(c_float)] * 3 + [c_float, c_float, c_int, c_int, c_float,
@@ -68,7 +70,7 @@ _SIGS = {
     "emd_smpl_deform_fwd": (c_int, [P] * 12 + [c_int] * 5 + [c_float, c_int, c_int] + [P] * 5 + [P]),
     "emd_smpl_deform_bwd": (c_int, [P] * 11 + [c_int] * 5 + [c_float, c_int, c_int] + [P] * 14 + [P]),
     "emd_rasterize_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
-                                  c_int, P, P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
+                                  c_int, P, P, P, P, P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
 }
 
 

@@ -32,6 +32,9 @@ namespace {
 constexpr int RB = 256;  // threads per CTA == pixels per tile == Gaussians per staged batch
 constexpr float ALPHA_MIN = 1.0f / 255.0f;
 constexpr int NPART = 12;  // floats per (tile, Gaussian) gradient slot
+constexpr int SEG_BATCHES = 4;            // a segment = 4 staged batches = 1024 Gaussians of a tile's list
+constexpr int SEG = SEG_BATCHES * RB;
+constexpr int CKPT_FLOATS = 5 * RB;       // per segment boundary: T and acc[4] of the 256 pixels
 
 // ---------------------------------------------------------------------------
 // pack: gather the per-(camera,Gaussian) fields the compositor reads into three
@@ -69,8 +72,9 @@ __global__ void raster_pack_kernel(const float* __restrict__ means2d, const floa
 __global__ void __launch_bounds__(RB) raster_fwd_kernel(
     const float4* __restrict__ recs, const int32_t* __restrict__ tile_offsets, const int32_t* __restrict__ flatten_ids,
     const int32_t* __restrict__ tile_order, int64_t P, int C, int width, int height, int tile_w, int tile_h, int CH,
-    int ed_mode, RasterCfg cfg, const float* __restrict__ backgrounds, float* __restrict__ out_colors,
-    float* __restrict__ out_alphas, int32_t* __restrict__ last_ids) {
+    int ed_mode, RasterCfg cfg, const float* __restrict__ backgrounds, const int32_t* __restrict__ ckpt_base,
+    float* __restrict__ ckpt, float* __restrict__ out_colors, float* __restrict__ out_alphas,
+    int32_t* __restrict__ last_ids) {
     __shared__ float4 s_r0[RB];
     __shared__ float4 s_r1[RB];
     __shared__ float2 s_r2[RB];
@@ -98,6 +102,12 @@ __global__ void __launch_bounds__(RB) raster_fwd_kernel(
 
     for (int b = 0; b < num_batches; ++b) {
         if (__syncthreads_count(done) >= RB) break;
+        if (ckpt != nullptr && b > 0 && (b % SEG_BATCHES) == 0) {
+            // segment boundary: per-pixel state BEFORE sorted index range_start + b*256.  The backward pass
+            // starts every 1024-Gaussian segment of a long tile from these, so segments run as parallel CTAs.
+            float* c = ckpt + ((int64_t)ckpt_base[tile_id] + b / SEG_BATCHES - 1) * CKPT_FLOATS;
+            c[tr] = T; c[RB + tr] = acc[0]; c[2 * RB + tr] = acc[1]; c[3 * RB + tr] = acc[2]; c[4 * RB + tr] = acc[3];
+        }
         const int64_t batch_start = range_start + (int64_t)RB * b;
         const int64_t idx = batch_start + tr;
         if (idx < range_end) {
@@ -190,7 +200,8 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
     const float4* __restrict__ recs, const int32_t* __restrict__ tile_offsets, const int32_t* __restrict__ flatten_ids,
     const int32_t* __restrict__ tile_order, const int32_t* __restrict__ radii, const int64_t* __restrict__ cum_tiles,
     int64_t P, int C, int width, int height, int tile_w, int tile_h, int CH, int ed_mode, RasterCfg cfg,
-    const float* __restrict__ backgrounds,
+    const float* __restrict__ backgrounds, const int32_t* __restrict__ seg_prefix,
+    const int32_t* __restrict__ ckpt_base, const float* __restrict__ ckpt,
     const float* __restrict__ out_colors, const float* __restrict__ out_alphas, const int32_t* __restrict__ last_ids,
     const float* __restrict__ v_out_colors, const float* __restrict__ v_out_alphas, float* __restrict__ partials,
     uint8_t* __restrict__ touched) {
@@ -202,7 +213,17 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
     __shared__ uint32_t s_tmask[RB / 32];
     __shared__ int s_red[RB / 32];
 
-    const int tile_id = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;
+    // CTA -> (tile, segment): segments of all tiles are laid out heavy-tile-first; seg_prefix[r] is the inclusive
+    // number of segments of the first r+1 tiles of that order (binary search; block-uniform)
+    const int n_cam_tiles = C * tile_w * tile_h;
+    if ((int)blockIdx.x >= seg_prefix[n_cam_tiles - 1]) return;
+    int lo_r = 0, hi_r = n_cam_tiles - 1;
+    while (lo_r < hi_r) {
+        const int mid = (lo_r + hi_r) >> 1;
+        if (seg_prefix[mid] > (int)blockIdx.x) hi_r = mid; else lo_r = mid + 1;
+    }
+    const int seg = (int)blockIdx.x - (lo_r > 0 ? seg_prefix[lo_r - 1] : 0);
+    const int tile_id = tile_order[lo_r];
     const int cam = tile_id / (tile_w * tile_h);
     const int tile_y = (tile_id - cam * tile_w * tile_h) / tile_w;
     const int tile_x = tile_id - (cam * tile_h + tile_y) * tile_w;
@@ -214,8 +235,11 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
     const bool inside = i < height && j < width;
     const int64_t pix = ((int64_t)cam * height + min(i, height - 1)) * width + min(j, width - 1);
 
-    const int64_t range_start = tile_offsets[tile_id];
-    const int64_t range_end = (tile_id == C * tile_h * tile_w - 1) ? P : (int64_t)tile_offsets[tile_id + 1];
+    const int64_t tile_start = tile_offsets[tile_id];
+    const int64_t tile_end = (tile_id == C * tile_h * tile_w - 1) ? P : (int64_t)tile_offsets[tile_id + 1];
+    // this CTA's slice of the tile's sorted list
+    const int64_t range_start = tile_start + (int64_t)seg * SEG;
+    const int64_t range_end = min(tile_end, range_start + SEG);
     if (range_end <= range_start) return;
 
     // per-pixel state
@@ -241,6 +265,23 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
         for (int k = 0; k < CH; ++k) bg_dot += backgrounds[cam * CH + k] * v_c[k];
     }
     float buf[4] = {0.f, 0.f, 0.f, 0.f};
+    if (inside && bin_final >= range_end) {
+        // the pixel blended Gaussians beyond this segment: start from the forward checkpoint taken at the
+        // segment's end (T before sorted index range_end; colour accumulated in front of it)
+        const float* c = ckpt + ((int64_t)ckpt_base[tile_id] + seg) * CKPT_FLOATS;
+        T = c[tr];
+        float raw[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < CH) {
+                float o = out_colors[pix * CH + k];
+                if (ed_mode && k == CH - 1) o *= fmaxf(alpha_out, 1e-10f);   // undo the expected-depth normalisation
+                if (backgrounds) o -= T_final * backgrounds[cam * CH + k];   // undo the background term
+                raw[k] = o;
+            }
+            buf[k] = raw[k] - c[(k + 1) * RB + tr];  // colour accumulated BEHIND the segment
+        }
+    }
 
     // last sorted index any pixel of this tile blended
     int wmax = (int)max(bin_final, (int64_t)-1);
@@ -354,13 +395,21 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
     }
 }
 
-// Heavy-first tile order: bucket tiles by floor(log2(list length)) (coarse LPT is enough) and emit
-// bucket 31 (longest) first.  One CTA; order within a bucket is arbitrary (it only affects scheduling).
+// Heavy-first tile order + segment bookkeeping.  One CTA.
+//   order[r]      : tile ids, bucketed by floor(log2(list length)), longest bucket first (coarse LPT; the order
+//                   within a bucket is arbitrary -- it only affects scheduling, never results)
+//   seg_prefix[r] : inclusive count of 1024-Gaussian segments of tiles order[0..r] (>= 1 per tile)
+//   ckpt_base[t]  : first checkpoint slot of TILE t (a tile with n segments owns n-1 slots)
 __global__ void __launch_bounds__(1024) tile_order_kernel(const int32_t* __restrict__ tile_offsets, int64_t P,
-                                                          int n_cam_tiles, int32_t* __restrict__ order) {
+                                                          int n_cam_tiles, int32_t* __restrict__ order,
+                                                          int32_t* __restrict__ seg_prefix,
+                                                          int32_t* __restrict__ ckpt_base) {
     __shared__ int s_cnt[33];
     __shared__ int s_base[33];
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
     if (threadIdx.x < 33) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     for (int t = threadIdx.x; t < n_cam_tiles; t += blockDim.x) {
         const int64_t e = t == n_cam_tiles - 1 ? P : (int64_t)tile_offsets[t + 1];
@@ -377,6 +426,46 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const int32_t* __restr
         const int64_t e = t == n_cam_tiles - 1 ? P : (int64_t)tile_offsets[t + 1];
         const int len = (int)(e - tile_offsets[t]);
         order[atomicAdd(&s_base[len > 0 ? 32 - __clz(len) : 0], 1)] = t;
+    }
+    __syncthreads();  // order[] (global) is visible to the whole CTA
+    if (seg_prefix == nullptr) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r0 = 0; r0 < n_cam_tiles; r0 += blockDim.x) {
+        const int r = r0 + threadIdx.x;
+        int nseg = 0, t = 0;
+        if (r < n_cam_tiles) {
+            t = order[r];
+            const int64_t e = t == n_cam_tiles - 1 ? P : (int64_t)tile_offsets[t + 1];
+            const int len = (int)(e - tile_offsets[t]);
+            nseg = len > 0 ? (len + SEG - 1) / SEG : 1;
+        }
+        int inc = nseg;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += n;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int incl = carry + inc + (warp > 0 ? s_warp[warp - 1] : 0);
+        if (r < n_cam_tiles) {
+            seg_prefix[r] = incl;
+            ckpt_base[t] = (incl - nseg) - r;  // sum over earlier tiles of (nseg - 1)
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = incl;
+        __syncthreads();
     }
 }
 
@@ -430,24 +519,33 @@ extern "C" int emd_raster_pack(const float* means2d, const float* conics, const 
     return EMD_OK;
 }
 
-// order[C*tile_h*tile_w]: tile ids, longest Gaussian list first (optional input of rasterize_fwd/bwd)
+extern "C" int emd_raster_segment_size() { return SEG; }
+extern "C" int emd_raster_checkpoint_floats() { return CKPT_FLOATS; }
+
+// order / seg_prefix / ckpt_base: [C*tile_h*tile_w] int32 each (see tile_order_kernel).  The checkpoint buffer the
+// forward fills and the backward reads needs (P / emd_raster_segment_size() + 1) * emd_raster_checkpoint_floats()
+// floats; the backward launches at most P / segment_size + n_cam_tiles CTAs.
 extern "C" int emd_tile_order(const int32_t* tile_offsets, int64_t P, int64_t n_cam_tiles, int32_t* order,
-                              cudaStream_t stream) {
+                              int32_t* seg_prefix, int32_t* ckpt_base, cudaStream_t stream) {
     EMD_CHECK_ARG(n_cam_tiles >= 1 && n_cam_tiles < (1 << 30), "tile_order: bad tile count");
-    EMD_LAUNCH(EK_MISC, stream, tile_order_kernel<<<1, 1024, 0, stream>>>(tile_offsets, P, (int)n_cam_tiles, order));
+    EMD_CHECK_ARG((seg_prefix == nullptr) == (ckpt_base == nullptr), "tile_order: seg_prefix and ckpt_base go together");
+    EMD_LAUNCH(EK_MISC, stream, tile_order_kernel<<<1, 1024, 0, stream>>>(tile_offsets, P, (int)n_cam_tiles, order, seg_prefix, ckpt_base));
     EMD_CHECK_LAUNCH("tile_order");
     return EMD_OK;
 }
 
 extern "C" int emd_rasterize_fwd(const float* recs, const int32_t* tile_offsets, const int32_t* flatten_ids,
                                  const int32_t* tile_order, int64_t P, int64_t C, int width, int height, int tile_w, int tile_h, int channels,
-                                 int ed_mode, int flavour, const float* backgrounds, float* out_colors,
-                                 float* out_alphas, int32_t* last_ids, cudaStream_t stream) {
+                                 int ed_mode, int flavour, const float* backgrounds, const int32_t* ckpt_base,
+                                 float* ckpt, float* out_colors, float* out_alphas, int32_t* last_ids,
+                                 cudaStream_t stream) {
     const RasterCfg cfg = flavour == 1 ? RasterCfg{0.0f, 0.99f, 1, 1} : RasterCfg{0.5f, 0.999f, 0, 0};
     EMD_CHECK_ARG(channels >= 1 && channels <= 4, "rasterize_fwd: channels must be 1..4");
     EMD_CHECK_ARG(C >= 1 && C * tile_w * tile_h < ((int64_t)1 << 31), "rasterize_fwd: grid too large");
     EMD_CHECK_ARG(tile_w == (width + EMD_TILE - 1) / EMD_TILE && tile_h == (height + EMD_TILE - 1) / EMD_TILE,
                   "rasterize_fwd: tile grid does not match image size (tile size is 16)");
+    EMD_CHECK_ARG((ckpt == nullptr) == (ckpt_base == nullptr), "rasterize_fwd: ckpt and ckpt_base go together");
+    EMD_CHECK_ARG(ckpt == nullptr || tile_order != nullptr, "rasterize_fwd: checkpoints need the tile order");
     if (!emd_aligned(recs, 16) || (channels == 4 && !emd_aligned(out_colors, 16))) {
         emd_set_error("rasterize_fwd: recs/out_colors must be 16-B aligned");
         return EMD_ERR_ALIGN;
@@ -455,7 +553,7 @@ extern "C" int emd_rasterize_fwd(const float* recs, const int32_t* tile_offsets,
     dim3 grid((unsigned)(C * tile_w * tile_h)), block(EMD_TILE, EMD_TILE, 1);
     EMD_LAUNCH(EK_RASTER_FWD, stream, raster_fwd_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, tile_order, P,
                                                   (int)C, width, height, tile_w, tile_h, channels, ed_mode, cfg,
-                                                  backgrounds, out_colors, out_alphas, last_ids));
+                                                  backgrounds, ckpt_base, ckpt, out_colors, out_alphas, last_ids));
     EMD_CHECK_LAUNCH("rasterize_fwd");
     return EMD_OK;
 }
@@ -469,7 +567,8 @@ extern "C" size_t emd_rasterize_bwd_workspace_bytes(int64_t P) {
 extern "C" int emd_rasterize_bwd(const float* recs, const int32_t* tile_offsets, const int32_t* flatten_ids,
                                  const int32_t* tile_order, const int32_t* radii, const int64_t* cum_tiles, int64_t P, int64_t N, int64_t C,
                                  int width, int height, int tile_w, int tile_h, int channels, int ed_mode, int flavour,
-                                 const float* backgrounds, const float* out_colors, const float* out_alphas,
+                                 const float* backgrounds, const int32_t* seg_prefix, const int32_t* ckpt_base,
+                                 const float* ckpt, const float* out_colors, const float* out_alphas,
                                  const int32_t* last_ids, const float* v_out_colors, const float* v_out_alphas,
                                  int d_color, int with_depth, float* v_means2d, float* v_means2d_abs, float* v_conics,
                                  float* v_colors, float* v_depths, float* v_opacities, void* workspace,
@@ -478,6 +577,7 @@ extern "C" int emd_rasterize_bwd(const float* recs, const int32_t* tile_offsets,
     EMD_CHECK_ARG(d_color + (with_depth ? 1 : 0) == channels, "rasterize_bwd: channel bookkeeping mismatch");
     const RasterCfg cfg = flavour == 1 ? RasterCfg{0.0f, 0.99f, 1, 1} : RasterCfg{0.5f, 0.999f, 0, 0};
     EMD_CHECK_ARG(P < ((int64_t)1 << 32), "rasterize_bwd: too many intersections");
+    EMD_CHECK_ARG(tile_order && seg_prefix && ckpt_base && ckpt, "rasterize_bwd: needs tile_order, seg_prefix, ckpt_base, ckpt");
     if (ws_bytes < emd_rasterize_bwd_workspace_bytes(P)) {
         emd_set_error("rasterize_bwd: workspace too small");
         return EMD_ERR_WORKSPACE;
@@ -493,10 +593,12 @@ extern "C" int emd_rasterize_bwd(const float* recs, const int32_t* tile_offsets,
     uint8_t* touched = reinterpret_cast<uint8_t*>(workspace) + part;
     if (P > 0) {
         cudaMemsetAsync(touched, 0, (size_t)P, stream);
-        dim3 grid((unsigned)(C * tile_w * tile_h)), block(EMD_TILE, EMD_TILE, 1);
+        // upper bound on the number of (tile, segment) CTAs; surplus CTAs exit at once
+        dim3 grid((unsigned)(P / SEG + C * tile_w * tile_h)), block(EMD_TILE, EMD_TILE, 1);
         EMD_LAUNCH(EK_RASTER_BWD, stream, raster_bwd_kernel<<<grid, block, 0, stream>>>(
             reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, tile_order, radii, cum_tiles, P, (int)C, width,
-            height, tile_w, tile_h, channels, ed_mode, cfg, backgrounds, out_colors, out_alphas, last_ids, v_out_colors,
+            height, tile_w, tile_h, channels, ed_mode, cfg, backgrounds, seg_prefix, ckpt_base, ckpt, out_colors, out_alphas,
+            last_ids, v_out_colors,
             v_out_alphas, partials, touched));
     }
     EMD_LAUNCH(EK_RASTER_GATHER, stream, raster_gather_kernel<<<(unsigned)emd_cdiv(CN, 256), 256, 0, stream>>>(partials, touched, cum_tiles, CN, d_color,

@@ -212,15 +212,21 @@ class _Rasterize(torch.autograd.Function):
         out_alphas = torch.empty(C, height, width, 1, dtype=torch.float32, device=dev)
         last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
         bg = _f32c(backgrounds) if backgrounds is not None else None
-        tile_order = torch.empty(C * th * tw, dtype=torch.int32, device=dev)
-        _C.check(L.emd_tile_order(_C.ptr(isect_offsets, torch.int32), P, C * th * tw, _C.ptr(tile_order), _C.stream()),
-                 "emd_tile_order")
+        n_ct = C * th * tw
+        sched = torch.empty(3, n_ct, dtype=torch.int32, device=dev)  # tile order | segment prefix | checkpoint base
+        tile_order, seg_prefix, ckpt_base = sched[0], sched[1], sched[2]
+        _C.check(L.emd_tile_order(_C.ptr(isect_offsets, torch.int32), P, n_ct, _C.ptr(tile_order), _C.ptr(seg_prefix),
+                                  _C.ptr(ckpt_base), _C.stream()), "emd_tile_order")
+        need_ckpt = any(ctx.needs_input_grad[:5])
+        ckpt = (torch.empty((P // L.emd_raster_segment_size() + 1) * L.emd_raster_checkpoint_floats(),
+                            dtype=torch.float32, device=dev) if need_ckpt else None)
         _C.check(L.emd_rasterize_fwd(_C.ptr(recs), _C.ptr(isect_offsets, torch.int32), _C.ptr(flatten_ids, torch.int32),
                                      _C.ptr(tile_order), P, C, width, height, tw, th, CH, 1 if ed_mode else 0, int(flavour), _C.ptr(bg),
+                                     _C.ptr(ckpt_base) if need_ckpt else None, _C.ptr(ckpt),
                                      _C.ptr(out_colors), _C.ptr(out_alphas), _C.ptr(last_ids), _C.stream()),
                  "emd_rasterize_fwd")
         ctx.save_for_backward(recs, isect_offsets, flatten_ids, radii, cum_tiles, bg if bg is not None else torch.empty(0, device=dev),
-                              out_colors, out_alphas, last_ids, tile_order)
+                              out_colors, out_alphas, last_ids, sched, ckpt if ckpt is not None else torch.empty(0, device=dev))
         ctx.cfg = (width, height, CH, d_color, bool(with_depth), bool(ed_mode), bool(absgrad), colors_per_cam,
                    opac_per_cam, bg is not None, int(flavour))
         ctx.means2d_ref = means2d if absgrad else None
@@ -230,7 +236,8 @@ class _Rasterize(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_colors_out, v_alphas_out, _v_last):
         L = _C.lib()
-        recs, isect_offsets, flatten_ids, radii, cum_tiles, bg, out_colors, out_alphas, last_ids, tile_order = ctx.saved_tensors
+        recs, isect_offsets, flatten_ids, radii, cum_tiles, bg, out_colors, out_alphas, last_ids, sched, ckpt = ctx.saved_tensors
+        tile_order, seg_prefix, ckpt_base = sched[0], sched[1], sched[2]
         width, height, CH, d_color, with_depth, ed_mode, absgrad, colors_per_cam, opac_per_cam, has_bg, flavour = ctx.cfg
         C, N = radii.shape
         dev = radii.device
@@ -248,7 +255,8 @@ class _Rasterize(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _C.check(L.emd_rasterize_bwd(
             _C.ptr(recs), _C.ptr(isect_offsets), _C.ptr(flatten_ids), _C.ptr(tile_order), _C.ptr(radii), _C.ptr(cum_tiles), P, N, C,
-            width, height, tw, th, CH, 1 if ed_mode else 0, flavour, _C.ptr(bg) if has_bg else None, _C.ptr(out_colors),
+            width, height, tw, th, CH, 1 if ed_mode else 0, flavour, _C.ptr(bg) if has_bg else None, _C.ptr(seg_prefix),
+            _C.ptr(ckpt_base), _C.ptr(ckpt), _C.ptr(out_colors),
             _C.ptr(out_alphas), _C.ptr(last_ids), _C.ptr(v_colors_out), _C.ptr(v_alphas_out), d_color,
             1 if with_depth else 0, _C.ptr(v_means2d), _C.ptr(v_abs), _C.ptr(v_conics), _C.ptr(v_colors),
             _C.ptr(v_depths), _C.ptr(v_opac), _C.ptr(ws), ws_bytes, _C.stream()), "emd_rasterize_bwd")

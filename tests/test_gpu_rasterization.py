@@ -85,6 +85,9 @@ def test_forward_parity(seed, n, W, H, yaws, mode, bg):
     (10, 2500, 208, 144, (0.0,), "RGB+ED", False),
     (11, 1200, 128, 96, (0.0, 25.0), "RGB", True),
     (12, 1000, 112, 80, (0.0,), "RGB+D", False),
+    # long per-tile lists (several 1024-Gaussian segments per tile): the segment-parallel backward + checkpoints
+    (13, 9000, 64, 48, (0.0,), "RGB+ED", False),
+    (14, 7000, 48, 32, (0.0, 20.0), "RGB", True),
 ])
 def test_backward_parity(seed, n, W, H, yaws, mode, bg):
     sc, cpu, gpu, (rc, ra, meta), (gc, ga, gmeta), g, D = _run_both(seed, n, W, H, yaws, mode, bg)
