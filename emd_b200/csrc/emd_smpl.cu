@@ -220,38 +220,174 @@ __global__ void __launch_bounds__(SM_THREADS) smpl_points_bwd_kernel(
     if (o1 < SM_RED) out[o1] = acc1;
 }
 
-__global__ void smpl_instance_bwd_kernel(SmplArgs a, const float* __restrict__ mean_emb,
-                                         const float* __restrict__ red_partial, float* __restrict__ v_theta,
-                                         float* __restrict__ v_trans, float* __restrict__ v_params_partial,
-                                         float* __restrict__ v_table, float* __restrict__ v_mean_emb) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.I) return;
+// One CTA per instance.  The per-joint work (EMD heads, joint rotations, v_A -> v_G, quaternion VJPs) runs one
+// thread per joint, the bulk work (chunk sums of v_A, head-weight outer products, temporal-table VJP) across the
+// whole CTA; only the 24-step kinematic chain and its reverse sweep stay on one thread, in shared memory.
+// Same arithmetic and summation order as smpl_instance_bwd (emd_math.cuh).
+constexpr int SIB_THREADS = 128;
+__global__ void __launch_bounds__(SIB_THREADS) smpl_instance_bwd_kernel(
+    SmplArgs a, const float* __restrict__ mean_emb, const float* __restrict__ red_partial,
+    float* __restrict__ v_theta, float* __restrict__ v_trans, float* __restrict__ v_params_partial,
+    float* __restrict__ v_table, float* __restrict__ v_mean_emb) {
+    constexpr int IN_MAX = EMD_TDIM_MAX + EMD_GDIM_MAX;
+    __shared__ float s_vA[SM_AOUT];
+    __shared__ float s_hc[IN_MAX], s_hf[IN_MAX], s_vhc[IN_MAX], s_vhf[IN_MAX];
+    __shared__ float s_ac[SMPL_J], s_af[SMPL_J], s_vac[SMPL_J];
+    __shared__ float s_G[SMPL_J][12], s_vG[SMPL_J][12], s_R[SMPL_J][9], s_vR[SMPL_J][9];
+    __shared__ float s_thn[SMPL_J][4], s_qo[SMPL_J][4], s_thinv[SMPL_J];
+    __shared__ int s_par[SMPL_J];
+    __shared__ int s_skip;
+    const int i = blockIdx.x, tid = threadIdx.x;
     const int nch = (a.V + SM_CHUNK - 1) / SM_CHUNK;
-    float vA[SM_AOUT];
-    for (int k = 0; k < SM_AOUT; ++k) {
-        float s = 0.f;
-        for (int c = 0; c < nch; ++c) s += red_partial[((int64_t)i * a.max_chunks + c) * SM_RED + k];
-        vA[k] = s;
-    }
-    for (int k = 0; k < 3; ++k) {
-        float s = 0.f;
-        for (int c = 0; c < nch; ++c) s += red_partial[((int64_t)i * a.max_chunks + c) * SM_RED + SM_AOUT + k];
-        v_trans[i * 3 + k] = s;
-    }
-    const int pc = smpl_param_count(a.d + a.g);
+    const int in = a.d + a.g;
+    const int pc = smpl_param_count(in);
     float* vp = v_params_partial + (int64_t)i * pc;
-    if (!a.visible[i]) {
-        for (int k = 0; k < SMPL_J * 4; ++k) v_theta[(int64_t)i * SMPL_J * 4 + k] = 0.f;
-        for (int k = 0; k < pc; ++k) vp[k] = 0.f;
-        for (int k = 0; k < a.g; ++k) v_mean_emb[i * a.g + k] = 0.f;
+    const float* rp = red_partial + (int64_t)i * a.max_chunks * SM_RED;
+    for (int k = tid; k < SM_RED; k += SIB_THREADS) {
+        float s = 0.f;
+        for (int c = 0; c < nch; ++c) s += rp[(int64_t)c * SM_RED + k];
+        if (k < SM_AOUT) s_vA[k] = s; else v_trans[i * 3 + (k - SM_AOUT)] = s;
+    }
+    if (!a.visible[i]) {  // block-uniform
+        for (int k = tid; k < SMPL_J * 4; k += SIB_THREADS) v_theta[(int64_t)i * SMPL_J * 4 + k] = 0.f;
+        for (int k = tid; k < pc; k += SIB_THREADS) vp[k] = 0.f;
+        for (int k = tid; k < a.g; k += SIB_THREADS) v_mean_emb[i * a.g + k] = 0.f;
         return;
     }
-    int par[SMPL_J];
-    for (int j = 0; j < SMPL_J; ++j) par[j] = a.parents[j];
-    smpl_instance_bwd(a.table + (int64_t)i * a.E * a.d, a.E, a.d, a.g, mean_emb + i * a.g, a.t, a.cur_c, a.cur_f, a.H,
-                      a.theta + (int64_t)i * SMPL_J * 4, a.J + (int64_t)i * SMPL_J * 3,
-                      a.A0inv + (int64_t)i * SMPL_J * 16, par, vA, v_theta + (int64_t)i * SMPL_J * 4, vp,
-                      v_table + (int64_t)i * a.E * a.d, v_mean_emb + i * a.g);
+    const float* table = a.table + (int64_t)i * a.E * a.d;
+    const float* theta = a.theta + (int64_t)i * SMPL_J * 4;
+    const float* J = a.J + (int64_t)i * SMPL_J * 3;
+    const float* A0inv = a.A0inv + (int64_t)i * SMPL_J * 16;
+    TembTaps tc, tf;
+    temb_taps(a.t, a.cur_c, a.E, tc);
+    temb_taps(a.t, a.cur_f, a.E, tf);
+    for (int k = tid; k < in; k += SIB_THREADS) {
+        float c, f;
+        if (k < a.d) {
+            c = 0.f; f = 0.f;
+            for (int q = 0; q < 4; ++q) { c += tc.w[q] * table[tc.row[q] * a.d + k]; f += tf.w[q] * table[tf.row[q] * a.d + k]; }
+        } else {
+            c = f = mean_emb[i * a.g + (k - a.d)];
+        }
+        s_hc[k] = c; s_hf[k] = f;
+    }
+    if (tid < SMPL_J) s_par[tid] = a.parents[tid];
+    __syncthreads();
+    if (tid < SMPL_J) {
+        float sc = a.H.c_b[tid], sf = a.H.f_b[tid];
+        for (int k = 0; k < in; ++k) { sc += a.H.c_w[tid * in + k] * s_hc[k]; sf += a.H.f_w[tid * in + k] * s_hf[k]; }
+        s_ac[tid] = sc; s_af[tid] = sf;
+    }
+    __syncthreads();
+    if (tid == 0) s_skip = (any_nan(s_ac, SMPL_J) || any_nan(s_af, SMPL_J)) ? 1 : 0;
+    __syncthreads();
+    const bool skip = s_skip != 0;
+    if (tid < SMPL_J) {
+        const int j = tid;
+        float th[4];
+        if (skip) { for (int k = 0; k < 4; ++k) th[k] = theta[j * 4 + k]; }
+        else {
+            const float qc[4] = {cosf(s_ac[j]), 0.f, 0.f, sinf(s_ac[j])}, qf[4] = {cosf(s_af[j]), 0.f, 0.f, sinf(s_af[j])};
+            float qo[4];
+            qmul(qc, qf, qo);
+            qmul(theta + j * 4, qo, th);
+            for (int k = 0; k < 4; ++k) s_qo[j][k] = qo[k];
+        }
+        float thn[4], R[9];
+        s_thinv[j] = qnormalize(th, thn);
+        qrot(thn, R);
+        for (int k = 0; k < 4; ++k) s_thn[j][k] = thn[k];
+        for (int k = 0; k < 9; ++k) s_R[j][k] = R[k];
+        // v_G from v_A:  A.R = G.R Ri ; A.t = G.R ti + (G.t - G.R J)
+        const float* I4 = A0inv + j * 16;
+        const float Ri[9] = {I4[0], I4[1], I4[2], I4[4], I4[5], I4[6], I4[8], I4[9], I4[10]};
+        const float ti[3] = {I4[3], I4[7], I4[11]};
+        const float* vAR = s_vA + j * 12;
+        const float* vAt = s_vA + j * 12 + 9;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) {
+                float s = vAR[r * 3] * Ri[c * 3] + vAR[r * 3 + 1] * Ri[c * 3 + 1] + vAR[r * 3 + 2] * Ri[c * 3 + 2];
+                s += vAt[r] * (ti[c] - J[j * 3 + c]);
+                s_vG[j][r * 3 + c] = s;
+            }
+        for (int k = 0; k < 3; ++k) s_vG[j][9 + k] = vAt[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // forward chain (parents precede children), then the reverse sweep
+        for (int j = 0; j < SMPL_J; ++j) {
+            const int p = s_par[j];
+            if (p < 0) {
+                for (int k = 0; k < 9; ++k) s_G[j][k] = s_R[j][k];
+                for (int k = 0; k < 3; ++k) s_G[j][9 + k] = J[j * 3 + k];
+            } else {
+                const float rel[3] = {J[j * 3] - J[p * 3], J[j * 3 + 1] - J[p * 3 + 1], J[j * 3 + 2] - J[p * 3 + 2]};
+                mat3_mul(s_G[p], s_R[j], s_G[j]);
+                float tr[3];
+                mat3_vec(s_G[p], rel, tr);
+                for (int k = 0; k < 3; ++k) s_G[j][9 + k] = tr[k] + s_G[p][9 + k];
+            }
+        }
+        for (int j = SMPL_J - 1; j >= 0; --j) {
+            const int p = s_par[j];
+            if (p < 0) {
+                for (int k = 0; k < 9; ++k) s_vR[j][k] = s_vG[j][k];
+            } else {
+                const float rel[3] = {J[j * 3] - J[p * 3], J[j * 3 + 1] - J[p * 3 + 1], J[j * 3 + 2] - J[p * 3 + 2]};
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) {
+                        s_vG[p][r * 3 + c] += s_vG[j][r * 3] * s_R[j][c * 3] + s_vG[j][r * 3 + 1] * s_R[j][c * 3 + 1] +
+                                              s_vG[j][r * 3 + 2] * s_R[j][c * 3 + 2] + s_vG[j][9 + r] * rel[c];
+                        s_vR[j][r * 3 + c] = s_G[p][0 * 3 + r] * s_vG[j][0 * 3 + c] + s_G[p][1 * 3 + r] * s_vG[j][1 * 3 + c] +
+                                             s_G[p][2 * 3 + r] * s_vG[j][2 * 3 + c];
+                    }
+                for (int k = 0; k < 3; ++k) s_vG[p][9 + k] += s_vG[j][9 + k];
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < SMPL_J) {
+        const int j = tid;
+        float vthn[4], vth[4];
+        qrot_vjp(s_thn[j], s_vR[j], vthn);
+        qnormalize_vjp(s_thn[j], s_thinv[j], vthn, vth);
+        float* vt = v_theta + (int64_t)i * SMPL_J * 4 + j * 4;
+        if (skip) {
+            for (int k = 0; k < 4; ++k) vt[k] = vth[k];
+            s_vac[j] = 0.0f;
+        } else {
+            float vqo[4];
+            qmul_vjp(theta + j * 4, s_qo[j], vth, vt, vqo);
+            s_vac[j] = -s_qo[j][3] * vqo[0] + s_qo[j][0] * vqo[3];
+        }
+    }
+    __syncthreads();
+    // head gradients: v_W[o][k] = v_ac[o] h[k], v_b[o] = v_ac[o]; layout c_w | c_b | f_w | f_b  (all zero when skipped)
+    const int wsz = SMPL_J * in;
+    for (int e = tid; e < pc; e += SIB_THREADS) {
+        float v = 0.f;
+        if (!skip) {
+            if (e < wsz) v = s_vac[e / in] * s_hc[e % in];
+            else if (e < wsz + SMPL_J) v = s_vac[e - wsz];
+            else if (e < 2 * wsz + SMPL_J) { const int q = e - wsz - SMPL_J; v = s_vac[q / in] * s_hf[q % in]; }
+            else v = s_vac[e - 2 * wsz - SMPL_J];
+        }
+        vp[e] = v;
+    }
+    for (int k = tid; k < in; k += SIB_THREADS) {
+        float c = 0.f, f = 0.f;
+        if (!skip)
+            for (int o = 0; o < SMPL_J; ++o) { c += a.H.c_w[o * in + k] * s_vac[o]; f += a.H.f_w[o * in + k] * s_vac[o]; }
+        s_vhc[k] = c; s_vhf[k] = f;
+    }
+    __syncthreads();
+    // temporal-table VJP: thread k owns column k of this instance's [E][d] slab (taps applied in the reference order)
+    float* vtab = v_table + (int64_t)i * a.E * a.d;
+    for (int k = tid; k < a.d; k += SIB_THREADS) {
+        for (int q = 0; q < 4; ++q) if (tc.w[q] != 0.0f) vtab[tc.row[q] * a.d + k] += tc.w[q] * s_vhc[k];
+        for (int q = 0; q < 4; ++q) if (tf.w[q] != 0.0f) vtab[tf.row[q] * a.d + k] += tf.w[q] * s_vhf[k];
+    }
+    for (int k = tid; k < a.g; k += SIB_THREADS) v_mean_emb[i * a.g + k] = s_vhc[a.d + k] + s_vhf[a.d + k];
 }
 
 __global__ void smpl_params_reduce_kernel(const float* __restrict__ partial, int I, int pc, float* __restrict__ out) {
@@ -333,7 +469,7 @@ extern "C" int emd_smpl_deform_bwd(const float* means, const float* quats, const
     dim3 sg(a.max_chunks, I);
     EMD_LAUNCH(EK_SMPL_BWD, stream, smpl_points_bwd_kernel<<<sg, SM_THREADS, 0, stream>>>(a, A, means, quats, v_world_means, v_world_quats, v_means,
                                                           v_quats, red_partial));
-    EMD_LAUNCH(EK_SMPL_BWD, stream, smpl_instance_bwd_kernel<<<(I + 31) / 32, 32, 0, stream>>>(a, mean_emb, red_partial, v_theta, v_trans,
+    EMD_LAUNCH(EK_SMPL_BWD, stream, smpl_instance_bwd_kernel<<<I, SIB_THREADS, 0, stream>>>(a, mean_emb, red_partial, v_theta, v_trans,
                                                                params_partial, v_table, v_mean_emb));
     const int pc = smpl_param_count(d + g);
     EMD_LAUNCH(EK_SMPL_BWD, stream, smpl_params_reduce_kernel<<<(pc + 127) / 128, 128, 0, stream>>>(params_partial, I, pc, v_params));

@@ -41,9 +41,29 @@ constexpr int CKPT_FLOATS = 5 * RB;       // per segment boundary: T and acc[4] 
 // aligned float4 records so a staged Gaussian costs three 128-bit loads.
 //   rec0 = (mean_x, mean_y, opacity, conic_a)
 //   rec1 = (conic_b, conic_c, ch0, ch1)
-//   rec2 = (ch2, ch3, 0, 0)
+//   rec2 = (ch2, ch3, hx, hy)
 // Channels: the D_color colour channels, then (optionally) the camera depth.
+// (hx, hy): half extents of the axis-aligned box around the region where the
+// Gaussian can pass the compositor's alpha test, opacity * exp(-sigma) >= 1/255
+// <=> sigma <= ln(255 opacity): |dx| <= sqrt(2 tau c / det), |dy| <= sqrt(2 tau a / det).
+// Conservative (tau, det and the result carry safety margins far above the
+// rounding of __expf / the conic), so skipping a (pixel block, Gaussian) pair
+// outside the box never changes a result.  NaN = "never passes" (opacity < 1/255),
+// +inf = "no bound" (degenerate conic).
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void alpha_extent(float opac, float ca, float cb, float cc, float& hx, float& hy) {
+    const float tau = __logf(255.0f * opac) + 0.02f;   // NaN / negative when the Gaussian can never reach 1/255
+    const float ac = ca * cc;
+    const float det = ac - cb * cb - 4e-6f * fabsf(ac);  // lower bound of the conic determinant under fp32 rounding
+    if (!(det > 0.0f) || !(ca > 0.0f) || !(cc > 0.0f)) {
+        hx = hy = (tau >= 0.0f) ? __int_as_float(0x7f800000) : __int_as_float(0x7fc00000);
+        return;
+    }
+    const float k = 2.0f * tau / det;                   // negative tau -> sqrt(negative) = NaN -> culled everywhere
+    hx = sqrtf(k * cc) * 1.001f + 0.02f;
+    hy = sqrtf(k * ca) * 1.001f + 0.02f;
+}
+
 __global__ void raster_pack_kernel(const float* __restrict__ means2d, const float* __restrict__ conics,
                                    const float* __restrict__ opacities, int opac_per_cam,
                                    const float* __restrict__ colors, int colors_per_cam, int d_color,
@@ -61,10 +81,36 @@ __global__ void raster_pack_kernel(const float* __restrict__ means2d, const floa
     const float* cp = colors + (colors_per_cam ? ci : i) * d_color;
     for (int k = 0; k < d_color; ++k) ch[k] = __ldg(cp + k);
     if (with_depth) ch[d_color] = __ldg(depths + ci);
+    float hx, hy;
+    alpha_extent(op, ca, cb, cc, hx, hy);
     recs[ci * 3 + 0] = make_float4(m.x, m.y, op, ca);
     recs[ci * 3 + 1] = make_float4(cb, cc, ch[0], ch[1]);
-    recs[ci * 3 + 2] = make_float4(ch[2], ch[3], 0.f, 0.f);
+    recs[ci * 3 + 2] = make_float4(ch[2], ch[3], hx, hy);
 }
+
+// A CTA's 8 warps own the 8 blocks of 8x4 pixels of a 16x16 tile (2 across, 4 down): compact footprints
+// keep the per-warp "does any of my pixels see this Gaussian" rate low.
+//   warp w -> block (bx = w & 1, by = w >> 1); lane l -> (lx = l & 7, ly = l >> 3)
+// block_mask: bit w set iff the alpha box of a staged Gaussian reaches a pixel centre of block w.
+// (cx0, cy0) = centre of the tile's first pixel.  Comparisons with NaN are false -> mask 0.
+__device__ __forceinline__ uint32_t block_mask(float mx, float my, float hx, float hy, float cx0, float cy0) {
+    const float xlo = mx - hx, xhi = mx + hx, ylo = my - hy, yhi = my + hy;
+    uint32_t cols = 0, mask = 0;
+    if (xhi >= cx0 && xlo <= cx0 + 7.0f) cols |= 1u;
+    if (xhi >= cx0 + 8.0f && xlo <= cx0 + 15.0f) cols |= 2u;
+#pragma unroll
+    for (int by = 0; by < 4; ++by)
+        if (yhi >= cy0 + 4.0f * by && ylo <= cy0 + 4.0f * by + 3.0f) mask |= cols << (2 * by);
+    return mask;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// exp(-sigma); underflow flushes to zero (the alpha test rejects those anyway)
+__device__ __forceinline__ float exp_neg(float sigma) { return ex2_approx(sigma * -1.4426950408889634f); }
 
 // ---------------------------------------------------------------------------
 // forward
@@ -78,6 +124,7 @@ __global__ void __launch_bounds__(RB) raster_fwd_kernel(
     __shared__ float4 s_r0[RB];
     __shared__ float4 s_r1[RB];
     __shared__ float2 s_r2[RB];
+    __shared__ uint32_t s_mask[RB];
 
     // heaviest tiles first (longest-processing-time-first): the long horizon tiles then overlap
     // with the many short ones instead of running alone at the tail of the grid
@@ -85,10 +132,12 @@ __global__ void __launch_bounds__(RB) raster_fwd_kernel(
     const int cam = tile_id / (tile_w * tile_h);
     const int tile_y = (tile_id - cam * tile_w * tile_h) / tile_w;
     const int tile_x = tile_id - (cam * tile_h + tile_y) * tile_w;
-    const int tr = threadIdx.y * EMD_TILE + threadIdx.x;
-    const int i = tile_y * EMD_TILE + threadIdx.y;
-    const int j = tile_x * EMD_TILE + threadIdx.x;
+    const int tr = threadIdx.x;
+    const int lane = tr & 31, warp = tr >> 5;
+    const int i = tile_y * EMD_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const int j = tile_x * EMD_TILE + (warp & 1) * 8 + (lane & 7);
     const float px = (float)j + cfg.px_off, py = (float)i + cfg.px_off;
+    const float cx0 = (float)(tile_x * EMD_TILE) + cfg.px_off, cy0 = (float)(tile_y * EMD_TILE) + cfg.px_off;
     const bool inside = i < height && j < width;
     bool done = !inside;
 
@@ -110,42 +159,56 @@ __global__ void __launch_bounds__(RB) raster_fwd_kernel(
         }
         const int64_t batch_start = range_start + (int64_t)RB * b;
         const int64_t idx = batch_start + tr;
+        uint32_t mask = 0;
         if (idx < range_end) {
             const int64_t g = flatten_ids[idx];
-            s_r0[tr] = __ldg(recs + g * 3 + 0);
-            s_r1[tr] = __ldg(recs + g * 3 + 1);
+            const float4 r0 = __ldg(recs + g * 3 + 0);
             const float4 r2 = __ldg(recs + g * 3 + 2);
+            s_r0[tr] = r0;
+            s_r1[tr] = __ldg(recs + g * 3 + 1);
             s_r2[tr] = make_float2(r2.x, r2.y);
+            mask = block_mask(r0.x, r0.y, r2.z, r2.w, cx0, cy0);
         }
+        s_mask[tr] = mask;
         __syncthreads();
-        const int batch_size = (int)min((int64_t)RB, range_end - batch_start);
+        if (__all_sync(0xffffffffu, done)) continue;  // every pixel of this warp's block has saturated
+        // This warp's list: the staged Gaussians whose alpha box reaches its 8x4 block, 32 candidates per ballot.
         // Groups of 4: the alphas (sigma, exp) do not depend on the running transmittance, so four are
-        // evaluated with full ILP before the short sequential T / accumulate chain.  This matters for
-        // the long horizon tiles, whose CTA ends up alone on its SM and is latency-bound otherwise.
-        for (int t = 0; t < batch_size && !done; t += 4) {
-            float alpha[4];
-            bool ok[4];
+        // evaluated with full ILP before the short sequential T / accumulate chain.
+        for (int chunk = 0; chunk < RB / 32; ++chunk) {
+            uint32_t word = __ballot_sync(0xffffffffu, (s_mask[chunk * 32 + lane] >> warp) & 1u);
+            while (word) {
+                int tt[4];
+                float alpha[4];
+                bool ok[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int tt = min(t + u, RB - 1);
-                const float4 r0 = s_r0[tt];
-                const float4 r1 = s_r1[tt];
-                const float dx = r0.x - px, dy = r0.y - py;
-                const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
-                alpha[u] = fminf(cfg.alpha_max, r0.z * __expf(-sigma));
-                ok[u] = (t + u < batch_size) && !(sigma < 0.f || alpha[u] < ALPHA_MIN);
-            }
+                for (int u = 0; u < 4; ++u) {
+                    tt[u] = word ? chunk * 32 + __ffs(word) - 1 : -1;
+                    word &= word - 1;   // 0 & 0xffffffff stays 0
+                }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (!ok[u] || done) continue;
-                const float next_T = T * (1.0f - alpha[u]);
-                if (cfg.strict_stop ? (next_T < 1e-4f) : (next_T <= 1e-4f)) { done = true; continue; }
-                const float vis = alpha[u] * T;
-                const float4 r1 = s_r1[t + u];
-                const float2 r2 = s_r2[t + u];
-                acc[0] += r1.z * vis; acc[1] += r1.w * vis; acc[2] += r2.x * vis; acc[3] += r2.y * vis;
-                cur_idx = (int32_t)(batch_start + t + u);
-                T = next_T;
+                for (int u = 0; u < 4; ++u) {
+                    const int t = max(tt[u], 0);
+                    const float4 r0 = s_r0[t];
+                    const float4 r1 = s_r1[t];
+                    const float dx = r0.x - px, dy = r0.y - py;
+                    const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
+                    alpha[u] = fminf(cfg.alpha_max, r0.z * exp_neg(sigma));
+                    ok[u] = (tt[u] >= 0) && !(sigma < 0.f || alpha[u] < ALPHA_MIN);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (!ok[u] || done) continue;
+                    const float next_T = T * (1.0f - alpha[u]);
+                    if (cfg.strict_stop ? (next_T < 1e-4f) : (next_T <= 1e-4f)) { done = true; continue; }
+                    const float vis = alpha[u] * T;
+                    const float4 r1 = s_r1[tt[u]];
+                    const float2 r2 = s_r2[tt[u]];
+                    acc[0] += r1.z * vis; acc[1] += r1.w * vis; acc[2] += r2.x * vis; acc[3] += r2.y * vis;
+                    cur_idx = (int32_t)(batch_start + tt[u]);
+                    T = next_T;
+                }
+                if (__all_sync(0xffffffffu, done)) { word = 0; chunk = RB / 32; }
             }
         }
     }
@@ -209,6 +272,7 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
     __shared__ float4 s_r1[RB];
     __shared__ float2 s_r2[RB];
     __shared__ uint32_t s_slot[RB];
+    __shared__ uint32_t s_mask[RB];
     __shared__ float s_slab[RB / 32][32][NPART];
     __shared__ uint32_t s_tmask[RB / 32];
     __shared__ int s_red[RB / 32];
@@ -227,11 +291,12 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
     const int cam = tile_id / (tile_w * tile_h);
     const int tile_y = (tile_id - cam * tile_w * tile_h) / tile_w;
     const int tile_x = tile_id - (cam * tile_h + tile_y) * tile_w;
-    const int tr = threadIdx.y * EMD_TILE + threadIdx.x;
+    const int tr = threadIdx.x;
     const int lane = tr & 31, warp = tr >> 5;
-    const int i = tile_y * EMD_TILE + threadIdx.y;
-    const int j = tile_x * EMD_TILE + threadIdx.x;
+    const int i = tile_y * EMD_TILE + (warp >> 1) * 4 + (lane >> 3);   // same pixel <-> thread map as the forward
+    const int j = tile_x * EMD_TILE + (warp & 1) * 8 + (lane & 7);
     const float px = (float)j + cfg.px_off, py = (float)i + cfg.px_off;
+    const float cx0 = (float)(tile_x * EMD_TILE) + cfg.px_off, cy0 = (float)(tile_y * EMD_TILE) + cfg.px_off;
     const bool inside = i < height && j < width;
     const int64_t pix = ((int64_t)cam * height + min(i, height - 1)) * width + min(j, width - 1);
 
@@ -264,6 +329,7 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
     if (backgrounds) {
         for (int k = 0; k < CH; ++k) bg_dot += backgrounds[cam * CH + k] * v_c[k];
     }
+    const float v_a_eff = T_final * (v_a - bg_dot);   // d(out)/d(alpha_i) term shared by every Gaussian of the pixel
     float buf[4] = {0.f, 0.f, 0.f, 0.f};
     if (inside && bin_final >= range_end) {
         // the pixel blended Gaussians beyond this segment: start from the forward checkpoint taken at the
@@ -283,7 +349,7 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
         }
     }
 
-    // last sorted index any pixel of this tile blended
+    // last sorted index any pixel of this warp / this tile blended
     int wmax = (int)max(bin_final, (int64_t)-1);
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
@@ -301,40 +367,45 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
         const int64_t batch_lo = max(range_start, batch_hi - RB);
         const int batch_size = (int)(batch_hi - batch_lo);
         __syncthreads();
+        uint32_t mask = 0;
         if (tr < batch_size) {
             // slot tr holds sorted index batch_hi-1-tr  (slot 0 = farthest)
             const int64_t idx = batch_hi - 1 - tr;
             const int64_t g = flatten_ids[idx];
             const float4 r0 = __ldg(recs + g * 3 + 0);
+            const float4 r2 = __ldg(recs + g * 3 + 2);
             s_r0[tr] = r0;
             s_r1[tr] = __ldg(recs + g * 3 + 1);
-            const float4 r2 = __ldg(recs + g * 3 + 2);
             s_r2[tr] = make_float2(r2.x, r2.y);
+            mask = block_mask(r0.x, r0.y, r2.z, r2.w, cx0, cy0);
             int x0, y0, x1, y1;
             if (cfg.dg_rect) tile_rect_dg(r0.x, r0.y, radii[g], tile_w, tile_h, x0, y0, x1, y1);
             else tile_rect_c(r0.x, r0.y, radii[g], tile_w, tile_h, x0, y0, x1, y1);
             const int64_t base = g == 0 ? 0 : cum_tiles[g - 1];
             s_slot[tr] = (uint32_t)(base + (int64_t)(tile_y - y0) * (x1 - x0) + (tile_x - x0));
         }
+        s_mask[tr] = mask;
         __syncthreads();
         for (int sub = 0; sub < batch_size; sub += 32) {
             const int sub_n = min(32, batch_size - sub);
+            // this warp's candidates of the 32 staged Gaussians: alpha box reaches its 8x4 block, and the
+            // Gaussian is not behind everything the block's pixels blended
+            const int64_t idx_l = batch_hi - 1 - (sub + lane);
+            uint32_t word = __ballot_sync(0xffffffffu, ((s_mask[sub + lane] >> warp) & 1u) && idx_l <= (int64_t)wmax);
             uint32_t tmask = 0;
-            for (int u = 0; u < sub_n; ++u) {
+            while (word) {
+                const int u = __ffs(word) - 1;
+                word &= word - 1;
                 const int t = sub + u;
                 const int64_t idx = batch_hi - 1 - t;
                 bool valid = inside && idx <= bin_final;
-                float4 r0, r1;
-                float dx = 0.f, dy = 0.f, vis = 0.f, alpha = 0.f;
-                if (valid) {
-                    r0 = s_r0[t];
-                    r1 = s_r1[t];
-                    dx = r0.x - px; dy = r0.y - py;
-                    const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
-                    vis = __expf(-sigma);
-                    alpha = fminf(cfg.alpha_max, r0.z * vis);
-                    if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
-                }
+                const float4 r0 = s_r0[t];
+                const float4 r1 = s_r1[t];
+                const float dx = r0.x - px, dy = r0.y - py;
+                const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
+                const float vis = exp_neg(sigma);
+                const float alpha = fminf(cfg.alpha_max, r0.z * vis);
+                if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
                 if (!__any_sync(0xffffffffu, valid)) continue;
                 float v[16];
 #pragma unroll
@@ -351,8 +422,7 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
                         v[k] = fac * v_c[k];
                         v_alpha += (col[k] * T - buf[k] * ra) * v_c[k];
                     }
-                    v_alpha += T_final * ra * v_a;
-                    v_alpha -= T_final * ra * bg_dot;
+                    v_alpha += ra * v_a_eff;
                     const float opac = r0.z;
                     if (opac * vis <= cfg.alpha_max) {
                         const float v_sigma = -opac * vis * v_alpha;
@@ -374,23 +444,25 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
                 tmask |= 1u << u;
             }
             if (lane == 0) s_tmask[warp] = tmask;
-            __syncthreads();
-            // fixed-order cross-warp sum, one writer per (Gaussian, component)
-            for (int q = tr; q < sub_n * NPART; q += RB) {
-                const int u = q / NPART, k = q - u * NPART;
-                float sum = 0.f;
-                bool any = false;
+            // barrier + block-wide "did any warp produce a partial for these 32 Gaussians"
+            if (__syncthreads_or(tmask != 0)) {
+                // fixed-order cross-warp sum, one writer per (Gaussian, component)
+                for (int q = tr; q < sub_n * NPART; q += RB) {
+                    const int u = q / NPART, k = q - u * NPART;
+                    float sum = 0.f;
+                    bool any = false;
 #pragma unroll
-                for (int w = 0; w < RB / 32; ++w) {
-                    if (s_tmask[w] & (1u << u)) { sum += s_slab[w][u][k]; any = true; }
+                    for (int w = 0; w < RB / 32; ++w) {
+                        if (s_tmask[w] & (1u << u)) { sum += s_slab[w][u][k]; any = true; }
+                    }
+                    if (any) {
+                        const uint32_t slot = s_slot[sub + u];
+                        partials[(int64_t)slot * NPART + k] = sum;
+                        if (k == 0) touched[slot] = 1;
+                    }
                 }
-                if (any) {
-                    const uint32_t slot = s_slot[sub + u];
-                    partials[(int64_t)slot * NPART + k] = sum;
-                    if (k == 0) touched[slot] = 1;
-                }
+                __syncthreads();
             }
-            __syncthreads();
         }
     }
 }
@@ -550,7 +622,7 @@ extern "C" int emd_rasterize_fwd(const float* recs, const int32_t* tile_offsets,
         emd_set_error("rasterize_fwd: recs/out_colors must be 16-B aligned");
         return EMD_ERR_ALIGN;
     }
-    dim3 grid((unsigned)(C * tile_w * tile_h)), block(EMD_TILE, EMD_TILE, 1);
+    dim3 grid((unsigned)(C * tile_w * tile_h)), block(RB, 1, 1);
     EMD_LAUNCH(EK_RASTER_FWD, stream, raster_fwd_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, tile_order, P,
                                                   (int)C, width, height, tile_w, tile_h, channels, ed_mode, cfg,
                                                   backgrounds, ckpt_base, ckpt, out_colors, out_alphas, last_ids));
@@ -594,7 +666,7 @@ extern "C" int emd_rasterize_bwd(const float* recs, const int32_t* tile_offsets,
     if (P > 0) {
         cudaMemsetAsync(touched, 0, (size_t)P, stream);
         // upper bound on the number of (tile, segment) CTAs; surplus CTAs exit at once
-        dim3 grid((unsigned)(P / SEG + C * tile_w * tile_h)), block(EMD_TILE, EMD_TILE, 1);
+        dim3 grid((unsigned)(P / SEG + C * tile_w * tile_h)), block(RB, 1, 1);
         EMD_LAUNCH(EK_RASTER_BWD, stream, raster_bwd_kernel<<<grid, block, 0, stream>>>(
             reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, tile_order, radii, cum_tiles, P, (int)C, width,
             height, tile_w, tile_h, channels, ed_mode, cfg, backgrounds, seg_prefix, ckpt_base, ckpt, out_colors, out_alphas,
