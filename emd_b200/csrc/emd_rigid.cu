@@ -79,26 +79,76 @@ struct RigidArgs {
     int max_chunks;
 };
 
-__global__ void rigid_instance_fwd_kernel(RigidArgs a, const float* __restrict__ seg_partial,
-                                          float* __restrict__ mean_emb, float* __restrict__ inst_out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.I) return;
+// One warp-pair CTA per instance: features and the 8 head outputs in parallel, the quaternion algebra on one
+// thread.  Same arithmetic / summation order as rigid_instance_fwd (emd_math.cuh).
+constexpr int RI_THREADS = 64;
+__device__ __forceinline__ void rigid_features(const RigidArgs& a, int i, const float* m /*smem [g]*/, float* s_hc,
+                                               float* s_hf, TembTaps& tc, TembTaps& tf) {
+    const float* table = a.table + (int64_t)i * a.E * a.d;
+    temb_taps(a.t, a.cur_c, a.E, tc);
+    temb_taps(a.t, a.cur_f, a.E, tf);
+    for (int k = threadIdx.x; k < a.d + a.g; k += RI_THREADS) {
+        float c, f;
+        if (k < a.d) {
+            c = 0.f; f = 0.f;
+            for (int q = 0; q < 4; ++q) { c += tc.w[q] * table[tc.row[q] * a.d + k]; f += tf.w[q] * table[tf.row[q] * a.d + k]; }
+        } else {
+            c = f = m[k - a.d];
+        }
+        s_hc[k] = c; s_hf[k] = f;
+    }
+}
+// head outputs y[0..2] = trans_c, y[3..5] = trans_f, y[6] = rot_c, y[7] = rot_f  (thread o < 8 computes y[o])
+__device__ __forceinline__ float rigid_head(const RigidArgs& a, int o, const float* s_hc, const float* s_hf) {
+    const int in = a.d + a.g;
+    const float* W; const float* h; float s;
+    if (o < 3) { W = a.H.trans_c_w + o * in; s = a.H.trans_c_b[o]; h = s_hc; }
+    else if (o < 6) { W = a.H.trans_f_w + (o - 3) * in; s = a.H.trans_f_b[o - 3]; h = s_hf; }
+    else if (o == 6) { W = a.H.rot_c_w; s = a.H.rot_c_b[0]; h = s_hc; }
+    else { W = a.H.rot_f_w; s = a.H.rot_f_b[0]; h = s_hf; }
+    for (int k = 0; k < in; ++k) s += W[k] * h[k];
+    return s;
+}
+
+__global__ void __launch_bounds__(RI_THREADS) rigid_instance_fwd_kernel(RigidArgs a, const float* __restrict__ seg_partial,
+                                                                        float* __restrict__ mean_emb,
+                                                                        float* __restrict__ inst_out) {
+    __shared__ float s_m[EMD_GDIM_MAX], s_hc[EMD_TDIM_MAX + EMD_GDIM_MAX], s_hf[EMD_TDIM_MAX + EMD_GDIM_MAX], s_y[8];
+    const int i = blockIdx.x, tid = threadIdx.x;
     const int64_t cnt = a.seg_start[i + 1] - a.seg_start[i];
     const int nch = (int)((cnt + RG_CHUNK - 1) / RG_CHUNK);
-    float m[EMD_GDIM_MAX];
-    for (int k = 0; k < a.g; ++k) {
+    if (tid < a.g) {
         float s = 0.f;
-        for (int c = 0; c < nch; ++c) s += seg_partial[((int64_t)i * a.max_chunks + c) * a.g + k];
-        m[k] = s / (float)cnt;  // 0/0 = NaN for an empty instance, exactly like torch.mean of an empty slice
-        mean_emb[i * a.g + k] = m[k];
+        for (int c = 0; c < nch; ++c) s += seg_partial[((int64_t)i * a.max_chunks + c) * a.g + tid];
+        s_m[tid] = s / (float)cnt;  // 0/0 = NaN for an empty instance, exactly like torch.mean of an empty slice
+        mean_emb[i * a.g + tid] = s_m[tid];
     }
-    RigidInstOut o;
-    rigid_instance_fwd(a.table + (int64_t)i * a.E * a.d, a.E, a.d, a.g, m, a.t, a.cur_c, a.cur_f, a.H,
-                       a.pose_q_means + i * 4, a.pose_q_quats + i * 4, a.pose_t + i * 3, o);
+    __syncthreads();
+    TembTaps tc, tf;
+    rigid_features(a, i, s_m, s_hc, s_hf, tc, tf);
+    __syncthreads();
+    if (tid < 8) s_y[tid] = rigid_head(a, tid, s_hc, s_hf);
+    __syncthreads();
+    if (tid != 0) return;
+    const float* pose_q_means = a.pose_q_means + i * 4;
+    const float* pose_q_quats = a.pose_q_quats + i * 4;
+    const float* pose_t = a.pose_t + i * 3;
+    const float dt[3] = {s_y[0] + s_y[3], s_y[1] + s_y[4], s_y[2] + s_y[5]};
+    const float ac = s_y[6], af = s_y[7];
+    const float qc[4] = {cosf(ac), 0.f, 0.f, sinf(ac)}, qf[4] = {cosf(af), 0.f, 0.f, sinf(af)};
+    float qoff[4], qn[4], R[9], Qg[4], Q[4];
+    qmul(qc, qf, qoff);
+    qnormalize(pose_q_means, qn);
+    qrot(qn, R);
+    const bool skip_t = any_nan(dt, 3);
+    const bool skip_q = any_nan(qoff, 4);
+    if (skip_q) { for (int k = 0; k < 4; ++k) Qg[k] = pose_q_quats[k]; }
+    else qmul(pose_q_quats, qoff, Qg);
+    qnormalize(Qg, Q);
     float* out = inst_out + i * RG_INST;
-    for (int k = 0; k < 9; ++k) out[k] = o.R[k];
-    for (int k = 0; k < 3; ++k) out[9 + k] = o.t[k];
-    for (int k = 0; k < 4; ++k) out[12 + k] = o.Q[k];
+    for (int k = 0; k < 9; ++k) out[k] = R[k];
+    for (int k = 0; k < 3; ++k) out[9 + k] = pose_t[k] + (skip_t ? 0.0f : dt[k]);
+    for (int k = 0; k < 4; ++k) out[12 + k] = Q[k];
 }
 
 __global__ void __launch_bounds__(RG_THREADS) rigid_points_fwd_kernel(
@@ -161,26 +211,96 @@ __global__ void __launch_bounds__(RG_THREADS) rigid_points_bwd_kernel(
         for (int k = 0; k < RG_INST; ++k) pose_partial[((int64_t)inst * max_chunks + chunk) * RG_INST + k] = acc[k];
 }
 
-__global__ void rigid_instance_bwd_kernel(RigidArgs a, const float* __restrict__ mean_emb,
-                                          const float* __restrict__ pose_partial, float* __restrict__ v_pose_q_means,
-                                          float* __restrict__ v_pose_q_quats, float* __restrict__ v_pose_t,
-                                          float* __restrict__ v_params_partial, float* __restrict__ v_table,
-                                          float* __restrict__ v_mean_emb) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.I) return;
+// One CTA per instance (see rigid_instance_fwd_kernel); same arithmetic as rigid_instance_bwd (emd_math.cuh).
+__global__ void __launch_bounds__(RI_THREADS) rigid_instance_bwd_kernel(
+    RigidArgs a, const float* __restrict__ mean_emb, const float* __restrict__ pose_partial,
+    float* __restrict__ v_pose_q_means, float* __restrict__ v_pose_q_quats, float* __restrict__ v_pose_t,
+    float* __restrict__ v_params_partial, float* __restrict__ v_table, float* __restrict__ v_mean_emb) {
+    constexpr int IN_MAX = EMD_TDIM_MAX + EMD_GDIM_MAX;
+    __shared__ float s_m[EMD_GDIM_MAX], s_hc[IN_MAX], s_hf[IN_MAX], s_vhc[IN_MAX], s_vhf[IN_MAX], s_y[8], s_vy[8], s_v[RG_INST];
+    __shared__ int s_skip[2];
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const int in = a.d + a.g;
     const int64_t cnt = a.seg_start[i + 1] - a.seg_start[i];
     const int nch = (int)((cnt + RG_CHUNK - 1) / RG_CHUNK);
-    float v[RG_INST];
-    for (int k = 0; k < RG_INST; ++k) {
+    if (tid < RG_INST) {
         float s = 0.f;
-        for (int c = 0; c < nch; ++c) s += pose_partial[((int64_t)i * a.max_chunks + c) * RG_INST + k];
-        v[k] = s;
+        for (int c = 0; c < nch; ++c) s += pose_partial[((int64_t)i * a.max_chunks + c) * RG_INST + tid];
+        s_v[tid] = s;
     }
-    const int pc = rigid_param_count(a.d + a.g);
-    rigid_instance_bwd(a.table + (int64_t)i * a.E * a.d, a.E, a.d, a.g, mean_emb + i * a.g, a.t, a.cur_c, a.cur_f, a.H,
-                       a.pose_q_means + i * 4, a.pose_q_quats + i * 4, a.pose_t + i * 3, v, v + 9, v + 12,
-                       v_pose_q_means + i * 4, v_pose_q_quats + i * 4, v_pose_t + i * 3,
-                       v_params_partial + (int64_t)i * pc, v_table + (int64_t)i * a.E * a.d, v_mean_emb + i * a.g);
+    if (tid < a.g) s_m[tid] = mean_emb[i * a.g + tid];
+    __syncthreads();
+    TembTaps tc, tf;
+    rigid_features(a, i, s_m, s_hc, s_hf, tc, tf);
+    __syncthreads();
+    if (tid < 8) s_y[tid] = rigid_head(a, tid, s_hc, s_hf);
+    __syncthreads();
+    if (tid == 0) {
+        const float* pose_q_means = a.pose_q_means + i * 4;
+        const float* pose_q_quats = a.pose_q_quats + i * 4;
+        const float* v_R = s_v; const float* v_t = s_v + 9; const float* v_Q = s_v + 12;
+        const float dt[3] = {s_y[0] + s_y[3], s_y[1] + s_y[4], s_y[2] + s_y[5]};
+        const float ac = s_y[6], af = s_y[7];
+        const float qc[4] = {cosf(ac), 0.f, 0.f, sinf(ac)}, qf[4] = {cosf(af), 0.f, 0.f, sinf(af)};
+        float qoff[4];
+        qmul(qc, qf, qoff);
+        const bool skip_t = any_nan(dt, 3), skip_q = any_nan(qoff, 4);
+        float qn[4], vqn[4];
+        const float inv = qnormalize(pose_q_means, qn);
+        qrot_vjp(qn, v_R, vqn);
+        qnormalize_vjp(qn, inv, vqn, v_pose_q_means + i * 4);
+        for (int k = 0; k < 3; ++k) v_pose_t[i * 3 + k] = v_t[k];
+        for (int k = 0; k < 3; ++k) { s_vy[k] = skip_t ? 0.f : v_t[k]; s_vy[3 + k] = s_vy[k]; }
+        float Qg[4], Qn[4], v_Qg[4];
+        if (skip_q) { for (int k = 0; k < 4; ++k) Qg[k] = pose_q_quats[k]; }
+        else qmul(pose_q_quats, qoff, Qg);
+        const float invQ = qnormalize(Qg, Qn);
+        qnormalize_vjp(Qn, invQ, v_Q, v_Qg);
+        float v_a = 0.f;
+        if (skip_q) {
+            for (int k = 0; k < 4; ++k) v_pose_q_quats[i * 4 + k] = v_Qg[k];
+        } else {
+            float v_qoff[4];
+            qmul_vjp(pose_q_quats, qoff, v_Qg, v_pose_q_quats + i * 4, v_qoff);
+            // qoff = qc (x) qf = (cos(ac+af), 0, 0, sin(ac+af)):  d/d ac = d/d af = (-qoff.z, 0, 0, qoff.w)
+            v_a = -qoff[3] * v_qoff[0] + qoff[0] * v_qoff[3];
+        }
+        s_vy[6] = v_a; s_vy[7] = v_a;
+        s_skip[0] = skip_t; s_skip[1] = skip_q;
+    }
+    __syncthreads();
+    // parameter partial, layout rot_c_w[in] rot_c_b[1] rot_f_w[in] rot_f_b[1] trans_c_w[3in] trans_c_b[3] trans_f_w[3in] trans_f_b[3]
+    const int pc = rigid_param_count(in);
+    float* vp = v_params_partial + (int64_t)i * pc;
+    for (int e = tid; e < pc; e += RI_THREADS) {
+        float v;
+        int q = e;
+        bool rot = true;   // a skipped branch contributes exact zeros (its features may be NaN: empty instance)
+        if (q < in) v = s_vy[6] * s_hc[q];
+        else if ((q -= in) < 1) v = s_vy[6];
+        else if ((q -= 1) < in) v = s_vy[7] * s_hf[q];
+        else if ((q -= in) < 1) v = s_vy[7];
+        else if ((q -= 1) < 3 * in) { v = s_vy[q / in] * s_hc[q % in]; rot = false; }
+        else if ((q -= 3 * in) < 3) { v = s_vy[q]; rot = false; }
+        else if ((q -= 3) < 3 * in) { v = s_vy[3 + q / in] * s_hf[q % in]; rot = false; }
+        else { v = s_vy[3 + (q - 3 * in)]; rot = false; }
+        if (s_skip[rot ? 1 : 0]) v = 0.f;
+        vp[e] = v;
+    }
+    for (int k = tid; k < in; k += RI_THREADS) {
+        float c = 0.f, f = 0.f;
+        for (int o = 0; o < 3; ++o) { c += a.H.trans_c_w[o * in + k] * s_vy[o]; f += a.H.trans_f_w[o * in + k] * s_vy[3 + o]; }
+        c += a.H.rot_c_w[k] * s_vy[6];
+        f += a.H.rot_f_w[k] * s_vy[7];
+        s_vhc[k] = c; s_vhf[k] = f;
+    }
+    __syncthreads();
+    float* vtab = v_table + (int64_t)i * a.E * a.d;
+    for (int k = tid; k < a.d; k += RI_THREADS) {
+        for (int q = 0; q < 4; ++q) if (tc.w[q] != 0.0f) vtab[tc.row[q] * a.d + k] += tc.w[q] * s_vhc[k];
+        for (int q = 0; q < 4; ++q) if (tf.w[q] != 0.0f) vtab[tf.row[q] * a.d + k] += tf.w[q] * s_vhf[k];
+    }
+    for (int k = tid; k < a.g; k += RI_THREADS) v_mean_emb[i * a.g + k] = s_vhc[a.d + k] + s_vhf[a.d + k];
 }
 
 // v_params[k] = sum_i partial[i][k], fixed order
@@ -240,7 +360,7 @@ extern "C" int emd_rigid_deform_fwd(const float* means, const float* quats, cons
     if (!emd_aligned(quats, 16) || !emd_aligned(world_quats, 16)) { emd_set_error("rigid_fwd: quats must be 16-B aligned"); return EMD_ERR_ALIGN; }
     dim3 sg(max_chunks, I);
     EMD_LAUNCH(EK_RIGID_FWD, stream, rigid_segmean_kernel<<<sg, RG_THREADS, 0, stream>>>(embeddings, g, order, seg_start, max_chunks, seg_partial));
-    EMD_LAUNCH(EK_RIGID_FWD, stream, rigid_instance_fwd_kernel<<<(I + 63) / 64, 64, 0, stream>>>(a, seg_partial, mean_emb, inst_out));
+    EMD_LAUNCH(EK_RIGID_FWD, stream, rigid_instance_fwd_kernel<<<I, RI_THREADS, 0, stream>>>(a, seg_partial, mean_emb, inst_out));
     if (N > 0)
         EMD_LAUNCH(EK_RIGID_FWD, stream, rigid_points_fwd_kernel<<<(unsigned)emd_cdiv(N, RG_THREADS), RG_THREADS, 0, stream>>>(
             means, quats, point_ids, inst_out, N, world_means, world_quats));
@@ -268,7 +388,7 @@ extern "C" int emd_rigid_deform_bwd(const float* means, const float* quats, cons
     dim3 sg(max_chunks, I);
     EMD_LAUNCH(EK_RIGID_BWD, stream, rigid_points_bwd_kernel<<<sg, RG_THREADS, 0, stream>>>(means, quats, order, seg_start, inst_out, max_chunks,
                                                            v_world_means, v_world_quats, v_means, v_quats, pose_partial));
-    EMD_LAUNCH(EK_RIGID_BWD, stream, rigid_instance_bwd_kernel<<<(I + 63) / 64, 64, 0, stream>>>(a, mean_emb, pose_partial, v_pose_q_means,
+    EMD_LAUNCH(EK_RIGID_BWD, stream, rigid_instance_bwd_kernel<<<I, RI_THREADS, 0, stream>>>(a, mean_emb, pose_partial, v_pose_q_means,
                                                                 v_pose_q_quats, v_pose_t, params_partial, v_table, v_mean_emb));
     const int pc = rigid_param_count(d + g);
     EMD_LAUNCH(EK_RIGID_BWD, stream, params_reduce_kernel<<<(pc + 127) / 128, 128, 0, stream>>>(params_partial, I, pc, v_params));

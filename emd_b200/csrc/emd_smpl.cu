@@ -66,24 +66,105 @@ __global__ void __launch_bounds__(SM_THREADS) smpl_segmean_kernel(const float* _
     }
 }
 
-__global__ void smpl_instance_fwd_kernel(SmplArgs a, const float* __restrict__ seg_partial,
-                                         float* __restrict__ mean_emb, float* __restrict__ A) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.I) return;
+// One CTA per instance: features, the 24 joint heads, joint rotations and the A = G * A0inv products run one
+// thread per joint; only the parent-to-child chain itself is sequential (one thread, shared memory).
+// Same arithmetic / summation order as smpl_instance_fwd (emd_math.cuh).
+constexpr int SIF_THREADS = 64;
+__global__ void __launch_bounds__(SIF_THREADS) smpl_instance_fwd_kernel(SmplArgs a, const float* __restrict__ seg_partial,
+                                                                        float* __restrict__ mean_emb, float* __restrict__ A) {
+    constexpr int IN_MAX = EMD_TDIM_MAX + EMD_GDIM_MAX;
+    __shared__ float s_m[EMD_GDIM_MAX], s_hc[IN_MAX], s_hf[IN_MAX], s_ac[SMPL_J], s_af[SMPL_J];
+    __shared__ float s_R[SMPL_J][9], s_G[SMPL_J][12];
+    __shared__ int s_par[SMPL_J];
+    __shared__ int s_skip;
+    const int i = blockIdx.x, tid = threadIdx.x;
     const int nch = (a.V + SM_CHUNK - 1) / SM_CHUNK;
-    float m[EMD_GDIM_MAX];
-    for (int k = 0; k < a.g; ++k) {
+    const int in = a.d + a.g;
+    if (tid < a.g) {
         float s = 0.f;
-        for (int c = 0; c < nch; ++c) s += seg_partial[((int64_t)i * a.max_chunks + c) * a.g + k];
-        m[k] = s / (float)a.V;
-        mean_emb[i * a.g + k] = m[k];
+        for (int c = 0; c < nch; ++c) s += seg_partial[((int64_t)i * a.max_chunks + c) * a.g + tid];
+        s_m[tid] = s / (float)a.V;
+        mean_emb[i * a.g + tid] = s_m[tid];
     }
-    if (!a.visible[i]) return;
-    int par[SMPL_J];
-    for (int j = 0; j < SMPL_J; ++j) par[j] = a.parents[j];
-    smpl_instance_fwd(a.table + (int64_t)i * a.E * a.d, a.E, a.d, a.g, m, a.t, a.cur_c, a.cur_f, a.H,
-                      a.theta + (int64_t)i * SMPL_J * 4, a.J + (int64_t)i * SMPL_J * 3,
-                      a.A0inv + (int64_t)i * SMPL_J * 16, par, A + (int64_t)i * SM_AOUT);
+    if (!a.visible[i]) return;  // block-uniform
+    if (tid < SMPL_J) s_par[tid] = a.parents[tid];
+    __syncthreads();
+    const float* table = a.table + (int64_t)i * a.E * a.d;
+    const float* theta = a.theta + (int64_t)i * SMPL_J * 4;
+    const float* J = a.J + (int64_t)i * SMPL_J * 3;
+    const float* A0inv = a.A0inv + (int64_t)i * SMPL_J * 16;
+    TembTaps tc, tf;
+    temb_taps(a.t, a.cur_c, a.E, tc);
+    temb_taps(a.t, a.cur_f, a.E, tf);
+    for (int k = tid; k < in; k += SIF_THREADS) {
+        float c, f;
+        if (k < a.d) {
+            c = 0.f; f = 0.f;
+            for (int q = 0; q < 4; ++q) { c += tc.w[q] * table[tc.row[q] * a.d + k]; f += tf.w[q] * table[tf.row[q] * a.d + k]; }
+        } else {
+            c = f = s_m[k - a.d];
+        }
+        s_hc[k] = c; s_hf[k] = f;
+    }
+    __syncthreads();
+    if (tid < SMPL_J) {
+        float sc = a.H.c_b[tid], sf = a.H.f_b[tid];
+        for (int k = 0; k < in; ++k) { sc += a.H.c_w[tid * in + k] * s_hc[k]; sf += a.H.f_w[tid * in + k] * s_hf[k]; }
+        s_ac[tid] = sc; s_af[tid] = sf;
+    }
+    __syncthreads();
+    if (tid == 0) s_skip = (any_nan(s_ac, SMPL_J) || any_nan(s_af, SMPL_J)) ? 1 : 0;
+    __syncthreads();
+    if (tid < SMPL_J) {
+        const int j = tid;
+        float th[4];
+        if (s_skip) { for (int k = 0; k < 4; ++k) th[k] = theta[j * 4 + k]; }
+        else {
+            const float qc[4] = {cosf(s_ac[j]), 0.f, 0.f, sinf(s_ac[j])}, qf[4] = {cosf(s_af[j]), 0.f, 0.f, sinf(s_af[j])};
+            float qo[4];
+            qmul(qc, qf, qo);
+            qmul(theta + j * 4, qo, th);
+        }
+        float thn[4], R[9];
+        qnormalize(th, thn);
+        qrot(thn, R);
+        for (int k = 0; k < 9; ++k) s_R[j][k] = R[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int j = 0; j < SMPL_J; ++j) {
+            const int p = s_par[j];
+            if (p < 0) {
+                for (int k = 0; k < 9; ++k) s_G[j][k] = s_R[j][k];
+                for (int k = 0; k < 3; ++k) s_G[j][9 + k] = J[j * 3 + k];
+            } else {
+                const float rel[3] = {J[j * 3] - J[p * 3], J[j * 3 + 1] - J[p * 3 + 1], J[j * 3 + 2] - J[p * 3 + 2]};
+                mat3_mul(s_G[p], s_R[j], s_G[j]);
+                float tr[3];
+                mat3_vec(s_G[p], rel, tr);
+                for (int k = 0; k < 3; ++k) s_G[j][9 + k] = tr[k] + s_G[p][9 + k];
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < SMPL_J) {
+        // A' = [G.R | G.t - G.R J];  A = A' * A0inv
+        const int j = tid;
+        float G[12];
+        for (int k = 0; k < 12; ++k) G[k] = s_G[j][k];
+        float RJ[3];
+        mat3_vec(G, J + j * 3, RJ);
+        const float tp[3] = {G[9] - RJ[0], G[10] - RJ[1], G[11] - RJ[2]};
+        const float* I4 = A0inv + j * 16;
+        const float Ri[9] = {I4[0], I4[1], I4[2], I4[4], I4[5], I4[6], I4[8], I4[9], I4[10]};
+        const float ti[3] = {I4[3], I4[7], I4[11]};
+        float* Ao = A + (int64_t)i * SM_AOUT + j * 12;
+        float AR[9], rt[3];
+        mat3_mul(G, Ri, AR);
+        mat3_vec(G, ti, rt);
+        for (int k = 0; k < 9; ++k) Ao[k] = AR[k];
+        for (int k = 0; k < 3; ++k) Ao[9 + k] = rt[k] + tp[k];
+    }
 }
 
 __device__ __forceinline__ void blend_T(const float* __restrict__ Wn, const float* __restrict__ Ab, float* T) {
@@ -442,7 +523,7 @@ extern "C" int emd_smpl_deform_fwd(const float* means, const float* quats, const
     const int64_t N = (int64_t)I * V;
     dim3 sg(a.max_chunks, I);
     EMD_LAUNCH(EK_SMPL_FWD, stream, smpl_segmean_kernel<<<sg, SM_THREADS, 0, stream>>>(embeddings, g, V, a.max_chunks, seg_partial));
-    EMD_LAUNCH(EK_SMPL_FWD, stream, smpl_instance_fwd_kernel<<<(I + 31) / 32, 32, 0, stream>>>(a, seg_partial, mean_emb, A));
+    EMD_LAUNCH(EK_SMPL_FWD, stream, smpl_instance_fwd_kernel<<<I, SIF_THREADS, 0, stream>>>(a, seg_partial, mean_emb, A));
     EMD_LAUNCH(EK_SMPL_FWD, stream, smpl_points_fwd_kernel<<<(unsigned)emd_cdiv(N, SM_THREADS), SM_THREADS, 0, stream>>>(a, A, means, quats, N, world_means, world_quats));
     EMD_CHECK_LAUNCH("smpl_deform_fwd");
     return EMD_OK;
