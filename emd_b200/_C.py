@@ -47,7 +47,10 @@ _SIGS = {
     "emd_tile_order": (c_int, [P, c_int64, c_int64, P, P, P, P]),
     "emd_raster_segment_size": (c_int, []),
     "emd_raster_checkpoint_floats": (c_int, []),
-    "emd_rasterize_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    "emd_raster_segout_floats": (c_int, []),
+    "emd_raster_segment_slots": (c_int64, [c_int64]),
+    "emd_rasterize_fwd": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P,
+                                  P, P, P, P]),
     "emd_dg_preprocess_fwd": (c_int, [P] * 4 + [ctypes.POINTER(c_float)] * 3 + [c_float, c_float, c_int, c_int, c_float,
                                                                               c_int, c_int, c_int64] + [P] * 7 + [P]),
     "emd_dg_preprocess_bwd": (c_int, [P] * 4 + [ctypes.POINTER(c_float)] * 3 + [c_float, c_float, c_int, c_int, c_float,

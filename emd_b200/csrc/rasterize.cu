@@ -35,6 +35,7 @@ constexpr int NPART = 12;  // floats per (tile, Gaussian) gradient slot
 constexpr int SEG_BATCHES = 4;            // a segment = 4 staged batches = 1024 Gaussians of a tile's list
 constexpr int SEG = SEG_BATCHES * RB;
 constexpr int CKPT_FLOATS = 5 * RB;       // per segment boundary: T and acc[4] of the 256 pixels
+constexpr int SEGOUT_FLOATS = 6 * RB;     // per segment of a multi-segment tile: T_end, local acc[4], last/stop code
 
 // ---------------------------------------------------------------------------
 // pack: gather the per-(camera,Gaussian) fields the compositor reads into three
@@ -115,50 +116,84 @@ __device__ __forceinline__ float exp_neg(float sigma) { return ex2_approx(sigma 
 // ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(RB) raster_fwd_kernel(
+// A tile whose sorted list is longer than SEG (1024) is composited by one CTA per 1024-Gaussian segment, all
+// segments in parallel, so the horizon tiles (tens of thousands of Gaussians) no longer run as one sequential
+// CTA at the tail of the grid:
+//   pass T (raster_fwd_seg_kernel<false>): pure transmittance product of every non-final segment, prod(1 - alpha)
+//   pass C (raster_fwd_seg_kernel<true>) : T at the segment's start = product of the segments in front of it (a
+//           pixel whose product has fallen to the stop threshold has stopped in an earlier segment); exact
+//           sequential compositing inside the segment; single-segment tiles finish here
+//   combine (raster_fwd_combine_kernel)  : per pixel, in segment order: colour sums, last contributor, the
+//           checkpoints (T, colour in front of every segment boundary) the segment-parallel backward starts from
+struct FwdTile {
+    int tile_id, cam, tile_x, tile_y, seg, nseg;
+};
+__device__ __forceinline__ bool decode_segment(const int32_t* __restrict__ seg_prefix, const int32_t* __restrict__ tile_order,
+                                               int n_cam_tiles, int tile_w, int tile_h, FwdTile& ft) {
+    if ((int)blockIdx.x >= seg_prefix[n_cam_tiles - 1]) return false;
+    int lo_r = 0, hi_r = n_cam_tiles - 1;
+    while (lo_r < hi_r) {
+        const int mid = (lo_r + hi_r) >> 1;
+        if (seg_prefix[mid] > (int)blockIdx.x) hi_r = mid; else lo_r = mid + 1;
+    }
+    const int before = lo_r > 0 ? seg_prefix[lo_r - 1] : 0;
+    ft.seg = (int)blockIdx.x - before;
+    ft.nseg = seg_prefix[lo_r] - before;
+    ft.tile_id = tile_order[lo_r];
+    ft.cam = ft.tile_id / (tile_w * tile_h);
+    ft.tile_y = (ft.tile_id - ft.cam * tile_w * tile_h) / tile_w;
+    ft.tile_x = ft.tile_id - (ft.cam * tile_h + ft.tile_y) * tile_w;
+    return true;
+}
+
+template <bool COMPOSITE>
+__global__ void __launch_bounds__(RB) raster_fwd_seg_kernel(
     const float4* __restrict__ recs, const int32_t* __restrict__ tile_offsets, const int32_t* __restrict__ flatten_ids,
-    const int32_t* __restrict__ tile_order, int64_t P, int C, int width, int height, int tile_w, int tile_h, int CH,
-    int ed_mode, RasterCfg cfg, const float* __restrict__ backgrounds, const int32_t* __restrict__ ckpt_base,
-    float* __restrict__ ckpt, float* __restrict__ out_colors, float* __restrict__ out_alphas,
+    const int32_t* __restrict__ tile_order, const int32_t* __restrict__ seg_prefix, const int32_t* __restrict__ ckpt_base,
+    int64_t P, int C, int width, int height, int tile_w, int tile_h, int CH,
+    int ed_mode, RasterCfg cfg, const float* __restrict__ backgrounds,
+    float* __restrict__ ckpt, float* __restrict__ seg_out, float* __restrict__ out_colors, float* __restrict__ out_alphas,
     int32_t* __restrict__ last_ids) {
     __shared__ float4 s_r0[RB];
     __shared__ float4 s_r1[RB];
     __shared__ float2 s_r2[RB];
     __shared__ uint32_t s_mask[RB];
 
-    // heaviest tiles first (longest-processing-time-first): the long horizon tiles then overlap
-    // with the many short ones instead of running alone at the tail of the grid
-    const int tile_id = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;
-    const int cam = tile_id / (tile_w * tile_h);
-    const int tile_y = (tile_id - cam * tile_w * tile_h) / tile_w;
-    const int tile_x = tile_id - (cam * tile_h + tile_y) * tile_w;
+    FwdTile ft;
+    if (!decode_segment(seg_prefix, tile_order, C * tile_w * tile_h, tile_w, tile_h, ft)) return;
+    if (!COMPOSITE && ft.seg == ft.nseg - 1) return;   // the product of a tile's last segment is never needed
     const int tr = threadIdx.x;
     const int lane = tr & 31, warp = tr >> 5;
-    const int i = tile_y * EMD_TILE + (warp >> 1) * 4 + (lane >> 3);
-    const int j = tile_x * EMD_TILE + (warp & 1) * 8 + (lane & 7);
+    const int i = ft.tile_y * EMD_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const int j = ft.tile_x * EMD_TILE + (warp & 1) * 8 + (lane & 7);
     const float px = (float)j + cfg.px_off, py = (float)i + cfg.px_off;
-    const float cx0 = (float)(tile_x * EMD_TILE) + cfg.px_off, cy0 = (float)(tile_y * EMD_TILE) + cfg.px_off;
+    const float cx0 = (float)(ft.tile_x * EMD_TILE) + cfg.px_off, cy0 = (float)(ft.tile_y * EMD_TILE) + cfg.px_off;
     const bool inside = i < height && j < width;
     bool done = !inside;
 
-    const int64_t range_start = tile_offsets[tile_id];
-    const int64_t range_end = (tile_id == C * tile_h * tile_w - 1) ? P : (int64_t)tile_offsets[tile_id + 1];
-    const int num_batches = (int)((range_end - range_start + RB - 1) / RB);
+    // P < 2^31 (checked by the host wrapper): sorted indices fit 32 bits
+    const int tile_start = tile_offsets[ft.tile_id];
+    const int tile_end = (ft.tile_id == C * tile_h * tile_w - 1) ? (int)P : tile_offsets[ft.tile_id + 1];
+    const int range_start = tile_start + ft.seg * SEG;
+    const int range_end = min(tile_end, range_start + SEG);
+    const int num_batches = (range_end - range_start + RB - 1) / RB;
+    const int64_t slot0 = ft.nseg > 1 ? (int64_t)ckpt_base[ft.tile_id] : 0;
 
     float T = 1.0f;
-    int32_t cur_idx = 0;
+    bool stopped = false;
+    int32_t cur_idx = -1;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (COMPOSITE && ft.seg > 0) {
+        // transmittance in front of this segment: the same left-to-right product in every CTA that needs it
+        for (int sp = 0; sp < ft.seg; ++sp) T *= ckpt[(slot0 + sp) * CKPT_FLOATS + tr];
+        if (cfg.strict_stop ? (T < 1e-4f) : (T <= 1e-4f)) done = true;   // stopped in an earlier segment
+    }
 
     for (int b = 0; b < num_batches; ++b) {
-        if (__syncthreads_count(done) >= RB) break;
-        if (ckpt != nullptr && b > 0 && (b % SEG_BATCHES) == 0) {
-            // segment boundary: per-pixel state BEFORE sorted index range_start + b*256.  The backward pass
-            // starts every 1024-Gaussian segment of a long tile from these, so segments run as parallel CTAs.
-            float* c = ckpt + ((int64_t)ckpt_base[tile_id] + b / SEG_BATCHES - 1) * CKPT_FLOATS;
-            c[tr] = T; c[RB + tr] = acc[0]; c[2 * RB + tr] = acc[1]; c[3 * RB + tr] = acc[2]; c[4 * RB + tr] = acc[3];
-        }
-        const int64_t batch_start = range_start + (int64_t)RB * b;
-        const int64_t idx = batch_start + tr;
+        if (COMPOSITE && __syncthreads_count(done) >= RB) break;
+        if (!COMPOSITE) __syncthreads();
+        const int batch_start = range_start + RB * b;
+        const int idx = batch_start + tr;
         uint32_t mask = 0;
         if (idx < range_end) {
             const int64_t g = flatten_ids[idx];
@@ -166,7 +201,7 @@ __global__ void __launch_bounds__(RB) raster_fwd_kernel(
             const float4 r2 = __ldg(recs + g * 3 + 2);
             s_r0[tr] = r0;
             s_r1[tr] = __ldg(recs + g * 3 + 1);
-            s_r2[tr] = make_float2(r2.x, r2.y);
+            if (COMPOSITE) s_r2[tr] = make_float2(r2.x, r2.y);
             mask = block_mask(r0.x, r0.y, r2.z, r2.w, cx0, cy0);
         }
         s_mask[tr] = mask;
@@ -196,20 +231,108 @@ __global__ void __launch_bounds__(RB) raster_fwd_kernel(
                     alpha[u] = fminf(cfg.alpha_max, r0.z * exp_neg(sigma));
                     ok[u] = (tt[u] >= 0) && !(sigma < 0.f || alpha[u] < ALPHA_MIN);
                 }
+                if (COMPOSITE) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (!ok[u] || done) continue;
-                    const float next_T = T * (1.0f - alpha[u]);
-                    if (cfg.strict_stop ? (next_T < 1e-4f) : (next_T <= 1e-4f)) { done = true; continue; }
-                    const float vis = alpha[u] * T;
-                    const float4 r1 = s_r1[tt[u]];
-                    const float2 r2 = s_r2[tt[u]];
-                    acc[0] += r1.z * vis; acc[1] += r1.w * vis; acc[2] += r2.x * vis; acc[3] += r2.y * vis;
-                    cur_idx = (int32_t)(batch_start + tt[u]);
-                    T = next_T;
+                    for (int u = 0; u < 4; ++u) {
+                        if (!ok[u] || done) continue;
+                        const float next_T = T * (1.0f - alpha[u]);
+                        if (cfg.strict_stop ? (next_T < 1e-4f) : (next_T <= 1e-4f)) { done = true; stopped = true; continue; }
+                        const float vis = alpha[u] * T;
+                        const float4 r1 = s_r1[tt[u]];
+                        const float2 r2 = s_r2[tt[u]];
+                        acc[0] += r1.z * vis; acc[1] += r1.w * vis; acc[2] += r2.x * vis; acc[3] += r2.y * vis;
+                        cur_idx = batch_start + tt[u];
+                        T = next_T;
+                    }
+                    if (__all_sync(0xffffffffu, done)) { word = 0; chunk = RB / 32; }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (ok[u]) T *= 1.0f - alpha[u];
                 }
-                if (__all_sync(0xffffffffu, done)) { word = 0; chunk = RB / 32; }
             }
+        }
+    }
+    if (!COMPOSITE) {
+        ckpt[(slot0 + ft.seg) * CKPT_FLOATS + tr] = T;   // staged in the checkpoint's T plane until the combine pass
+        return;
+    }
+    if (ft.nseg > 1) {
+        float* o = seg_out + (slot0 + ft.seg) * SEGOUT_FLOATS;
+        o[tr] = T; o[RB + tr] = acc[0]; o[2 * RB + tr] = acc[1]; o[3 * RB + tr] = acc[2]; o[4 * RB + tr] = acc[3];
+        // code: bit 31 = the pixel stopped inside this segment; low bits = 1 + sorted index of the last Gaussian
+        // it blended here (0 = none)
+        reinterpret_cast<uint32_t*>(o)[5 * RB + tr] = (uint32_t)(cur_idx + 1) | (stopped ? 0x80000000u : 0u);
+        return;
+    }
+    if (inside) {
+        const int64_t pix = ((int64_t)ft.cam * height + i) * width + j;
+        const float alpha_out = 1.0f - T;
+        out_alphas[pix] = alpha_out;
+        if (backgrounds) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < CH) acc[k] += T * backgrounds[ft.cam * CH + k];
+        }
+        if (ed_mode) {
+            const float inv = 1.0f / fmaxf(alpha_out, 1e-10f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k == CH - 1) acc[k] *= inv;
+        }
+        float* o = out_colors + pix * CH;
+        if (CH == 4) {
+            *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < CH) o[k] = acc[k];
+        }
+        last_ids[pix] = max(cur_idx, 0);
+    }
+}
+
+// One CTA per multi-segment tile (grid = tiles in heavy-first order; single-segment tiles leave at once).
+__global__ void __launch_bounds__(RB) raster_fwd_combine_kernel(
+    const int32_t* __restrict__ tile_order, const int32_t* __restrict__ seg_prefix, const int32_t* __restrict__ ckpt_base,
+    int C, int width, int height, int tile_w, int tile_h, int CH, int ed_mode, RasterCfg cfg,
+    const float* __restrict__ backgrounds, float* __restrict__ ckpt, const float* __restrict__ seg_out,
+    float* __restrict__ out_colors, float* __restrict__ out_alphas, int32_t* __restrict__ last_ids) {
+    const int r = blockIdx.x;
+    const int nseg = seg_prefix[r] - (r > 0 ? seg_prefix[r - 1] : 0);
+    if (nseg <= 1) return;
+    const int tile_id = tile_order[r];
+    const int cam = tile_id / (tile_w * tile_h);
+    const int tile_y = (tile_id - cam * tile_w * tile_h) / tile_w;
+    const int tile_x = tile_id - (cam * tile_h + tile_y) * tile_w;
+    const int tr = threadIdx.x;
+    const int lane = tr & 31, warp = tr >> 5;
+    const int i = tile_y * EMD_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const int j = tile_x * EMD_TILE + (warp & 1) * 8 + (lane & 7);
+    const bool inside = i < height && j < width;
+    const int64_t slot0 = ckpt_base[tile_id];
+    float T = 1.0f;        // the pixel's transmittance so far
+    float Tprod = 1.0f;    // product of the pure segment products (what pass C started each segment from)
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int32_t last = 0;
+    bool live = inside;
+    for (int sgm = 0; sgm < nseg; ++sgm) {
+        if (live && !(cfg.strict_stop ? (Tprod < 1e-4f) : (Tprod <= 1e-4f))) {
+            const float* o = seg_out + (slot0 + sgm) * SEGOUT_FLOATS;
+            T = o[tr];
+            acc[0] += o[RB + tr]; acc[1] += o[2 * RB + tr]; acc[2] += o[3 * RB + tr]; acc[3] += o[4 * RB + tr];
+            const uint32_t code = reinterpret_cast<const uint32_t*>(o)[5 * RB + tr];
+            if (code & 0x7fffffffu) last = (int32_t)(code & 0x7fffffffu) - 1;
+            if (code & 0x80000000u) live = false;
+        } else {
+            live = false;
+        }
+        if (sgm < nseg - 1) {
+            // checkpoint at the boundary behind segment sgm: T before the next segment (as pass C used it) and the
+            // colour accumulated in front of it.  Only read back for pixels that blended beyond the boundary.
+            float* c = ckpt + (slot0 + sgm) * CKPT_FLOATS;
+            Tprod *= c[tr];
+            c[tr] = Tprod; c[RB + tr] = acc[0]; c[2 * RB + tr] = acc[1]; c[3 * RB + tr] = acc[2]; c[4 * RB + tr] = acc[3];
         }
     }
     if (inside) {
@@ -235,7 +358,7 @@ __global__ void __launch_bounds__(RB) raster_fwd_kernel(
             for (int k = 0; k < 4; ++k)
                 if (k < CH) o[k] = acc[k];
         }
-        last_ids[pix] = cur_idx;
+        last_ids[pix] = last;
     }
 }
 
@@ -471,15 +594,16 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
 //   order[r]      : tile ids, bucketed by floor(log2(list length)), longest bucket first (coarse LPT; the order
 //                   within a bucket is arbitrary -- it only affects scheduling, never results)
 //   seg_prefix[r] : inclusive count of 1024-Gaussian segments of tiles order[0..r] (>= 1 per tile)
-//   ckpt_base[t]  : first checkpoint slot of TILE t (a tile with n segments owns n-1 slots)
+//   ckpt_base[t]  : first checkpoint / segment-output slot of TILE t (a tile with n > 1 segments owns n slots,
+//                   a single-segment tile none)
 __global__ void __launch_bounds__(1024) tile_order_kernel(const int32_t* __restrict__ tile_offsets, int64_t P,
                                                           int n_cam_tiles, int32_t* __restrict__ order,
                                                           int32_t* __restrict__ seg_prefix,
                                                           int32_t* __restrict__ ckpt_base) {
     __shared__ int s_cnt[33];
     __shared__ int s_base[33];
-    __shared__ int s_warp[32];
-    __shared__ int s_carry;
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry;
     if (threadIdx.x < 33) s_cnt[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
@@ -501,6 +625,7 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const int32_t* __restr
     }
     __syncthreads();  // order[] (global) is visible to the whole CTA
     if (seg_prefix == nullptr) return;
+    // scan of (segments, single-segment tiles) packed as (low, high) 32-bit halves of one 64-bit value
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int r0 = 0; r0 < n_cam_tiles; r0 += blockDim.x) {
         const int r = r0 + threadIdx.x;
@@ -511,29 +636,32 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const int32_t* __restr
             const int len = (int)(e - tile_offsets[t]);
             nseg = len > 0 ? (len + SEG - 1) / SEG : 1;
         }
-        int inc = nseg;
+        const long long mine = (long long)nseg | ((long long)(nseg == 1 ? 1 : 0) << 32);
+        long long inc = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, inc, o);
+            const long long n = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += n;
         }
         if (lane == 31) s_warp[warp] = inc;
         __syncthreads();
         if (warp == 0) {
-            int w = s_warp[lane];
+            long long w = s_warp[lane];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(0xffffffffu, w, o);
+                const long long n = __shfl_up_sync(0xffffffffu, w, o);
                 if (lane >= o) w += n;
             }
             s_warp[lane] = w;
         }
         __syncthreads();
-        const int carry = s_carry;
-        const int incl = carry + inc + (warp > 0 ? s_warp[warp - 1] : 0);
+        const long long carry = s_carry;
+        const long long incl = carry + inc + (warp > 0 ? s_warp[warp - 1] : 0ll);
         if (r < n_cam_tiles) {
-            seg_prefix[r] = incl;
-            ckpt_base[t] = (incl - nseg) - r;  // sum over earlier tiles of (nseg - 1)
+            const long long excl = incl - mine;
+            seg_prefix[r] = (int)(incl & 0xffffffffll);
+            // slots of the multi-segment tiles before this one (single-segment tiles own none)
+            ckpt_base[t] = (int)(excl & 0xffffffffll) - (int)(excl >> 32);
         }
         __syncthreads();
         if (threadIdx.x == blockDim.x - 1) s_carry = incl;
@@ -593,10 +721,14 @@ extern "C" int emd_raster_pack(const float* means2d, const float* conics, const 
 
 extern "C" int emd_raster_segment_size() { return SEG; }
 extern "C" int emd_raster_checkpoint_floats() { return CKPT_FLOATS; }
+extern "C" int emd_raster_segout_floats() { return SEGOUT_FLOATS; }
+// upper bound on the slots owned by multi-segment tiles: a tile of len > SEG has ceil(len/SEG) <= 2 len / SEG segments
+extern "C" int64_t emd_raster_segment_slots(int64_t P) { return 2 * (P / SEG) + 2; }
 
 // order / seg_prefix / ckpt_base: [C*tile_h*tile_w] int32 each (see tile_order_kernel).  The checkpoint buffer the
-// forward fills and the backward reads needs (P / emd_raster_segment_size() + 1) * emd_raster_checkpoint_floats()
-// floats; the backward launches at most P / segment_size + n_cam_tiles CTAs.
+// forward fills and the backward reads holds emd_raster_segment_slots(P) * emd_raster_checkpoint_floats() floats, the
+// forward's segment-output scratch emd_raster_segment_slots(P) * emd_raster_segout_floats(); forward and backward
+// launch at most P / segment_size + n_cam_tiles CTAs.
 extern "C" int emd_tile_order(const int32_t* tile_offsets, int64_t P, int64_t n_cam_tiles, int32_t* order,
                               int32_t* seg_prefix, int32_t* ckpt_base, cudaStream_t stream) {
     EMD_CHECK_ARG(n_cam_tiles >= 1 && n_cam_tiles < (1 << 30), "tile_order: bad tile count");
@@ -607,25 +739,37 @@ extern "C" int emd_tile_order(const int32_t* tile_offsets, int64_t P, int64_t n_
 }
 
 extern "C" int emd_rasterize_fwd(const float* recs, const int32_t* tile_offsets, const int32_t* flatten_ids,
-                                 const int32_t* tile_order, int64_t P, int64_t C, int width, int height, int tile_w, int tile_h, int channels,
-                                 int ed_mode, int flavour, const float* backgrounds, const int32_t* ckpt_base,
-                                 float* ckpt, float* out_colors, float* out_alphas, int32_t* last_ids,
-                                 cudaStream_t stream) {
+                                 const int32_t* tile_order, const int32_t* seg_prefix, const int32_t* ckpt_base,
+                                 int64_t P, int64_t C, int width, int height, int tile_w, int tile_h, int channels,
+                                 int ed_mode, int flavour, const float* backgrounds, float* ckpt, float* seg_out,
+                                 float* out_colors, float* out_alphas, int32_t* last_ids, cudaStream_t stream) {
     const RasterCfg cfg = flavour == 1 ? RasterCfg{0.0f, 0.99f, 1, 1} : RasterCfg{0.5f, 0.999f, 0, 0};
     EMD_CHECK_ARG(channels >= 1 && channels <= 4, "rasterize_fwd: channels must be 1..4");
-    EMD_CHECK_ARG(C >= 1 && C * tile_w * tile_h < ((int64_t)1 << 31), "rasterize_fwd: grid too large");
+    EMD_CHECK_ARG(C >= 1 && C * tile_w * tile_h < ((int64_t)1 << 30), "rasterize_fwd: grid too large");
     EMD_CHECK_ARG(tile_w == (width + EMD_TILE - 1) / EMD_TILE && tile_h == (height + EMD_TILE - 1) / EMD_TILE,
                   "rasterize_fwd: tile grid does not match image size (tile size is 16)");
-    EMD_CHECK_ARG((ckpt == nullptr) == (ckpt_base == nullptr), "rasterize_fwd: ckpt and ckpt_base go together");
-    EMD_CHECK_ARG(ckpt == nullptr || tile_order != nullptr, "rasterize_fwd: checkpoints need the tile order");
+    EMD_CHECK_ARG(tile_order && seg_prefix && ckpt_base && ckpt && seg_out,
+                  "rasterize_fwd: needs tile_order, seg_prefix, ckpt_base and the ckpt / seg_out buffers");
+    EMD_CHECK_ARG(P >= 0 && P < ((int64_t)1 << 31), "rasterize_fwd: too many intersections");
     if (!emd_aligned(recs, 16) || (channels == 4 && !emd_aligned(out_colors, 16))) {
         emd_set_error("rasterize_fwd: recs/out_colors must be 16-B aligned");
         return EMD_ERR_ALIGN;
     }
-    dim3 grid((unsigned)(C * tile_w * tile_h)), block(RB, 1, 1);
-    EMD_LAUNCH(EK_RASTER_FWD, stream, raster_fwd_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, tile_order, P,
-                                                  (int)C, width, height, tile_w, tile_h, channels, ed_mode, cfg,
-                                                  backgrounds, ckpt_base, ckpt, out_colors, out_alphas, last_ids));
+    const int n_ct = (int)(C * tile_w * tile_h);
+    // upper bound on the number of (tile, segment) CTAs; surplus CTAs exit at once
+    dim3 grid((unsigned)(P / SEG + n_ct)), block(RB, 1, 1);
+    const float4* r4 = reinterpret_cast<const float4*>(recs);
+    if (P > SEG)  // only then can a tile have more than one segment
+        EMD_LAUNCH(EK_RASTER_FWD, stream, raster_fwd_seg_kernel<false><<<grid, block, 0, stream>>>(
+            r4, tile_offsets, flatten_ids, tile_order, seg_prefix, ckpt_base, P, (int)C, width, height, tile_w, tile_h,
+            channels, ed_mode, cfg, backgrounds, ckpt, seg_out, out_colors, out_alphas, last_ids));
+    EMD_LAUNCH(EK_RASTER_FWD, stream, raster_fwd_seg_kernel<true><<<grid, block, 0, stream>>>(
+        r4, tile_offsets, flatten_ids, tile_order, seg_prefix, ckpt_base, P, (int)C, width, height, tile_w, tile_h,
+        channels, ed_mode, cfg, backgrounds, ckpt, seg_out, out_colors, out_alphas, last_ids));
+    if (P > SEG)
+        EMD_LAUNCH(EK_RASTER_FWD, stream, raster_fwd_combine_kernel<<<n_ct, block, 0, stream>>>(
+            tile_order, seg_prefix, ckpt_base, (int)C, width, height, tile_w, tile_h, channels, ed_mode, cfg, backgrounds,
+            ckpt, seg_out, out_colors, out_alphas, last_ids));
     EMD_CHECK_LAUNCH("rasterize_fwd");
     return EMD_OK;
 }

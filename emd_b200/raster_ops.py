@@ -217,16 +217,18 @@ class _Rasterize(torch.autograd.Function):
         tile_order, seg_prefix, ckpt_base = sched[0], sched[1], sched[2]
         _C.check(L.emd_tile_order(_C.ptr(isect_offsets, torch.int32), P, n_ct, _C.ptr(tile_order), _C.ptr(seg_prefix),
                                   _C.ptr(ckpt_base), _C.stream()), "emd_tile_order")
-        need_ckpt = any(ctx.needs_input_grad[:5])
-        ckpt = (torch.empty((P // L.emd_raster_segment_size() + 1) * L.emd_raster_checkpoint_floats(),
-                            dtype=torch.float32, device=dev) if need_ckpt else None)
+        # checkpoints (kept for the backward) + per-segment scratch of the segment-parallel forward
+        slots = int(L.emd_raster_segment_slots(P))
+        ckpt = torch.empty(slots * L.emd_raster_checkpoint_floats(), dtype=torch.float32, device=dev)
+        seg_out = torch.empty(slots * L.emd_raster_segout_floats(), dtype=torch.float32, device=dev)
         _C.check(L.emd_rasterize_fwd(_C.ptr(recs), _C.ptr(isect_offsets, torch.int32), _C.ptr(flatten_ids, torch.int32),
-                                     _C.ptr(tile_order), P, C, width, height, tw, th, CH, 1 if ed_mode else 0, int(flavour), _C.ptr(bg),
-                                     _C.ptr(ckpt_base) if need_ckpt else None, _C.ptr(ckpt),
+                                     _C.ptr(tile_order), _C.ptr(seg_prefix), _C.ptr(ckpt_base), P, C, width, height, tw, th,
+                                     CH, 1 if ed_mode else 0, int(flavour), _C.ptr(bg), _C.ptr(ckpt), _C.ptr(seg_out),
                                      _C.ptr(out_colors), _C.ptr(out_alphas), _C.ptr(last_ids), _C.stream()),
                  "emd_rasterize_fwd")
+        del seg_out
         ctx.save_for_backward(recs, isect_offsets, flatten_ids, radii, cum_tiles, bg if bg is not None else torch.empty(0, device=dev),
-                              out_colors, out_alphas, last_ids, sched, ckpt if ckpt is not None else torch.empty(0, device=dev))
+                              out_colors, out_alphas, last_ids, sched, ckpt)
         ctx.cfg = (width, height, CH, d_color, bool(with_depth), bool(ed_mode), bool(absgrad), colors_per_cam,
                    opac_per_cam, bg is not None, int(flavour))
         ctx.means2d_ref = means2d if absgrad else None

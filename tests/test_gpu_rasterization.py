@@ -73,6 +73,9 @@ def _check_images(rc, ra, meta, gc, ga, tol=1e-4, max_unstable_frac=2e-3):
     (1, 2000, 200, 136, (0.0, 20.0), "RGB", True),      # ragged tiles (136 = 8.5 tiles), 2 cameras, background
     (2, 1500, 160, 96, (0.0,), "RGB+D", False),
     (3, 800, 96, 64, (0.0, -30.0, 30.0), "ED", False),
+    # several 1024-Gaussian segments per tile: transmittance pass + per-segment compositing + combine
+    (4, 12000, 64, 48, (0.0,), "RGB+ED", False),
+    (7, 9000, 64, 40, (0.0, 15.0), "RGB", True),
 ])
 def test_forward_parity(seed, n, W, H, yaws, mode, bg):
     _, _, _, (rc, ra, meta), (gc, ga, gmeta), _, _ = _run_both(seed, n, W, H, yaws, mode, bg, grads=False)

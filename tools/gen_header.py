@@ -21,7 +21,8 @@ GROUPS = [
     ("K3   tile intersection", ["emd_scan_workspace_bytes", "emd_cumsum_i32_i64", "emd_exclusive_scan_u32",
                                 "emd_isect_emit", "emd_dg_isect_emit"]),
     ("K4   radix sort", ["emd_radix_sort_workspace_bytes", "emd_radix_sort_pairs"]),
-    ("K5   tile ranges", ["emd_isect_offsets", "emd_tile_order", "emd_raster_segment_size", "emd_raster_checkpoint_floats"]),
+    ("K5   tile ranges", ["emd_isect_offsets", "emd_tile_order", "emd_raster_segment_size", "emd_raster_checkpoint_floats",
+                        "emd_raster_segout_floats", "emd_raster_segment_slots"]),
     ("K6/K7 rasterization", ["emd_raster_pack", "emd_rasterize_fwd", "emd_rasterize_bwd_workspace_bytes",
                              "emd_rasterize_bwd"]),
 ]
@@ -86,13 +87,18 @@ DOC = {
                             "*result_buffer = 0/1 tells which buffer holds the result.",
     "emd_isect_offsets": "gsplat isect_offset_encode / diff_gauss identifyTileRanges: first sorted index of every (camera, tile).",
     "emd_tile_order": "Tile ids ordered longest-list-first (scheduling only; results do not depend on it) plus the segment "
-                      "bookkeeping of the segment-parallel backward: seg_prefix (inclusive #segments along that order) and "
-                      "ckpt_base (first checkpoint slot per tile).",
+                      "bookkeeping of the segment-parallel forward / backward: seg_prefix (inclusive #segments along that order) "
+                      "and ckpt_base (first checkpoint slot per multi-segment tile).",
     "emd_raster_segment_size": "Gaussians per segment of a tile's sorted list (the backward runs one CTA per segment).",
     "emd_raster_checkpoint_floats": "Floats per forward checkpoint (T and 4 accumulators of a tile's 256 pixels).",
+    "emd_raster_segout_floats": "Floats per segment-output record of the segment-parallel forward (scratch).",
+    "emd_raster_segment_slots": "Upper bound on the checkpoint / segment-output slots needed for P intersections.",
     "emd_raster_pack": "Packs per-(camera,Gaussian) mean2d/conic/opacity/colour(+depth) into three float4 records for the compositor.",
     "emd_rasterize_fwd": "gsplat rasterize_to_pixels forward (RGB / +depth / expected depth, alpha, last_ids) "
-                         "(reference call OmniRe/models/trainers/base.py:393-408).",
+                         "(reference call OmniRe/models/trainers/base.py:393-408).  Tiles longer than one segment are "
+                         "composited one CTA per segment (transmittance pass, compositing pass, combine); ckpt "
+                         "[emd_raster_segment_slots(P) x emd_raster_checkpoint_floats()] is kept for the backward, seg_out "
+                         "[slots x emd_raster_segout_floats()] is scratch.",
     "emd_rasterize_bwd_workspace_bytes": "Workspace bytes of emd_rasterize_bwd for P intersections.",
     "emd_rasterize_bwd": "gsplat rasterize_to_pixels backward: v_means2d (+abs), v_conics, v_colors, v_depths, v_opacities; "
                          "deterministic (no float atomics).",
