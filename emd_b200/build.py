@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "--fmad=true",  # contraction allowed everywhere EXCEPT the c_* intrinsics (which ptxas never fuses)
     "-Xcompiler", "-fPIC", "-shared",
     "-Xptxas", "-v",
-]
+] + [f"-D{k}={os.environ[k]}" for k in ("EMD_SEG_BATCHES",) if os.environ.get(k)]  # tuning experiments only
 
 
 def _nvcc() -> str:

@@ -103,10 +103,13 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(
 
 // ---- onesweep ------------------------------------------------------------------------------------
 constexpr int OS_MAX_PASSES = 8;
+constexpr int OS_ITEMS = 8;                      // keys per thread: 2048-key tiles, <= 64 registers -> 4 CTAs per SM
+constexpr int OS_TILE = RS_THREADS * OS_ITEMS;
+constexpr int OS_WARP_KEYS = 32 * OS_ITEMS;
 constexpr uint32_t OS_FLAG_AGG = 1u << 30, OS_FLAG_PREFIX = 2u << 30, OS_VAL_MASK = (1u << 30) - 1u;
 struct OsSmem {
-    uint64_t keys[RS_TILE];
-    uint32_t vals[RS_TILE];
+    uint64_t keys[OS_TILE];
+    uint32_t vals[OS_TILE];
     uint32_t whist[RS_WARPS][RS_BINS];
     uint32_t lstart[RS_BINS];   // first position of digit d inside the sorted tile
     uint32_t gbase[RS_BINS];    // global position of sorted-tile slot i with digit d = gbase[d] + i  (wraps mod 2^32)
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(RS_BINS) rs_digit_prefix_kernel(uint32_t* __re
     h[threadIdx.x] = base + inc - v;
 }
 
-__global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(
+__global__ void __launch_bounds__(RS_THREADS, 4) rs_onesweep_kernel(
     const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, int64_t n, int shift, uint32_t mask, const uint32_t* __restrict__ digit_base,
     uint32_t* __restrict__ state /*[nblocks][256], zeroed*/, uint32_t* __restrict__ ticket) {
@@ -165,19 +168,19 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(
     for (int w = 0; w < RS_WARPS; ++w) sm.whist[w][tid] = 0;
     __syncthreads();
     const uint32_t b = sm.bid;
-    const int64_t tile_base = (int64_t)b * RS_TILE;
-    const int64_t wbase = tile_base + (int64_t)warp * RS_WARP_KEYS;
-    uint64_t key[RS_ITEMS];
-    uint32_t val[RS_ITEMS];
-    uint32_t rank[RS_ITEMS];
+    const int64_t tile_base = (int64_t)b * OS_TILE;
+    const int64_t wbase = tile_base + (int64_t)warp * OS_WARP_KEYS;
+    uint64_t key[OS_ITEMS];
+    uint32_t val[OS_ITEMS];
+    uint32_t rank[OS_ITEMS];
 #pragma unroll
-    for (int r = 0; r < RS_ITEMS; ++r) {
+    for (int r = 0; r < OS_ITEMS; ++r) {
         const int64_t i = wbase + r * 32 + lane;
         key[r] = i < n ? __ldg(keys_in + i) : ~0ull;
         val[r] = i < n ? __ldg(vals_in + i) : 0u;
     }
 #pragma unroll
-    for (int r = 0; r < RS_ITEMS; ++r) {
+    for (int r = 0; r < OS_ITEMS; ++r) {
         const int64_t i = wbase + r * 32 + lane;
         const bool ok = i < n;
         const uint32_t d = ok ? ((uint32_t)(key[r] >> shift) & mask) : 0xFFFFu;
@@ -214,37 +217,12 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(
     __syncthreads();
     uint32_t lstart = inc - cnt;
     for (int w = 0; w < warp; ++w) lstart += sm.wsum[w];
-    // decoupled look-back: sum the counts of the tiles before this one for digit `tid`
-    uint32_t excl = 0;
-    if (b > 0) {
-        // windows of 8 predecessors: the 8 loads are independent, so a long walk over tiles that have only
-        // published their aggregate costs one L2 round trip per window instead of one per tile
-        int64_t p = (int64_t)b - 1;
-        bool found = false;
-        while (!found) {
-            uint32_t v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                v[k] = p - k >= 0 ? __ldcg(state + (p - k) * RS_BINS + tid) : OS_FLAG_PREFIX;   // in front of tile 0: prefix 0
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (found) continue;
-                while ((v[k] & ~OS_VAL_MASK) == 0) {
-                    __nanosleep(20);
-                    v[k] = __ldcg(state + (p - k) * RS_BINS + tid);
-                }
-                excl += v[k] & OS_VAL_MASK;
-                if ((v[k] & ~OS_VAL_MASK) == OS_FLAG_PREFIX) found = true;
-            }
-            p -= 8;
-        }
-        __stcg(my_state, OS_FLAG_PREFIX | (excl + cnt));
-    }
     sm.lstart[tid] = lstart;
-    sm.gbase[tid] = digit_base[tid] + excl - lstart;
     __syncthreads();
+    // reorder the tile by digit in shared memory first (needs tile-local offsets only): the keys leave the
+    // registers, which the look-back below then uses for a wide window of independent loads
 #pragma unroll
-    for (int r = 0; r < RS_ITEMS; ++r) {
+    for (int r = 0; r < OS_ITEMS; ++r) {
         const int64_t i = wbase + r * 32 + lane;
         if (i < n) {
             const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
@@ -253,10 +231,38 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(
             sm.vals[pos] = val[r];
         }
     }
-    __syncthreads();
-    const int tile_n = (int)min((int64_t)RS_TILE, n - tile_base);
+    // decoupled look-back: sum the counts of the tiles before this one for digit `tid`.  Windows of 32
+    // predecessors: the loads are independent, so a long walk over tiles that have only published their
+    // aggregate (the whole first wave of CTAs) costs one L2 round trip per 32 tiles instead of one per tile.
+    uint32_t excl = 0;
+    if (b > 0) {
+        constexpr int WIN = 32;
+        int64_t p = (int64_t)b - 1;
+        bool found = false;
+        while (!found) {
+            uint32_t v[WIN];
 #pragma unroll
-    for (int k = 0; k < RS_ITEMS; ++k) {
+            for (int k = 0; k < WIN; ++k)
+                v[k] = p - k >= 0 ? __ldcg(state + (p - k) * RS_BINS + tid) : OS_FLAG_PREFIX;   // in front of tile 0: prefix 0
+#pragma unroll
+            for (int k = 0; k < WIN; ++k) {
+                if (found) continue;
+                while ((v[k] & ~OS_VAL_MASK) == 0) {
+                    __nanosleep(20);
+                    v[k] = __ldcg(state + (p - k) * RS_BINS + tid);
+                }
+                excl += v[k] & OS_VAL_MASK;
+                if ((v[k] & ~OS_VAL_MASK) == OS_FLAG_PREFIX) found = true;
+            }
+            p -= WIN;
+        }
+        __stcg(my_state, OS_FLAG_PREFIX | (excl + cnt));
+    }
+    sm.gbase[tid] = digit_base[tid] + excl - lstart;
+    __syncthreads();
+    const int tile_n = (int)min((int64_t)OS_TILE, n - tile_base);
+#pragma unroll
+    for (int k = 0; k < OS_ITEMS; ++k) {
         const int i = k * RS_THREADS + tid;
         if (i < tile_n) {
             const uint64_t kk = sm.keys[i];
@@ -270,7 +276,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(
 }  // namespace
 
 static size_t os_workspace_bytes(int64_t n) {
-    const int64_t nb = emd_cdiv(n > 0 ? n : 1, RS_TILE);
+    const int64_t nb = emd_cdiv(n > 0 ? n : 1, OS_TILE);
     // [ghist 8*256][tickets 8][pad to 256 B][state passes*nb*256]
     return 256 * ((OS_MAX_PASSES * RS_BINS + OS_MAX_PASSES) * sizeof(uint32_t) / 256 + 1) +
            (size_t)OS_MAX_PASSES * nb * RS_BINS * sizeof(uint32_t);
@@ -304,6 +310,7 @@ extern "C" int emd_radix_sort_pairs(uint64_t* keys0, uint32_t* vals0, uint64_t* 
     int cur = 0;
     const int npasses = (end_bit - begin_bit + 7) / 8;
     if (n < ((int64_t)1 << 30) && npasses <= OS_MAX_PASSES) {
+        const int64_t nb = emd_cdiv(n, OS_TILE);   // shadows the legacy tile count
         uint32_t* ghist = reinterpret_cast<uint32_t*>(workspace);
         uint32_t* tickets = ghist + OS_MAX_PASSES * RS_BINS;
         const size_t head = 256 * ((OS_MAX_PASSES * RS_BINS + OS_MAX_PASSES) * sizeof(uint32_t) / 256 + 1);

@@ -32,7 +32,11 @@ namespace {
 constexpr int RB = 256;  // threads per CTA == pixels per tile == Gaussians per staged batch
 constexpr float ALPHA_MIN = 1.0f / 255.0f;
 constexpr int NPART = 12;  // floats per (tile, Gaussian) gradient slot
-constexpr int SEG_BATCHES = 4;            // a segment = 4 staged batches = 1024 Gaussians of a tile's list
+constexpr int BSUB = 64;   // staged Gaussians per cross-warp reduction step of the backward
+#ifndef EMD_SEG_BATCHES
+#define EMD_SEG_BATCHES 4
+#endif
+constexpr int SEG_BATCHES = EMD_SEG_BATCHES;  // a segment = this many staged batches of 256 Gaussians of a tile's list
 constexpr int SEG = SEG_BATCHES * RB;
 constexpr int CKPT_FLOATS = 5 * RB;       // per segment boundary: T and acc[4] of the 256 pixels
 constexpr int SEGOUT_FLOATS = 6 * RB;     // per segment of a multi-segment tile: T_end, local acc[4], last/stop code
@@ -147,17 +151,18 @@ __device__ __forceinline__ bool decode_segment(const int32_t* __restrict__ seg_p
 }
 
 template <bool COMPOSITE>
-__global__ void __launch_bounds__(RB) raster_fwd_seg_kernel(
+__global__ void __launch_bounds__(RB, 4) raster_fwd_seg_kernel(
     const float4* __restrict__ recs, const int32_t* __restrict__ tile_offsets, const int32_t* __restrict__ flatten_ids,
     const int32_t* __restrict__ tile_order, const int32_t* __restrict__ seg_prefix, const int32_t* __restrict__ ckpt_base,
     int64_t P, int C, int width, int height, int tile_w, int tile_h, int CH,
     int ed_mode, RasterCfg cfg, const float* __restrict__ backgrounds,
     float* __restrict__ ckpt, float* __restrict__ seg_out, float* __restrict__ out_colors, float* __restrict__ out_alphas,
     int32_t* __restrict__ last_ids) {
-    __shared__ float4 s_r0[RB];
-    __shared__ float4 s_r1[RB];
-    __shared__ float2 s_r2[RB];
+    __shared__ float4 s_g0[RB];    // mean x, mean y, opacity, A       (exp(-sigma) = exp2(A dx^2 + B dx dy + Cc dy^2))
+    __shared__ float2 s_g1[RB];    // B, Cc
+    __shared__ float4 s_col[RB];   // the four composited channels
     __shared__ uint32_t s_mask[RB];
+    __shared__ __align__(4) uint8_t s_list[RB / 32][RB];   // per warp: staged slots whose alpha box reaches its block
 
     FwdTile ft;
     if (!decode_segment(seg_prefix, tile_order, C * tile_w * tile_h, tile_w, tile_h, ft)) return;
@@ -199,57 +204,60 @@ __global__ void __launch_bounds__(RB) raster_fwd_seg_kernel(
             const int64_t g = flatten_ids[idx];
             const float4 r0 = __ldg(recs + g * 3 + 0);
             const float4 r2 = __ldg(recs + g * 3 + 2);
-            s_r0[tr] = r0;
-            s_r1[tr] = __ldg(recs + g * 3 + 1);
-            if (COMPOSITE) s_r2[tr] = make_float2(r2.x, r2.y);
+            const float4 r1 = __ldg(recs + g * 3 + 1);
+            // conic pre-scaled so that exp(-sigma) = exp2(A dx^2 + B dx dy + Cc dy^2)
+            constexpr float L2E = 1.4426950408889634f;
+            s_g0[tr] = make_float4(r0.x, r0.y, r0.z, -0.5f * L2E * r0.w);
+            s_g1[tr] = make_float2(-L2E * r1.x, -0.5f * L2E * r1.y);
+            if (COMPOSITE) s_col[tr] = make_float4(r1.z, r1.w, r2.x, r2.y);
             mask = block_mask(r0.x, r0.y, r2.z, r2.w, cx0, cy0);
         }
         s_mask[tr] = mask;
         __syncthreads();
         if (__all_sync(0xffffffffu, done)) continue;  // every pixel of this warp's block has saturated
-        // This warp's list: the staged Gaussians whose alpha box reaches its 8x4 block, 32 candidates per ballot.
-        // Groups of 4: the alphas (sigma, exp) do not depend on the running transmittance, so four are
-        // evaluated with full ILP before the short sequential T / accumulate chain.
+        // This warp's candidate list: the staged Gaussians whose alpha box reaches its 8x4 block, compacted in order.
+        int cnt = 0;
+#pragma unroll
         for (int chunk = 0; chunk < RB / 32; ++chunk) {
-            uint32_t word = __ballot_sync(0xffffffffu, (s_mask[chunk * 32 + lane] >> warp) & 1u);
-            while (word) {
-                int tt[4];
-                float alpha[4];
-                bool ok[4];
+            const bool c = (s_mask[chunk * 32 + lane] >> warp) & 1u;
+            const uint32_t word = __ballot_sync(0xffffffffu, c);
+            if (c) s_list[warp][cnt + __popc(word & ((1u << lane) - 1u))] = (uint8_t)(chunk * 32 + lane);
+            cnt += __popc(word);
+        }
+        __syncwarp();
+        // Groups of 4: the alphas do not depend on the running transmittance, so four are evaluated with full
+        // ILP before the short sequential T / accumulate chain.  (Slots past cnt hold stale in-range indices.)
+        for (int q = 0; q < cnt; q += 4) {
+            const uchar4 t4 = *reinterpret_cast<const uchar4*>(&s_list[warp][q]);
+            const int tt[4] = {t4.x, t4.y, t4.z, t4.w};
+            float alpha[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 g0 = s_g0[tt[u]];
+                const float2 g1 = s_g1[tt[u]];
+                const float dx = g0.x - px, dy = g0.y - py;
+                const float pw = fmaf(g1.y * dy, dy, fmaf(g1.x, dy, g0.w * dx) * dx);   // -sigma * log2(e)
+                alpha[u] = fminf(cfg.alpha_max, g0.z * ex2_approx(pw));
+                ok[u] = (q + u < cnt) && !(pw > 0.f || alpha[u] < ALPHA_MIN);
+            }
+            if (COMPOSITE) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    tt[u] = word ? chunk * 32 + __ffs(word) - 1 : -1;
-                    word &= word - 1;   // 0 & 0xffffffff stays 0
+                    if (!ok[u] || done) continue;
+                    const float next_T = T * (1.0f - alpha[u]);
+                    if (cfg.strict_stop ? (next_T < 1e-4f) : (next_T <= 1e-4f)) { done = true; stopped = true; continue; }
+                    const float vis = alpha[u] * T;
+                    const float4 col = s_col[tt[u]];
+                    acc[0] += col.x * vis; acc[1] += col.y * vis; acc[2] += col.z * vis; acc[3] += col.w * vis;
+                    cur_idx = batch_start + tt[u];
+                    T = next_T;
                 }
+                if (__all_sync(0xffffffffu, done)) break;
+            } else {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int t = max(tt[u], 0);
-                    const float4 r0 = s_r0[t];
-                    const float4 r1 = s_r1[t];
-                    const float dx = r0.x - px, dy = r0.y - py;
-                    const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
-                    alpha[u] = fminf(cfg.alpha_max, r0.z * exp_neg(sigma));
-                    ok[u] = (tt[u] >= 0) && !(sigma < 0.f || alpha[u] < ALPHA_MIN);
-                }
-                if (COMPOSITE) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (!ok[u] || done) continue;
-                        const float next_T = T * (1.0f - alpha[u]);
-                        if (cfg.strict_stop ? (next_T < 1e-4f) : (next_T <= 1e-4f)) { done = true; stopped = true; continue; }
-                        const float vis = alpha[u] * T;
-                        const float4 r1 = s_r1[tt[u]];
-                        const float2 r2 = s_r2[tt[u]];
-                        acc[0] += r1.z * vis; acc[1] += r1.w * vis; acc[2] += r2.x * vis; acc[3] += r2.y * vis;
-                        cur_idx = batch_start + tt[u];
-                        T = next_T;
-                    }
-                    if (__all_sync(0xffffffffu, done)) { word = 0; chunk = RB / 32; }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (ok[u]) T *= 1.0f - alpha[u];
-                }
+                for (int u = 0; u < 4; ++u)
+                    if (ok[u]) T *= 1.0f - alpha[u];
             }
         }
     }
@@ -365,21 +373,41 @@ __global__ void __launch_bounds__(RB) raster_fwd_combine_kernel(
 // ---------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------
-// Butterfly all-lanes reduction of 16 values: after the call, lane l holds the
-// warp-wide sum of value index ((l>>1)&15 with bits reversed as below) in v[0]:
-//   idx(l) = ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1)
-__device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
+// Reduce-scatter of 12 per-lane values across the warp in 13 shuffles (6 + 3 + 2 + 1 + 1): every step halves the
+// values a lane is responsible for.  On return the lanes with (lane & 1) == 0 and not ((lane & 4) && (lane & 2))
+// hold, in the return value, the warp-wide sum of component
+//   6 * bit4 + 3 * bit3 + (bit2 ? 2 : bit1)          (bitN = (lane >> N) & 1)
+// Fixed association order -> bit-reproducible.
+__device__ __forceinline__ float butterfly12(float (&v)[12], int lane) {
+    {
+        const bool up = (lane & 16) != 0;
 #pragma unroll
-    for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
-        const bool up = (lane & off) != 0;
-#pragma unroll
-        for (int k = 0; k < half; ++k) {
-            const float send = up ? v[k] : v[k + half];
-            const float keep = up ? v[k + half] : v[k];
-            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        for (int k = 0; k < 6; ++k) {
+            const float send = up ? v[k] : v[k + 6];
+            const float keep = up ? v[k + 6] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
         }
     }
-    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+    {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float send = up ? v[k] : v[k + 3];
+            const float keep = up ? v[k + 3] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    const bool up4 = (lane & 4) != 0, up2 = (lane & 2) != 0;
+    // 3 -> (2 | 1): lanes with bit2 clear take components 0 and 1, lanes with bit2 set take component 2
+    const float r0 = __shfl_xor_sync(0xffffffffu, up4 ? v[0] : v[2], 4);
+    const float r1 = __shfl_xor_sync(0xffffffffu, v[1], 4);
+    const float a0 = (up4 ? v[2] : v[0]) + r0;
+    const float a1 = v[1] + r1;   // meaningful on the bit2-clear lanes only
+    // (2 | 1) -> 1
+    const float send = up4 ? a0 : (up2 ? a0 : a1);
+    const float keep = up4 ? a0 : (up2 ? a1 : a0);
+    const float c = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    return c + __shfl_xor_sync(0xffffffffu, c, 1);
 }
 
 __global__ void __launch_bounds__(RB) raster_bwd_kernel(
@@ -396,8 +424,8 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
     __shared__ float2 s_r2[RB];
     __shared__ uint32_t s_slot[RB];
     __shared__ uint32_t s_mask[RB];
-    __shared__ float s_slab[RB / 32][32][NPART];
-    __shared__ uint32_t s_tmask[RB / 32];
+    __shared__ float s_slab[RB / 32][BSUB][NPART];
+    __shared__ uint32_t s_tmask[RB / 32][BSUB / 32];
     __shared__ int s_red[RB / 32];
 
     // CTA -> (tile, segment): segments of all tiles are laid out heavy-tile-first; seg_prefix[r] is the inclusive
@@ -509,66 +537,76 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
         }
         s_mask[tr] = mask;
         __syncthreads();
-        for (int sub = 0; sub < batch_size; sub += 32) {
-            const int sub_n = min(32, batch_size - sub);
-            // this warp's candidates of the 32 staged Gaussians: alpha box reaches its 8x4 block, and the
-            // Gaussian is not behind everything the block's pixels blended
-            const int64_t idx_l = batch_hi - 1 - (sub + lane);
-            uint32_t word = __ballot_sync(0xffffffffu, ((s_mask[sub + lane] >> warp) & 1u) && idx_l <= (int64_t)wmax);
-            uint32_t tmask = 0;
-            while (word) {
-                const int u = __ffs(word) - 1;
-                word &= word - 1;
-                const int t = sub + u;
-                const int64_t idx = batch_hi - 1 - t;
-                bool valid = inside && idx <= bin_final;
-                const float4 r0 = s_r0[t];
-                const float4 r1 = s_r1[t];
-                const float dx = r0.x - px, dy = r0.y - py;
-                const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
-                const float vis = exp_neg(sigma);
-                const float alpha = fminf(cfg.alpha_max, r0.z * vis);
-                if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
-                if (!__any_sync(0xffffffffu, valid)) continue;
-                float v[16];
+        for (int sub = 0; sub < batch_size; sub += BSUB) {
+            const int sub_n = min(BSUB, batch_size - sub);
+            uint32_t tmask[BSUB / 32];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) v[k] = 0.f;
-                if (valid) {
-                    const float2 r2 = s_r2[t];
-                    const float col[4] = {r1.z, r1.w, r2.x, r2.y};
-                    const float ra = 1.0f / (1.0f - alpha);
-                    T *= ra;
-                    const float fac = alpha * T;
-                    float v_alpha = 0.f;
+            for (int h = 0; h < BSUB / 32; ++h) {
+                tmask[h] = 0;
+                if (sub + 32 * h >= batch_size) continue;   // block-uniform
+                // this warp's candidates of 32 staged Gaussians: alpha box reaches its 8x4 block, and the
+                // Gaussian is not behind everything the block's pixels blended
+                const int64_t idx_l = batch_hi - 1 - (sub + 32 * h + lane);
+                uint32_t word = __ballot_sync(0xffffffffu, ((s_mask[sub + 32 * h + lane] >> warp) & 1u) && idx_l <= (int64_t)wmax);
+                while (word) {
+                    const int u = __ffs(word) - 1;
+                    word &= word - 1;
+                    const int t = sub + 32 * h + u;
+                    const int64_t idx = batch_hi - 1 - t;
+                    bool valid = inside && idx <= bin_final;
+                    const float4 r0 = s_r0[t];
+                    const float4 r1 = s_r1[t];
+                    const float dx = r0.x - px, dy = r0.y - py;
+                    const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
+                    const float vis = exp_neg(sigma);
+                    const float alpha = fminf(cfg.alpha_max, r0.z * vis);
+                    if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
+                    if (!__any_sync(0xffffffffu, valid)) continue;
+                    float v[12];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        v[k] = fac * v_c[k];
-                        v_alpha += (col[k] * T - buf[k] * ra) * v_c[k];
+                    for (int k = 0; k < 12; ++k) v[k] = 0.f;
+                    if (valid) {
+                        const float2 r2 = s_r2[t];
+                        const float col[4] = {r1.z, r1.w, r2.x, r2.y};
+                        const float ra = __fdividef(1.0f, 1.0f - alpha);   // 1 - alpha in [1e-3, 1]: the fast reciprocal is safe
+                        T *= ra;
+                        const float fac = alpha * T;
+                        float v_alpha = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            v[k] = fac * v_c[k];
+                            v_alpha += (col[k] * T - buf[k] * ra) * v_c[k];
+                        }
+                        v_alpha += ra * v_a_eff;
+                        const float opac = r0.z;
+                        if (opac * vis <= cfg.alpha_max) {
+                            const float v_sigma = -opac * vis * v_alpha;
+                            v[4] = 0.5f * v_sigma * dx * dx;
+                            v[5] = v_sigma * dx * dy;
+                            v[6] = 0.5f * v_sigma * dy * dy;
+                            const float gx = v_sigma * (r0.w * dx + r1.x * dy);
+                            const float gy = v_sigma * (r1.x * dx + r1.y * dy);
+                            v[7] = gx; v[8] = gy;
+                            v[9] = fabsf(gx); v[10] = fabsf(gy);
+                            v[11] = vis * v_alpha;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) buf[k] += col[k] * fac;
                     }
-                    v_alpha += ra * v_a_eff;
-                    const float opac = r0.z;
-                    if (opac * vis <= cfg.alpha_max) {
-                        const float v_sigma = -opac * vis * v_alpha;
-                        v[4] = 0.5f * v_sigma * dx * dx;
-                        v[5] = v_sigma * dx * dy;
-                        v[6] = 0.5f * v_sigma * dy * dy;
-                        const float gx = v_sigma * (r0.w * dx + r1.x * dy);
-                        const float gy = v_sigma * (r1.x * dx + r1.y * dy);
-                        v[7] = gx; v[8] = gy;
-                        v[9] = fabsf(gx); v[10] = fabsf(gy);
-                        v[11] = vis * v_alpha;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) buf[k] += col[k] * fac;
+                    const float tot = butterfly12(v, lane);
+                    const int vidx = 6 * ((lane >> 4) & 1) + 3 * ((lane >> 3) & 1) + ((lane & 4) ? 2 : ((lane >> 1) & 1));
+                    if ((lane & 1) == 0 && !((lane & 4) && (lane & 2))) s_slab[warp][32 * h + u][vidx] = tot;
+                    tmask[h] |= 1u << u;
                 }
-                const float tot = butterfly16(v, lane);
-                const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                if ((lane & 1) == 0 && vidx < NPART) s_slab[warp][u][vidx] = tot;
-                tmask |= 1u << u;
             }
-            if (lane == 0) s_tmask[warp] = tmask;
-            // barrier + block-wide "did any warp produce a partial for these 32 Gaussians"
-            if (__syncthreads_or(tmask != 0)) {
+            bool any_t = false;
+#pragma unroll
+            for (int h = 0; h < BSUB / 32; ++h) {
+                if (lane == 0) s_tmask[warp][h] = tmask[h];
+                any_t |= tmask[h] != 0;
+            }
+            // barrier + block-wide "did any warp produce a partial for these Gaussians"
+            if (__syncthreads_or(any_t)) {
                 // fixed-order cross-warp sum, one writer per (Gaussian, component)
                 for (int q = tr; q < sub_n * NPART; q += RB) {
                     const int u = q / NPART, k = q - u * NPART;
@@ -576,7 +614,7 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
                     bool any = false;
 #pragma unroll
                     for (int w = 0; w < RB / 32; ++w) {
-                        if (s_tmask[w] & (1u << u)) { sum += s_slab[w][u][k]; any = true; }
+                        if (s_tmask[w][u >> 5] & (1u << (u & 31))) { sum += s_slab[w][u][k]; any = true; }
                     }
                     if (any) {
                         const uint32_t slot = s_slot[sub + u];

@@ -13,7 +13,12 @@ def main(path, top=25):
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hdr_i]
     iS, iN, iI = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
-    body = [r for r in rows[hdr_i + 1:] if len(r) > iI]
+    body = []
+    for r in rows[hdr_i + 1:]:   # first kernel instance only (the export repeats the header per launch)
+        if r and r[0] in ("Kernel Name", "Address"):
+            break
+        if len(r) > iI:
+            body.append(r)
     tot_i = sum(int(r[iI]) for r in body)
     tot_s = sum(int(r[iN]) for r in body)
     by_op = defaultdict(lambda: [0, 0])
