@@ -41,6 +41,7 @@ _SIGS = {
     "emd_raster_pack": (c_int, [P, P, P, c_int, P, c_int, c_int, P, c_int, P, c_int64, c_int64, P, P]),
     "emd_linear_bwd_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "emd_linear_fwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P]),
+    "emd_linear_fwd_tc": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P]),
     "emd_linear_bwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),
     "emd_temb_fwd": (c_int, [P, c_int, c_int, P, c_int, P, P]),
     "emd_temb_bwd": (c_int, [P, c_int, c_int, P, c_int, P, P, P, P]),

@@ -16,7 +16,7 @@ GROUPS = [
                                                          "emd_smpl_reduce_width", "emd_smpl_deform_fwd",
                                                          "emd_smpl_deform_bwd"]),
     ("K1b  spherical harmonics + node activations", ["emd_sh_fwd", "emd_sh_bwd", "emd_activate_fwd", "emd_activate_bwd"]),
-    ("K1d  S3Gaussian EMD deformation MLP", ["emd_linear_bwd_workspace_bytes", "emd_linear_fwd", "emd_linear_bwd", "emd_temb_fwd", "emd_temb_bwd"]),
+    ("K1d  S3Gaussian EMD deformation MLP", ["emd_linear_bwd_workspace_bytes", "emd_linear_fwd", "emd_linear_fwd_tc", "emd_linear_bwd", "emd_temb_fwd", "emd_temb_bwd"]),
     ("K2   projection", ["emd_projection_fwd", "emd_projection_bwd", "emd_dg_preprocess_fwd", "emd_dg_preprocess_bwd"]),
     ("K3   tile intersection", ["emd_scan_workspace_bytes", "emd_cumsum_i32_i64", "emd_exclusive_scan_u32",
                                 "emd_isect_emit", "emd_dg_isect_emit"]),
@@ -74,6 +74,8 @@ DOC = {
     "emd_linear_bwd_workspace_bytes": "Workspace bytes of emd_linear_bwd.",
     "emd_linear_fwd": "One Linear layer of the S3Gaussian EMD deformation network with its ReLUs fused "
                       "(S3Gaussian/scene/deformation.py:100-185, 339-386): Y = act_out(act_in(X) W^T + b); X[M,K], W[Nout,K].",
+    "emd_linear_fwd_tc": "emd_linear_fwd on the tensor cores: tcgen05.mma kind::tf32 with every operand split hi/lo (3xTF32, "
+                         "fp32-class accuracy), accumulator in TMEM.  K % 4 == 0, K <= 136, Nout <= 64.",
     "emd_linear_bwd": "VJP of emd_linear_fwd: dX (may be NULL), dW, db; fixed-order reductions.",
     "emd_temb_fwd": "get_temporal_embed (deformation.py:208-221 / rigid.py:150-164): resample table[E,d] to `cur` rows and "
                     "sample at time t -> emb[d].  t is a DEVICE scalar (time + learnable time_offset, deformation.py:325-328).",
