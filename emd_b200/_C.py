@@ -43,6 +43,7 @@ _SIGS = {
     "emd_linear_fwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P]),
     "emd_linear_fwd_tc": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P]),
     "emd_linear_bwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),
+    "emd_linear_bwd_tc": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),
     "emd_temb_fwd": (c_int, [P, c_int, c_int, P, c_int, P, P]),
     "emd_temb_bwd": (c_int, [P, c_int, c_int, P, c_int, P, P, P, P]),
     "emd_tile_order": (c_int, [P, c_int64, c_int64, P, P, P, P]),

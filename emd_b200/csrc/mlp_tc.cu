@@ -9,12 +9,14 @@
 // TF32) and lo = x - hi (exact in fp32), and a product is accumulated as hi*hi + lo*hi + hi*lo in the fp32 TMEM
 // accumulator ("3xTF32"): relative error ~2^-21 per product, i.e. fp32-class results at three tensor-core passes.
 //
-// CTA = 128 threads (4 warps) = one 128-row tile at a time (persistent over tiles):
-//   stage   : all threads read the tile's contiguous 128 x K block coalesced (float4), apply act_in, split hi/lo
-//             and write both copies in the K-major no-swizzle UMMA canonical layout
+// CTA = 256 threads, one 128-row tile at a time (persistent over tiles), two CTAs per SM so one CTA's loads and
+// epilogue run under the other's MMAs:
+//   stage   : the tile's X block is consumed 32 columns at a time: global float4 loads one chunk ahead into
+//             registers, act_in, hi/lo split, both copies written in the K-major no-swizzle UMMA canonical layout
 //             (core matrix = 8 rows x 16 B contiguous; row groups 128 B apart; K-adjacent core matrices LBO apart)
-//   mma     : one elected thread issues K/8 x 3 tcgen05.mma.kind::tf32 (M=128, N=Npad, K=8) and commits to an mbarrier
-//   epilogue: warp w reads TMEM lanes 32w..32w+31 (tcgen05.ld 32x32b), adds the bias, applies act_out, stores Y
+//   mma     : one thread issues 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=Npad, K=8) per chunk and commits to
+//             an mbarrier; the A buffer is rewritten only after that barrier completes
+//   epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31 (tcgen05.ld 32x32b), adds the bias, applies act_out, stores Y
 // W (hi and lo) is staged once per CTA.  No cuBLAS, no CUTLASS: descriptors and PTX are written out below.
 #include "common.cuh"
 
@@ -93,44 +95,48 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = x - hi;
 }
 
-// dynamic shared memory: [A_hi | A_lo | B_hi | B_lo], every region a multiple of 16 B
+// dynamic shared memory: [A_hi chunk | A_lo chunk | B_hi | B_lo], every region a multiple of 16 B.  A is staged
+// TC_KC columns at a time (one buffer; the second CTA on the SM supplies the overlap), W stays resident.
+constexpr int TC_THREADS = 256;
+constexpr int TC_KC = 32;                    // A columns staged per chunk (8 core-matrix columns, 4 MMA k-steps)
+constexpr int TC_A_CHUNK_BYTES = (TC_KC / 4) * TC_A_LBO;
+
 struct TcLayout {
-    int kchunks;        // Kpad / 4
+    int kchunks;        // Kpad / 4 core-matrix columns
     int npad;           // Nout padded to a multiple of 16
     int b_lbo;          // bytes between K-adjacent core-matrix columns of B
-    int a_bytes, b_bytes;
+    int b_bytes;
     __host__ __device__ TcLayout(int K, int Nout) {
         const int kpad = (K + 7) / 8 * 8;
         kchunks = kpad / 4;
         npad = (Nout + 15) / 16 * 16;
         b_lbo = npad * 16 + 16;
-        a_bytes = kchunks * TC_A_LBO;
         b_bytes = kchunks * b_lbo;
     }
-    __host__ __device__ size_t total() const { return 2 * (size_t)a_bytes + 2 * (size_t)b_bytes; }
+    __host__ __device__ size_t total() const { return 2 * (size_t)TC_A_CHUNK_BYTES + 2 * (size_t)b_bytes; }
 };
 
 template <bool RELU_IN, bool RELU_OUT>
-__global__ void __launch_bounds__(TC_ROWS, 1) linear_fwd_tc_kernel(const float* __restrict__ X, const float* __restrict__ W,
-                                                                   const float* __restrict__ bias, int64_t M, int K,
-                                                                   int Nout, float* __restrict__ Y) {
+__global__ void __launch_bounds__(TC_THREADS, 2) linear_fwd_tc_kernel(const float* __restrict__ X, const float* __restrict__ W,
+                                                                      const float* __restrict__ bias, int64_t M, int K,
+                                                                      int Nout, float* __restrict__ Y) {
     extern __shared__ __align__(128) unsigned char tc_smem[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_tmem;
     __shared__ float s_bias[TC_NMAX];
     const TcLayout L(K, Nout);
     unsigned char* sAhi = tc_smem;
-    unsigned char* sAlo = sAhi + L.a_bytes;
-    unsigned char* sBhi = sAlo + L.a_bytes;
+    unsigned char* sAlo = sAhi + TC_A_CHUNK_BYTES;
+    unsigned char* sBhi = sAlo + TC_A_CHUNK_BYTES;
     unsigned char* sBlo = sBhi + L.b_bytes;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kq = K / 4;   // float4 per row (K % 4 == 0)
 
     // ---- one-time setup: zero the padded operands, stage W (hi / lo), bias, barrier, TMEM ----
-    for (int e = tid; e < (int)(L.total() / 16); e += TC_ROWS) reinterpret_cast<float4*>(tc_smem)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = tid; e < (int)(L.total() / 16); e += TC_THREADS) reinterpret_cast<float4*>(tc_smem)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid < TC_NMAX) s_bias[tid] = tid < Nout ? __ldg(bias + tid) : 0.f;
     __syncthreads();
-    for (int e = tid; e < Nout * kq; e += TC_ROWS) {
+    for (int e = tid; e < Nout * kq; e += TC_THREADS) {
         const int n = e / kq, j = e - n * kq;
         const float4 w = __ldg(reinterpret_cast<const float4*>(W) + e);   // W[n][4j..4j+3]
         float4 hi, lo;
@@ -154,48 +160,76 @@ __global__ void __launch_bounds__(TC_ROWS, 1) linear_fwd_tc_kernel(const float* 
     const uint32_t tmem = s_tmem;
     const uint32_t idesc = umma_idesc_tf32(TC_ROWS, L.npad);
     const uint32_t aHi = smem_u32(sAhi), aLo = smem_u32(sAlo), bHi = smem_u32(sBhi), bLo = smem_u32(sBlo);
-    const int ksteps = L.kchunks / 2;
+    const int nchunks = (L.kchunks * 4 + TC_KC - 1) / TC_KC;   // A chunks per tile
     uint32_t phase = 0;
 
+    // thread -> (row, core-matrix column) of the 128 x 32 chunk: 4 float4 per thread, rows r0 + 32 i
+    const int cj = tid & 7, cr = tid >> 3;
     const int64_t n_tiles = (M + TC_ROWS - 1) / TC_ROWS;
+    float4 pre[4];
+    auto load_chunk = [&](int64_t row0, int c) {
+        const int jg = c * (TC_KC / 4) + cj;   // core-matrix column in the full K
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t row = row0 + cr + 32 * i;
+            pre[i] = (row < M && jg < kq) ? __ldg(reinterpret_cast<const float4*>(X + row * K) + jg) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    if ((int64_t)blockIdx.x < n_tiles) load_chunk((int64_t)blockIdx.x * TC_ROWS, 0);
+    bool mma_pending = false;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * TC_ROWS;
-        const int rows = (int)min((int64_t)TC_ROWS, M - row0);
-        // ---- stage A: the tile is one contiguous span of rows * K floats ----
-        const float4* x4 = reinterpret_cast<const float4*>(X + row0 * K);
-        for (int q = tid; q < TC_ROWS * kq; q += TC_ROWS) {
-            const int r = q / kq, j = q - r * kq;
-            float4 x = r < rows ? __ldg(x4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (RELU_IN) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-            float4 hi, lo;
-            split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
-            *reinterpret_cast<float4*>(sAhi + j * TC_A_LBO + r * 16) = hi;
-            *reinterpret_cast<float4*>(sAlo + j * TC_A_LBO + r * 16) = lo;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
-        __syncthreads();
-        // ---- MMA: one thread issues, completion arrives on the mbarrier ----
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int s = 0; s < ksteps; ++s) {
-                const uint64_t dAh = umma_desc(aHi + 2 * s * TC_A_LBO, TC_A_LBO, TC_SBO);
-                const uint64_t dAl = umma_desc(aLo + 2 * s * TC_A_LBO, TC_A_LBO, TC_SBO);
-                const uint64_t dBh = umma_desc(bHi + 2 * s * L.b_lbo, L.b_lbo, TC_SBO);
-                const uint64_t dBl = umma_desc(bLo + 2 * s * L.b_lbo, L.b_lbo, TC_SBO);
-                umma_tf32(tmem, dAl, dBh, idesc, s > 0 ? 1u : 0u);   // small terms first
-                umma_tf32(tmem, dAh, dBl, idesc, 1u);
-                umma_tf32(tmem, dAh, dBh, idesc, 1u);
+        for (int c = 0; c < nchunks; ++c) {
+            if (mma_pending) {   // the MMAs that read the A buffer must have completed before it is overwritten
+                mbar_wait(bar, phase);
+                phase ^= 1u;
+                mma_pending = false;
             }
-            umma_commit(bar);
+            // ---- registers (loaded one step ahead) -> act_in, hi/lo split, canonical K-major layout ----
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float4 x = pre[i];
+                if (RELU_IN) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                float4 hi, lo;
+                split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+                *reinterpret_cast<float4*>(sAhi + cj * TC_A_LBO + (cr + 32 * i) * 16) = hi;
+                *reinterpret_cast<float4*>(sAlo + cj * TC_A_LBO + (cr + 32 * i) * 16) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
+            __syncthreads();
+            // ---- next chunk's global loads fly under this chunk's MMAs ----
+            if (c + 1 < nchunks) load_chunk(row0, c + 1);
+            else if (tile + gridDim.x < n_tiles) load_chunk((tile + gridDim.x) * TC_ROWS, 0);
+            // ---- MMA: one thread issues, completion arrives on the mbarrier ----
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int s0 = c * (TC_KC / 8);
+                const int s1 = min(s0 + TC_KC / 8, L.kchunks / 2);
+                for (int s = s0; s < s1; ++s) {
+                    const int sl = s - s0;   // k-step inside the A chunk buffer
+                    const uint64_t dAh = umma_desc(aHi + 2 * sl * TC_A_LBO, TC_A_LBO, TC_SBO);
+                    const uint64_t dAl = umma_desc(aLo + 2 * sl * TC_A_LBO, TC_A_LBO, TC_SBO);
+                    const uint64_t dBh = umma_desc(bHi + 2 * s * L.b_lbo, L.b_lbo, TC_SBO);
+                    const uint64_t dBl = umma_desc(bLo + 2 * s * L.b_lbo, L.b_lbo, TC_SBO);
+                    umma_tf32(tmem, dAl, dBh, idesc, s > 0 ? 1u : 0u);   // small terms first
+                    umma_tf32(tmem, dAh, dBl, idesc, 1u);
+                    umma_tf32(tmem, dAh, dBh, idesc, 1u);
+                }
+                umma_commit(bar);
+            }
+            mma_pending = true;
         }
         mbar_wait(bar, phase);
         phase ^= 1u;
+        mma_pending = false;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- epilogue: thread = row (TMEM lane), 16 columns at a time ----
-        const int64_t row = row0 + tid;
-        for (int c0 = 0; c0 < L.npad; c0 += 16) {
+        // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31; warps 4-7 take the upper half of the columns ----
+        const int64_t row = row0 + (warp & 3) * 32 + lane;
+        const int cbeg = (warp >> 2) * 32;                       // warps 0-3: columns [0, 32), warps 4-7: [32, npad)
+        const int cend = min(L.npad, cbeg + 32);
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
             float v[16];
-            tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
             if (row < M) {
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
@@ -215,11 +249,321 @@ __global__ void __launch_bounds__(TC_ROWS, 1) linear_fwd_tc_kernel(const float* 
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();   // TMEM and the A tile are free again
+        __syncthreads();   // TMEM is free again
     }
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TC_TMEM_COLS) : "memory");
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward, data gradient:  dG = dY (.) relu'(Y)  (written out for the weight-gradient kernel),
+//                           dX = (dG . W) (.) relu'(X)
+// The same GEMM skeleton as the forward with A = dG [rows x Nout] (reduction over Nout) and B[n][k] = W[k][n].
+// ---------------------------------------------------------------------------------------------------------------
+template <bool RELU_IN, bool RELU_OUT>
+__global__ void __launch_bounds__(TC_THREADS, 2) linear_dgrad_tc_kernel(
+    const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ Y, const float* __restrict__ dY,
+    int64_t M, int K, int Nout, int tmem_cols, float* __restrict__ dG, float* __restrict__ dX) {
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const TcLayout L(Nout, K);   // reduction = Nout, output columns = K
+    unsigned char* sAhi = tc_smem;
+    unsigned char* sAlo = sAhi + TC_A_CHUNK_BYTES;
+    unsigned char* sBhi = sAlo + TC_A_CHUNK_BYTES;
+    unsigned char* sBlo = sBhi + L.b_bytes;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool vec = (Nout & 3) == 0;
+
+    for (int e = tid; e < (int)(L.total() / 16); e += TC_THREADS) reinterpret_cast<float4*>(tc_smem)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    for (int e = tid; e < Nout * K; e += TC_THREADS) {
+        const int k = e / K, n = e - k * K;   // W[k][n]: k = output feature (reduction index here), n = input feature
+        float hi, lo;
+        split_tf32(__ldg(W + e), hi, lo);
+        *reinterpret_cast<float*>(sBhi + (k >> 2) * L.b_lbo + n * 16 + (k & 3) * 4) = hi;
+        *reinterpret_cast<float*>(sBlo + (k >> 2) * L.b_lbo + n * 16 + (k & 3) * 4) = lo;
+    }
+    const uint32_t bar = smem_u32(&s_bar);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = umma_idesc_tf32(TC_ROWS, L.npad);
+    const uint32_t aHi = smem_u32(sAhi), aLo = smem_u32(sAlo), bHi = smem_u32(sBhi), bLo = smem_u32(sBlo);
+    const int nchunks = (L.kchunks * 4 + TC_KC - 1) / TC_KC;
+    uint32_t phase = 0;
+    const int cj = tid & 7, cr = tid >> 3;
+    const int64_t n_tiles = (M + TC_ROWS - 1) / TC_ROWS;
+    const int split = ((L.npad / 16 + 1) / 2) * 16;   // warps 0-3: columns [0, split), warps 4-7: [split, npad)
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * TC_ROWS;
+        for (int c = 0; c < nchunks; ++c) {
+            // dG chunk: rows cr + 32 i, reduction columns 4 jg .. 4 jg + 3
+            const int jg = c * (TC_KC / 4) + cj;
+            float4 g[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t row = row0 + cr + 32 * i;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < M && 4 * jg < Nout) {
+                    if (vec) {
+                        v = __ldg(reinterpret_cast<const float4*>(dY + row * Nout) + jg);
+                        if (RELU_OUT) {
+                            const float4 y = __ldg(reinterpret_cast<const float4*>(Y + row * Nout) + jg);
+                            if (!(y.x > 0.f)) v.x = 0.f; if (!(y.y > 0.f)) v.y = 0.f; if (!(y.z > 0.f)) v.z = 0.f; if (!(y.w > 0.f)) v.w = 0.f;
+                        }
+                        reinterpret_cast<float4*>(dG + row * Nout)[jg] = v;
+                    } else {
+                        float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int col = 4 * jg + q;
+                            if (col < Nout) {
+                                float gq = __ldg(dY + row * Nout + col);
+                                if (RELU_OUT && !(__ldg(Y + row * Nout + col) > 0.f)) gq = 0.f;
+                                dG[row * Nout + col] = gq;
+                                t[q] = gq;
+                            }
+                        }
+                        v = make_float4(t[0], t[1], t[2], t[3]);
+                    }
+                }
+                g[i] = v;
+            }
+            if (dX == nullptr) continue;   // (kernel-uniform) only dG is wanted
+            if (c > 0) {   // the MMAs reading the A buffer must have completed before it is overwritten
+                mbar_wait(bar, phase);
+                phase ^= 1u;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float4 hi, lo;
+                split_tf32(g[i].x, hi.x, lo.x); split_tf32(g[i].y, hi.y, lo.y); split_tf32(g[i].z, hi.z, lo.z); split_tf32(g[i].w, hi.w, lo.w);
+                *reinterpret_cast<float4*>(sAhi + cj * TC_A_LBO + (cr + 32 * i) * 16) = hi;
+                *reinterpret_cast<float4*>(sAlo + cj * TC_A_LBO + (cr + 32 * i) * 16) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int s0 = c * (TC_KC / 8);
+                const int s1 = min(s0 + TC_KC / 8, L.kchunks / 2);
+                for (int s = s0; s < s1; ++s) {
+                    const int sl = s - s0;
+                    const uint64_t dAh = umma_desc(aHi + 2 * sl * TC_A_LBO, TC_A_LBO, TC_SBO);
+                    const uint64_t dAl = umma_desc(aLo + 2 * sl * TC_A_LBO, TC_A_LBO, TC_SBO);
+                    const uint64_t dBh = umma_desc(bHi + 2 * s * L.b_lbo, L.b_lbo, TC_SBO);
+                    const uint64_t dBl = umma_desc(bLo + 2 * s * L.b_lbo, L.b_lbo, TC_SBO);
+                    umma_tf32(tmem, dAl, dBh, idesc, s > 0 ? 1u : 0u);
+                    umma_tf32(tmem, dAh, dBl, idesc, 1u);
+                    umma_tf32(tmem, dAh, dBh, idesc, 1u);
+                }
+                umma_commit(bar);
+            }
+        }
+        if (dX == nullptr) continue;
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int64_t row = row0 + (warp & 3) * 32 + lane;
+        const int cbeg = warp < 4 ? 0 : split, cend = warp < 4 ? split : L.npad;
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
+            if (row < M) {
+#pragma unroll
+                for (int cc = 0; cc < 16; cc += 4) {
+                    const int col = c0 + cc;
+                    if (col + 4 <= K) {   // K % 4 == 0: whole float4 groups only
+                        float4 o = make_float4(v[cc], v[cc + 1], v[cc + 2], v[cc + 3]);
+                        if (RELU_IN) {
+                            const float4 x = __ldg(reinterpret_cast<const float4*>(X + row * K + col));
+                            if (!(x.x > 0.f)) o.x = 0.f; if (!(x.y > 0.f)) o.y = 0.f; if (!(x.z > 0.f)) o.z = 0.f; if (!(x.w > 0.f)) o.w = 0.f;
+                        }
+                        *reinterpret_cast<float4*>(dX + row * K + col) = o;
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+    }
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(tmem_cols) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward, weight gradient:  dW[Nout][K] = dG^T . act_in(X),  db = colsum(dG)  (a ones column appended to X)
+// D[m = output feature (padded to 128)][n = input feature | ones] accumulates in TMEM over ALL row tiles of the CTA;
+// the reduction runs over rows, 32 at a time.  Both operands are written TRANSPOSED into the K-major canonical
+// layout (element (m, row) at (row / 4) * LBO + m * 16 + (row % 4) * 4): lanes run along the rows, which makes the
+// 4-byte shared-memory stores conflict-free (32 lanes -> 32 banks).
+// Per-CTA partials are reduced in a fixed order by linear_wgrad_tc_reduce_kernel: no float atomics.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TC_WR = 32;                         // rows (= reduction depth) staged per step: 8 core columns, 4 k-steps
+
+template <bool RELU_IN>
+__global__ void __launch_bounds__(TC_THREADS, 2) linear_wgrad_tc_kernel(const float* __restrict__ X, const float* __restrict__ dG,
+                                                                        int64_t M, int K, int Nout, int tmem_cols,
+                                                                        float* __restrict__ partial) {
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const int npad = (K + 1 + 15) / 16 * 16;          // columns of [X | 1], padded to N % 16 == 0
+    const int x_lbo = npad * 16 + 16;
+    const int g_bytes = (TC_WR / 4) * TC_A_LBO, x_bytes = (TC_WR / 4) * x_lbo;
+    unsigned char* sGhi = tc_smem;
+    unsigned char* sGlo = sGhi + g_bytes;
+    unsigned char* sXhi = sGlo + g_bytes;
+    unsigned char* sXlo = sXhi + x_bytes;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool gvec = (Nout & 3) == 0;
+    const int ggroups = (Nout + 3) / 4, kq = K / 4;
+
+    for (int e = tid; e < (2 * g_bytes + 2 * x_bytes) / 16; e += TC_THREADS) reinterpret_cast<float4*>(tc_smem)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t bar = smem_u32(&s_bar);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = umma_idesc_tf32(TC_ROWS, npad);
+    const uint32_t gHi = smem_u32(sGhi), gLo = smem_u32(sGlo), xHi = smem_u32(sXhi), xLo = smem_u32(sXlo);
+    uint32_t phase = 0;
+    bool pending = false, first = true;
+
+    const int64_t n_tiles = (M + TC_ROWS - 1) / TC_ROWS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int rc = 0; rc < TC_ROWS / TC_WR; ++rc) {
+            const int64_t row0 = tile * TC_ROWS + rc * TC_WR;
+            if (row0 >= M) break;   // CTA-uniform
+            if (pending) {
+                mbar_wait(bar, phase);
+                phase ^= 1u;
+                pending = false;
+            }
+            const int64_t row = row0 + lane;                       // lane = row of the 32-row chunk
+            const int roff = (lane >> 2) * TC_A_LBO + (lane & 3) * 4;
+            const int xoff = (lane >> 2) * x_lbo + (lane & 3) * 4;
+            // dG^T: output feature m = 4 j + q
+            for (int j = warp; j < ggroups; j += TC_THREADS / 32) {
+                float t[4] = {0.f, 0.f, 0.f, 0.f};
+                if (row < M) {
+                    if (gvec) { const float4 v = __ldg(reinterpret_cast<const float4*>(dG + row * Nout) + j); t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w; }
+                    else {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) if (4 * j + c < Nout) t[c] = __ldg(dG + row * Nout + 4 * j + c);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float hi, lo;
+                    split_tf32(t[c], hi, lo);
+                    *reinterpret_cast<float*>(sGhi + roff + (4 * j + c) * 16) = hi;
+                    *reinterpret_cast<float*>(sGlo + roff + (4 * j + c) * 16) = lo;
+                }
+            }
+            // [X | 1]^T: input feature n = 4 j + q, the ones column at n = K
+            for (int j = warp; j <= kq; j += TC_THREADS / 32) {
+                float t[4] = {0.f, 0.f, 0.f, 0.f};
+                if (row < M) {
+                    if (j < kq) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(X + row * K) + j);
+                        t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+                        if (RELU_IN) { t[0] = fmaxf(t[0], 0.f); t[1] = fmaxf(t[1], 0.f); t[2] = fmaxf(t[2], 0.f); t[3] = fmaxf(t[3], 0.f); }
+                    } else {
+                        t[0] = 1.0f;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float hi, lo;
+                    split_tf32(t[c], hi, lo);
+                    *reinterpret_cast<float*>(sXhi + xoff + (4 * j + c) * 16) = hi;
+                    *reinterpret_cast<float*>(sXlo + xoff + (4 * j + c) * 16) = lo;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int ks = 0; ks < TC_WR / 8; ++ks) {   // one MMA k-step = 8 rows = 2 core-matrix columns
+                    const uint64_t dAh = umma_desc(gHi + 2 * ks * TC_A_LBO, TC_A_LBO, TC_SBO);
+                    const uint64_t dAl = umma_desc(gLo + 2 * ks * TC_A_LBO, TC_A_LBO, TC_SBO);
+                    const uint64_t dBh = umma_desc(xHi + 2 * ks * x_lbo, x_lbo, TC_SBO);
+                    const uint64_t dBl = umma_desc(xLo + 2 * ks * x_lbo, x_lbo, TC_SBO);
+                    umma_tf32(tmem, dAl, dBh, idesc, (first && ks == 0) ? 0u : 1u);
+                    umma_tf32(tmem, dAh, dBl, idesc, 1u);
+                    umma_tf32(tmem, dAh, dBh, idesc, 1u);
+                }
+                umma_commit(bar);
+            }
+            first = false;
+            pending = true;
+        }
+    }
+    float* out = partial + (size_t)blockIdx.x * ((size_t)Nout * K + Nout);
+    if (first) {   // this CTA owned no rows
+        for (int e = tid; e < Nout * K + Nout; e += TC_THREADS) out[e] = 0.f;
+    } else {
+        if (pending) mbar_wait(bar, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int m = (warp & 3) * 32 + lane;            // output feature = TMEM lane
+        const int split = ((npad / 16 + 1) / 2) * 16;
+        const int cbeg = warp < 4 ? 0 : split, cend = warp < 4 ? split : npad;
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
+            if (m < Nout) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const int col = c0 + c;
+                    if (col < K) out[(size_t)m * K + col] = v[c];
+                    else if (col == K) out[(size_t)Nout * K + m] = v[c];
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(tmem_cols) : "memory");
+}
+
+__global__ void linear_wgrad_tc_reduce_kernel(const float* __restrict__ partial, int nparts, int count,
+                                              float* __restrict__ dW, float* __restrict__ db, int nW) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * count + i];
+    if (i < nW) dW[i] = s; else db[i - nW] = s;
+}
+
+int tc_grid(int64_t M) {
+    const int64_t tiles = (M + TC_ROWS - 1) / TC_ROWS;
+    return (int)(tiles < EMD_NUM_SMS * 2 ? (tiles > 0 ? tiles : 1) : EMD_NUM_SMS * 2);
+}
+int tmem_cols_for(int npad) { return npad <= 32 ? 32 : npad <= 64 ? 64 : npad <= 128 ? 128 : 256; }
 
 }  // namespace
 
@@ -236,11 +580,11 @@ extern "C" int emd_linear_fwd_tc(const float* X, const float* W, const float* b,
     const TcLayout L(K, Nout);
     const size_t smem = L.total();
     const int64_t n_tiles = (M + TC_ROWS - 1) / TC_ROWS;
-    const unsigned grid = (unsigned)(n_tiles < EMD_NUM_SMS ? n_tiles : EMD_NUM_SMS);
+    const unsigned grid = (unsigned)(n_tiles < 2 * EMD_NUM_SMS ? n_tiles : 2 * EMD_NUM_SMS);
 #define EMD_TC_LAUNCH(RI, RO)                                                                                          \
     do {                                                                                                               \
         cudaFuncSetAttribute(linear_fwd_tc_kernel<RI, RO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-        EMD_LAUNCH(EK_MLP_FWD, stream, (linear_fwd_tc_kernel<RI, RO><<<grid, TC_ROWS, smem, stream>>>(X, W, b, M, K, Nout, Y))); \
+        EMD_LAUNCH(EK_MLP_FWD, stream, (linear_fwd_tc_kernel<RI, RO><<<grid, TC_THREADS, smem, stream>>>(X, W, b, M, K, Nout, Y))); \
     } while (0)
     if (relu_in && relu_out) EMD_TC_LAUNCH(true, true);
     else if (relu_in) EMD_TC_LAUNCH(true, false);
@@ -248,5 +592,59 @@ extern "C" int emd_linear_fwd_tc(const float* X, const float* W, const float* b,
     else EMD_TC_LAUNCH(false, false);
 #undef EMD_TC_LAUNCH
     EMD_CHECK_LAUNCH("linear_fwd_tc");
+    return EMD_OK;
+}
+
+extern "C" size_t emd_linear_bwd_workspace_bytes(int64_t M, int K, int Nout);
+
+// Tensor-core VJP of one Linear layer: same contract as emd_linear_bwd (dX may be NULL), same workspace size.
+extern "C" int emd_linear_bwd_tc(const float* X, const float* W, const float* Y, const float* dY, int64_t M, int K,
+                                 int Nout, int relu_in, int relu_out, float* dX, float* dW, float* db, void* workspace,
+                                 size_t ws_bytes, cudaStream_t stream) {
+    EMD_CHECK_ARG(M >= 0 && K >= 4 && K <= TC_KMAX && (K % 4) == 0, "linear_bwd_tc: K must be a multiple of 4 in [4, %d]", TC_KMAX);
+    EMD_CHECK_ARG(Nout >= 1 && Nout <= TC_NMAX, "linear_bwd_tc: Nout must be in [1, %d]", TC_NMAX);
+    if (ws_bytes < emd_linear_bwd_workspace_bytes(M, K, Nout)) { emd_set_error("linear_bwd_tc: workspace too small"); return EMD_ERR_WORKSPACE; }
+    if (!emd_aligned(X, 16) || !emd_aligned(dY, 16) || !emd_aligned(Y, 16) || !emd_aligned(workspace, 16) || (dX && !emd_aligned(dX, 16))) {
+        emd_set_error("linear_bwd_tc: X, Y, dY, dX and the workspace must be 16-B aligned");
+        return EMD_ERR_ALIGN;
+    }
+    const int count = Nout * K + Nout;
+    if (M == 0) {
+        cudaMemsetAsync(dW, 0, (size_t)Nout * K * sizeof(float), stream);
+        cudaMemsetAsync(db, 0, (size_t)Nout * sizeof(float), stream);
+        return EMD_OK;
+    }
+    float* dG = reinterpret_cast<float*>(workspace);
+    float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ((size_t)M * Nout * sizeof(float) + 255) / 256 * 256);
+    const int grid = tc_grid(M);
+    {
+        const TcLayout L(Nout, K);
+        const size_t smem = L.total();
+        const int tcols = tmem_cols_for(L.npad);
+#define EMD_TC_DG(RI, RO)                                                                                              \
+    do {                                                                                                               \
+        cudaFuncSetAttribute(linear_dgrad_tc_kernel<RI, RO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        EMD_LAUNCH(EK_MLP_BWD, stream, (linear_dgrad_tc_kernel<RI, RO><<<grid, TC_THREADS, smem, stream>>>(X, W, Y, dY, M, K, Nout, tcols, dG, dX))); \
+    } while (0)
+        if (relu_in && relu_out) EMD_TC_DG(true, true);
+        else if (relu_in) EMD_TC_DG(true, false);
+        else if (relu_out) EMD_TC_DG(false, true);
+        else EMD_TC_DG(false, false);
+#undef EMD_TC_DG
+    }
+    {
+        const int npad = (K + 1 + 15) / 16 * 16;
+        const size_t smem = 2 * (size_t)(TC_WR / 4) * (TC_A_LBO + npad * 16 + 16);
+        const int tcols = tmem_cols_for(npad);
+        if (relu_in) {
+            cudaFuncSetAttribute(linear_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            EMD_LAUNCH(EK_MLP_BWD, stream, (linear_wgrad_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(X, dG, M, K, Nout, tcols, partial)));
+        } else {
+            cudaFuncSetAttribute(linear_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            EMD_LAUNCH(EK_MLP_BWD, stream, (linear_wgrad_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(X, dG, M, K, Nout, tcols, partial)));
+        }
+    }
+    EMD_LAUNCH(EK_MLP_BWD, stream, (linear_wgrad_tc_reduce_kernel<<<(count + 127) / 128, 128, 0, stream>>>(partial, grid, count, dW, db, Nout * K)));
+    EMD_CHECK_LAUNCH("linear_bwd_tc");
     return EMD_OK;
 }

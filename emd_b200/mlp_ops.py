@@ -17,8 +17,11 @@ class _Linear(torch.autograd.Function):
         Nout = W.shape[0]
         assert W.shape[1] == K and b.shape[0] == Nout
         Y = torch.empty(M, Nout, dtype=torch.float32, device=X.device)
-        _C.check(L.emd_linear_fwd(_C.ptr(X, torch.float32, "X"), _C.ptr(W), _C.ptr(b), M, K, Nout, int(relu_in),
-                                  int(relu_out), _C.ptr(Y), _C.stream()), "emd_linear_fwd")
+        # tensor-core path (tcgen05, 3xTF32: fp32-class accuracy) for every shape of the deformation network;
+        # the fp32 SIMT kernel covers the shapes outside its limits
+        fwd = L.emd_linear_fwd_tc if (K % 4 == 0 and K <= 136 and Nout <= 64) else L.emd_linear_fwd
+        _C.check(fwd(_C.ptr(X, torch.float32, "X"), _C.ptr(W), _C.ptr(b), M, K, Nout, int(relu_in),
+                     int(relu_out), _C.ptr(Y), _C.stream()), "emd_linear_fwd")
         ctx.save_for_backward(X, W, Y)
         ctx.cfg = (M, K, Nout, int(relu_in), int(relu_out))
         return Y
@@ -35,8 +38,9 @@ class _Linear(torch.autograd.Function):
         db = torch.empty(Nout, dtype=torch.float32, device=dev)
         ws_bytes = L.emd_linear_bwd_workspace_bytes(M, K, Nout)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _C.check(L.emd_linear_bwd(_C.ptr(X), _C.ptr(W), _C.ptr(Y), _C.ptr(dY), M, K, Nout, relu_in, relu_out,
-                                  _C.ptr(dX), _C.ptr(dW), _C.ptr(db), _C.ptr(ws), ws_bytes, _C.stream()),
+        bwd = L.emd_linear_bwd_tc if (K % 4 == 0 and K <= 136 and Nout <= 64) else L.emd_linear_bwd
+        _C.check(bwd(_C.ptr(X), _C.ptr(W), _C.ptr(Y), _C.ptr(dY), M, K, Nout, relu_in, relu_out,
+                     _C.ptr(dX), _C.ptr(dW), _C.ptr(db), _C.ptr(ws), ws_bytes, _C.stream()),
                  "emd_linear_bwd")
         return dX, dW, db, None, None
 

@@ -16,7 +16,7 @@ GROUPS = [
                                                          "emd_smpl_reduce_width", "emd_smpl_deform_fwd",
                                                          "emd_smpl_deform_bwd"]),
     ("K1b  spherical harmonics + node activations", ["emd_sh_fwd", "emd_sh_bwd", "emd_activate_fwd", "emd_activate_bwd"]),
-    ("K1d  S3Gaussian EMD deformation MLP", ["emd_linear_bwd_workspace_bytes", "emd_linear_fwd", "emd_linear_fwd_tc", "emd_linear_bwd", "emd_temb_fwd", "emd_temb_bwd"]),
+    ("K1d  S3Gaussian EMD deformation MLP", ["emd_linear_bwd_workspace_bytes", "emd_linear_fwd", "emd_linear_fwd_tc", "emd_linear_bwd", "emd_linear_bwd_tc", "emd_temb_fwd", "emd_temb_bwd"]),
     ("K2   projection", ["emd_projection_fwd", "emd_projection_bwd", "emd_dg_preprocess_fwd", "emd_dg_preprocess_bwd"]),
     ("K3   tile intersection", ["emd_scan_workspace_bytes", "emd_cumsum_i32_i64", "emd_exclusive_scan_u32",
                                 "emd_isect_emit", "emd_dg_isect_emit"]),
@@ -77,6 +77,9 @@ DOC = {
     "emd_linear_fwd_tc": "emd_linear_fwd on the tensor cores: tcgen05.mma kind::tf32 with every operand split hi/lo (3xTF32, "
                          "fp32-class accuracy), accumulator in TMEM.  K % 4 == 0, K <= 136, Nout <= 64.",
     "emd_linear_bwd": "VJP of emd_linear_fwd: dX (may be NULL), dW, db; fixed-order reductions.",
+    "emd_linear_bwd_tc": "emd_linear_bwd on the tensor cores (3xTF32): data gradient as a K-major GEMM against W^T, weight "
+                         "gradient + bias gradient accumulated in TMEM over each CTA's row tiles from MN-major operands, "
+                         "fixed-order reduction of the per-CTA partials.  Same workspace as emd_linear_bwd.",
     "emd_temb_fwd": "get_temporal_embed (deformation.py:208-221 / rigid.py:150-164): resample table[E,d] to `cur` rows and "
                     "sample at time t -> emb[d].  t is a DEVICE scalar (time + learnable time_offset, deformation.py:325-328).",
     "emd_temb_bwd": "VJP of emd_temb_fwd w.r.t. the table (ADDS into v_table) and t.",
