@@ -319,7 +319,7 @@ def run_ours(args):
             b.record()
             torch.cuda.synchronize()
             line["fwd_ms_per_frame"] = round(a.elapsed_time(b) / args.steps / C, 4)
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported at N=1 only (rank 0's host cores)
             line["cpu_baseline"] = cpu_baseline(args, steps=1, warmup=0)
         print(json.dumps(line))
     if world > 1:

@@ -457,50 +457,71 @@ __global__ void __launch_bounds__(TC_THREADS, 2) linear_wgrad_tc_kernel(const fl
         for (int rc = 0; rc < TC_ROWS / TC_WR; ++rc) {
             const int64_t row0 = tile * TC_ROWS + rc * TC_WR;
             if (row0 >= M) break;   // CTA-uniform
-            if (pending) {
+            const int64_t row = row0 + lane;                       // lane = row of the 32-row chunk
+            const int roff = (lane >> 2) * TC_A_LBO + (lane & 3) * 4;
+            const int xoff = (lane >> 2) * x_lbo + (lane & 3) * 4;
+            // all global loads of the chunk first (<= 2 + 5 float4 per thread), so they fly together and under the
+            // previous chunk's MMAs; warp w owns column groups w, w + 8, ...
+            constexpr int NW = TC_THREADS / 32;
+            float4 gv[2], xv[5];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int j = warp + NW * u;
+                gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < M && j < ggroups) {
+                    if (gvec) gv[u] = __ldg(reinterpret_cast<const float4*>(dG + row * Nout) + j);
+                    else {
+                        float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) if (4 * j + c < Nout) t[c] = __ldg(dG + row * Nout + 4 * j + c);
+                        gv[u] = make_float4(t[0], t[1], t[2], t[3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+                const int j = warp + NW * u;
+                xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < M && j <= kq) {
+                    if (j < kq) {
+                        xv[u] = __ldg(reinterpret_cast<const float4*>(X + row * K) + j);
+                        if (RELU_IN) { xv[u].x = fmaxf(xv[u].x, 0.f); xv[u].y = fmaxf(xv[u].y, 0.f); xv[u].z = fmaxf(xv[u].z, 0.f); xv[u].w = fmaxf(xv[u].w, 0.f); }
+                    } else {
+                        xv[u].x = 1.0f;   // the ones column: db = colsum(dG)
+                    }
+                }
+            }
+            if (pending) {   // the MMAs reading the buffers must have completed before they are overwritten
                 mbar_wait(bar, phase);
                 phase ^= 1u;
                 pending = false;
             }
-            const int64_t row = row0 + lane;                       // lane = row of the 32-row chunk
-            const int roff = (lane >> 2) * TC_A_LBO + (lane & 3) * 4;
-            const int xoff = (lane >> 2) * x_lbo + (lane & 3) * 4;
-            // dG^T: output feature m = 4 j + q
-            for (int j = warp; j < ggroups; j += TC_THREADS / 32) {
-                float t[4] = {0.f, 0.f, 0.f, 0.f};
-                if (row < M) {
-                    if (gvec) { const float4 v = __ldg(reinterpret_cast<const float4*>(dG + row * Nout) + j); t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w; }
-                    else {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) if (4 * j + c < Nout) t[c] = __ldg(dG + row * Nout + 4 * j + c);
+            for (int u = 0; u < 2; ++u) {
+                const int j = warp + NW * u;
+                if (j < ggroups) {
+                    const float t[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float hi, lo;
+                        split_tf32(t[c], hi, lo);
+                        *reinterpret_cast<float*>(sGhi + roff + (4 * j + c) * 16) = hi;
+                        *reinterpret_cast<float*>(sGlo + roff + (4 * j + c) * 16) = lo;
                     }
-                }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float hi, lo;
-                    split_tf32(t[c], hi, lo);
-                    *reinterpret_cast<float*>(sGhi + roff + (4 * j + c) * 16) = hi;
-                    *reinterpret_cast<float*>(sGlo + roff + (4 * j + c) * 16) = lo;
                 }
             }
-            // [X | 1]^T: input feature n = 4 j + q, the ones column at n = K
-            for (int j = warp; j <= kq; j += TC_THREADS / 32) {
-                float t[4] = {0.f, 0.f, 0.f, 0.f};
-                if (row < M) {
-                    if (j < kq) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(X + row * K) + j);
-                        t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
-                        if (RELU_IN) { t[0] = fmaxf(t[0], 0.f); t[1] = fmaxf(t[1], 0.f); t[2] = fmaxf(t[2], 0.f); t[3] = fmaxf(t[3], 0.f); }
-                    } else {
-                        t[0] = 1.0f;
-                    }
-                }
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float hi, lo;
-                    split_tf32(t[c], hi, lo);
-                    *reinterpret_cast<float*>(sXhi + xoff + (4 * j + c) * 16) = hi;
-                    *reinterpret_cast<float*>(sXlo + xoff + (4 * j + c) * 16) = lo;
+            for (int u = 0; u < 5; ++u) {
+                const int j = warp + NW * u;
+                if (j <= kq) {
+                    const float t[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float hi, lo;
+                        split_tf32(t[c], hi, lo);
+                        *reinterpret_cast<float*>(sXhi + xoff + (4 * j + c) * 16) = hi;
+                        *reinterpret_cast<float*>(sXlo + xoff + (4 * j + c) * 16) = lo;
+                    }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
