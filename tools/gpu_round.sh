@@ -23,10 +23,12 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_bench.log 2>&1
 wc -l $OUT/${TAG}_launches.csv
 if [ "${2:-}" != "skip_full" ]; then
-echo "== ncu --set full (raster_bwd, raster_fwd, sort, projection_bwd, smpl_bwd)"
+echo "== ncu --set full (raster_bwd, raster_fwd_seg, onesweep, projection_bwd, gather, activate_bwd)"
 timeout 1500 ncu --set full --clock-control none --import-source on \
-    -k regex:'raster_bwd_kernel|raster_fwd_kernel|rs_scatter|projection_bwd|smpl_point_bwd|smpl_.*bwd|raster_gather' \
-    -s 30 -c 14 -o $OUT/${TAG}_full python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
+    -k regex:'raster_bwd_kernel|raster_fwd_seg_kernel|rs_onesweep|projection_bwd|projection_fwd|raster_gather|activate_bwd|activate_fwd|isect_emit' \
+    -s 60 -c 20 -o $OUT/${TAG}_full python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
 ls -la $OUT/${TAG}_full.ncu-rep
 fi
+echo '== s3g'
+timeout 300 python tools/s3g_bench.py 1000000 > $OUT/${TAG}_s3g.json 2>&1; tail -c 1500 $OUT/${TAG}_s3g.json
 echo done
