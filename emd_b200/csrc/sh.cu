@@ -144,7 +144,11 @@ struct ActArgs {
     int64_t N;
     int K;          // total bases stored (1 + rest rows)
     int deg;        // degree to use
+    int parts;      // bit 0: colours (dc/rest/means -> rgbs), bit 1: geometry (opacity, scales, quats); the host
+                    // mirror runs them as two autograd nodes so the SH-coefficient gradient (75 % of the bytes the
+                    // all-reduce moves) is ready before the projection backward runs
 };
+constexpr int ACT_COLORS = 1, ACT_GEOM = 2;
 
 __global__ void __launch_bounds__(SH_THREADS) activate_fwd_kernel(ActArgs a, float* __restrict__ rgbs,
                                                                   float* __restrict__ opac, float* __restrict__ scales,
@@ -156,13 +160,16 @@ __global__ void __launch_bounds__(SH_THREADS) activate_fwd_kernel(ActArgs a, flo
     if (row0 >= a.N) return;
     const int nb = (a.deg + 1) * (a.deg + 1);
     float* tile = s_tile[warp];
-    warp_load_rows(a.dc, row0, a.N, 3, tile, 0, lane);
-    if (a.K > 1 && nb > 1) warp_load_rows(a.rest, row0, a.N, (a.K - 1) * 3, tile, 3, lane);
+    const bool do_col = a.parts & ACT_COLORS, do_geom = a.parts & ACT_GEOM;
+    if (do_col) {
+        warp_load_rows(a.dc, row0, a.N, 3, tile, 0, lane);
+        if (a.K > 1 && nb > 1) warp_load_rows(a.rest, row0, a.N, (a.K - 1) * 3, tile, 3, lane);
+    }
     __syncwarp();
     const int64_t n = row0 + lane;
     float mx = 0.f, my = 0.f, mz = 0.f;
-    if (n < a.N) {
-        mx = a.means[n * 3 + 0]; my = a.means[n * 3 + 1]; mz = a.means[n * 3 + 2];
+    if (n < a.N && do_col) { mx = a.means[n * 3 + 0]; my = a.means[n * 3 + 1]; mz = a.means[n * 3 + 2]; }
+    if (n < a.N && do_geom) {
         float valid = 1.f;
         if (a.inst_valid) valid = a.inst_valid[a.point_ids[n]] ? 1.f : 0.f;
         opac[n] = valid / (1.0f + expf(-a.opac_logit[n]));
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(SH_THREADS) activate_fwd_kernel(ActArgs a, flo
     // colours: one pass per camera over the staged coefficients (read from HBM once); each camera's
     // colours leave through a small second tile so the stores stay coalesced.
     __shared__ float s_rgb[SH_WARPS][32 * 3];
-    for (int c = 0; c < a.C; ++c) {
+    for (int c = 0; c < (do_col ? a.C : 0); ++c) {
         float col[3] = {0.f, 0.f, 0.f};
         if (n < a.N) {
             float x = mx - a.cam[c][0], y = my - a.cam[c][1], z = mz - a.cam[c][2];
@@ -209,6 +216,7 @@ __global__ void __launch_bounds__(SH_THREADS) activate_fwd_kernel(ActArgs a, flo
         }
     }
     __syncwarp();
+    if (!do_geom) return;
     if (n < a.N) {
         float* row = tile + lane * SH_STRIDE;
         row[3] = expf(a.log_scales[n * 3 + 0]); row[4] = expf(a.log_scales[n * 3 + 1]); row[5] = expf(a.log_scales[n * 3 + 2]);
@@ -229,7 +237,8 @@ __global__ void __launch_bounds__(SH_THREADS) activate_bwd_kernel(
     const int nb = (a.deg + 1) * (a.deg + 1);
     float* tile = s_tile[warp];
     const int64_t n = row0 + lane;
-    if (n < a.N) {
+    const bool do_col = a.parts & ACT_COLORS, do_geom = a.parts & ACT_GEOM;
+    if (n < a.N && do_col) {
         float* row = tile + lane * SH_STRIDE;
         for (int k = 0; k < a.K * 3; ++k) row[k] = 0.f;
         const float mx = a.means[n * 3 + 0], my = a.means[n * 3 + 1], mz = a.means[n * 3 + 2];
@@ -249,6 +258,8 @@ __global__ void __launch_bounds__(SH_THREADS) activate_bwd_kernel(
                 }
             }
         }
+    }
+    if (n < a.N && do_geom) {
         // sigmoid * mask
         float valid = 1.f;
         if (a.inst_valid) valid = a.inst_valid[a.point_ids[n]] ? 1.f : 0.f;
@@ -264,8 +275,11 @@ __global__ void __launch_bounds__(SH_THREADS) activate_bwd_kernel(
             make_float4((g.x - d * qn[0]) * qi, (g.y - d * qn[1]) * qi, (g.z - d * qn[2]) * qi, (g.w - d * qn[3]) * qi);
     }
     __syncwarp();
-    warp_store_rows(v_dc, row0, a.N, 3, tile, 0, lane);
-    if (a.K > 1) warp_store_rows(v_rest, row0, a.N, (a.K - 1) * 3, tile, 3, lane);
+    if (do_col) {
+        warp_store_rows(v_dc, row0, a.N, 3, tile, 0, lane);
+        if (a.K > 1) warp_store_rows(v_rest, row0, a.N, (a.K - 1) * 3, tile, 3, lane);
+    }
+    if (!do_geom) return;
     __syncwarp();
     if (n < a.N) {
         float* row = tile + lane * SH_STRIDE;
@@ -309,7 +323,7 @@ static int make_act_args(ActArgs& a, const float* means, const float* dc, const 
     EMD_CHECK_ARG(C >= 1 && C <= 8, "activate: 1..8 cameras per call (got %d)", C);
     for (int c = 0; c < C; ++c)
         for (int k = 0; k < 3; ++k) a.cam[c][k] = cam_pos_host[c * 3 + k];
-    a.C = C; a.N = N; a.K = K; a.deg = degree;
+    a.C = C; a.N = N; a.K = K; a.deg = degree; a.parts = ACT_COLORS | ACT_GEOM;
     return EMD_OK;
 }
 
@@ -322,6 +336,11 @@ extern "C" int emd_activate_fwd(const float* means, const float* dc, const float
     ActArgs a;
     int rc = make_act_args(a, means, dc, rest, opac_logit, log_scales, quats, point_ids, inst_valid, cam_pos_host, C, N, K, degree);
     if (rc != EMD_OK) return rc;
+    // a null output group selects the other part alone: rgbs == null -> geometry only; opac == null -> colours only
+    a.parts = (rgbs ? ACT_COLORS : 0) | (opac ? ACT_GEOM : 0);
+    EMD_CHECK_ARG(a.parts != 0, "activate_fwd: nothing to compute (rgbs and opac both null)");
+    EMD_CHECK_ARG(!(a.parts & ACT_COLORS) || clamp_pass, "activate_fwd: colours need clamp_pass");
+    EMD_CHECK_ARG(!(a.parts & ACT_GEOM) || (scales && quats_n), "activate_fwd: geometry needs opac, scales and quats_n");
     if (N == 0) return EMD_OK;
     EMD_LAUNCH(EK_ACT_FWD, stream, activate_fwd_kernel<<<(unsigned)emd_cdiv(N, SH_WARPS * 32), SH_THREADS, 0, stream>>>(a, rgbs, opac, scales, quats_n, clamp_pass));
     EMD_CHECK_LAUNCH("activate_fwd");
@@ -338,8 +357,14 @@ extern "C" int emd_activate_bwd(const float* means, const float* dc, const float
     ActArgs a;
     int rc = make_act_args(a, means, dc, rest, opac_logit, log_scales, quats, point_ids, inst_valid, cam_pos_host, C, N, K, degree);
     if (rc != EMD_OK) return rc;
+    // v_rgbs == null -> geometry only; v_opac == null -> colours only (same rule as the forward)
+    a.parts = (v_rgbs ? ACT_COLORS : 0) | (v_opac ? ACT_GEOM : 0);
+    EMD_CHECK_ARG(a.parts != 0, "activate_bwd: nothing to compute (v_rgbs and v_opac both null)");
+    EMD_CHECK_ARG(!(a.parts & ACT_COLORS) || (clamp_pass && v_dc), "activate_bwd: colours need clamp_pass and v_dc");
+    EMD_CHECK_ARG(!(a.parts & ACT_GEOM) || (scales && v_scales && v_quats_n && v_opac_logit && v_log_scales && v_quats),
+                  "activate_bwd: geometry needs scales, v_scales, v_quats_n and the three outputs");
     if (N == 0) return EMD_OK;
-    if (!emd_aligned(v_quats, 16) || !emd_aligned(v_quats_n, 16)) { emd_set_error("activate_bwd: quats grads must be 16-B aligned"); return EMD_ERR_ALIGN; }
+    if ((a.parts & ACT_GEOM) && (!emd_aligned(v_quats, 16) || !emd_aligned(v_quats_n, 16))) { emd_set_error("activate_bwd: quats grads must be 16-B aligned"); return EMD_ERR_ALIGN; }
     EMD_LAUNCH(EK_ACT_BWD, stream, activate_bwd_kernel<<<(unsigned)emd_cdiv(N, SH_WARPS * 32), SH_THREADS, 0, stream>>>(
         a, clamp_pass, scales, v_rgbs, v_opac, v_scales, v_quats_n, v_dc, v_rest, v_opac_logit, v_log_scales, v_quats));
     EMD_CHECK_LAUNCH("activate_bwd");

@@ -70,6 +70,104 @@ def allreduce_grads(params: Iterable[Tensor], average: bool = False, bucket_byte
     return total
 
 
+def _allreduce_group_async(tensors: List[Tensor]):
+    """One asynchronous all-reduce over several tensors: a single grouped NCCL launch (``ncclGroupStart/End``
+    around one ``ncclAllReduce`` per tensor -- no packing copies), gloo's coalesced all-reduce in the CPU tests."""
+    if len(tensors) == 1:
+        return dist.all_reduce(tensors[0], async_op=True)
+    from torch.distributed.distributed_c10d import _coalescing_manager
+    with _coalescing_manager(async_ops=True) as cm:
+        for t in tensors:
+            dist.all_reduce(t)
+    return cm
+
+
+class GradReducer:
+    """Gradient all-reduce that starts while the backward pass is still running.
+
+    ``early`` is a list of GROUPS of parameters that take part in EVERY step on EVERY rank (background SH
+    coefficients first of all: 180 of the 252 B/Gaussian the exchange moves).  Every member gets a post-accumulate
+    hook; the moment autograd has written the ``.grad`` of a group's last member, ONE grouped asynchronous
+    all-reduce of the group is issued on the collective's own stream, and the rest of the backward pass
+    (projection, EMD deformation) runs under it.
+    ``finish()`` -- called once after ``backward()`` -- reduces everything else in one more grouped launch
+    (a parameter that got no gradient on this rank, e.g. SMPL nodes of a frame without visible pedestrians,
+    contributes zeros so every rank issues the same sequence) and waits for all of it.
+
+    The early sequence is the order in which autograd completes the groups, which is the same on every rank as
+    long as the early parameters are used by every rank's step; that is the contract of ``early``."""
+
+    def __init__(self, params: Sequence[Tensor], early: Optional[Sequence[Sequence[Tensor]]] = None,
+                 average: bool = False):
+        self.params = list(params)
+        self.average = average
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.groups: List[List[Tensor]] = [list(g) for g in (early or []) if len(g)]
+        self._group_of = {id(p): gi for gi, g in enumerate(self.groups) for p in g}
+        self._pending = [len(g) for g in self.groups]
+        self._seen = set()
+        self._group_launched = [False] * len(self.groups)
+        self._works: List = []
+        self._handles = []
+        self.bytes = 0
+        self.early_bytes = 0
+        if self.active:
+            for g in self.groups:
+                for p in g:
+                    self._handles.append(p.register_post_accumulate_grad_hook(self._hook))
+
+    def _launch(self, tensors: List[Tensor]) -> int:
+        self._works.append(_allreduce_group_async(tensors))
+        n = sum(t.numel() * t.element_size() for t in tensors)
+        self.bytes += n
+        return n
+
+    def _hook(self, p: Tensor) -> None:
+        if p.grad is None or id(p) in self._seen:
+            return
+        self._seen.add(id(p))
+        gi = self._group_of[id(p)]
+        self._pending[gi] -= 1
+        if self._pending[gi] == 0 and not self._group_launched[gi]:
+            self._group_launched[gi] = True
+            self.early_bytes += self._launch([q.grad for q in self.groups[gi]])
+
+    def finish(self) -> int:
+        """Reduce what the hooks did not, wait for everything; returns the bytes reduced this step (per rank)."""
+        if not self.active:
+            return 0
+        world = dist.get_world_size()
+
+        def grad_of(p):
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            return p.grad
+
+        for gi, g in enumerate(self.groups):   # an early group whose hooks did not all fire (unused this step)
+            if not self._group_launched[gi]:
+                self._group_launched[gi] = True
+                self._launch([grad_of(q) for q in g])
+        rest = [grad_of(p) for p in self.params if p.requires_grad and id(p) not in self._group_of]
+        if rest:
+            self._launch(rest)
+        for w in self._works:
+            w.wait()
+        if self.average:
+            for p in self.params:
+                if p.grad is not None:
+                    p.grad.div_(world)
+        total = self.bytes
+        self._works, self._seen, self.bytes, self.early_bytes = [], set(), 0, 0
+        self._pending = [len(g) for g in self.groups]
+        self._group_launched = [False] * len(self.groups)
+        return total
+
+    def close(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
 def allreduce_densify_stats(grad_norm_sum: Tensor, vis_count: Tensor, max_radii: Optional[Tensor] = None) -> None:
     """Densification statistics are not gradients but must agree across replicas or they diverge at the next
     refinement (vanilla.py:171-191): sums for the accumulated |grad| and visibility counts, max for radii."""

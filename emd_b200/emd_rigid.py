@@ -12,7 +12,7 @@ import torch
 from torch import Tensor
 
 from . import _C
-from .sh_ops import activate_gaussians
+from .sh_ops import activate_gaussians, activate_geometry, sh_colors
 
 HEAD_NAMES = ("rot_c_w", "rot_c_b", "rot_f_w", "rot_f_b", "trans_c_w", "trans_c_b", "trans_f_w", "trans_f_b")
 
@@ -199,3 +199,16 @@ class RigidNodesEMD:
             wm, p["_features_dc"], p["_features_rest"], p["_opacities"], p["_scales"], wq, cam_pos, n,
             point_ids=p["point_ids"].reshape(-1), inst_valid=p["instances_fv"][frame])
         return dict(_means=wm, _opacities=opac[:, None], _rgbs=rgbs, _scales=scales, _quats=quats)
+
+    # The same result in two calls, so a caller can place the colour node after the projection in the autograd
+    # graph (its backward -- the largest gradient -- then runs first; see sh_ops.sh_colors).
+    def get_geometry(self, frame: int, step: int) -> Dict[str, Tensor]:
+        p = self.p
+        wm, wq = self.transform_means_and_quats(frame, step)
+        opac, scales, quats = activate_geometry(p["_opacities"], p["_scales"], wq, point_ids=p["point_ids"].reshape(-1),
+                                                inst_valid=p["instances_fv"][frame])
+        return dict(_means=wm, _opacities=opac[:, None], _scales=scales, _quats=quats)
+
+    def get_colors(self, means_world: Tensor, cam_pos, step: int) -> Tensor:
+        n = min(step // self.sh_degree_interval, self.sh_degree)
+        return sh_colors(means_world, self.p["_features_dc"], self.p["_features_rest"], cam_pos, n)

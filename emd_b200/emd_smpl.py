@@ -18,7 +18,7 @@ from torch import Tensor
 
 from . import _C
 from .emd_rigid import _interpolate_quats, int_lininterp
-from .sh_ops import activate_gaussians
+from .sh_ops import activate_gaussians, activate_geometry, sh_colors
 
 SMPL_PARENTS = (-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21)
 HEAD_NAMES = ("smpl_c_w", "smpl_c_b", "smpl_f_w", "smpl_f_b")
@@ -146,7 +146,7 @@ class SMPLNodesEMD:
 
     def get_gaussians(self, cam_pos, frame: int, step: int):
         p = self.p
-        if not bool(p["instances_fv"][frame].any()):  # smpl.py:539-541
+        if not self._any_visible(frame):  # smpl.py:539-541
             return None
         wm, wq = self.transform_means_and_quats(frame, step)
         n = min(step // self.sh_degree_interval, self.sh_degree)
@@ -154,3 +154,26 @@ class SMPLNodesEMD:
             wm, p["_features_dc"], p["_features_rest"], p["_opacities"], p["_scales"], wq, cam_pos, n,
             point_ids=p["point_ids"].reshape(-1), inst_valid=p["instances_fv"][frame])
         return dict(_means=wm, _opacities=opac[:, None], _rgbs=rgbs, _scales=scales, _quats=quats)
+
+    def _any_visible(self, frame: int) -> bool:
+        """``instances_fv[frame].any()`` (smpl.py:539) answered from a host copy of the (non-trainable) visibility
+        table: the reference pays a device->host sync for it every step."""
+        fv = self.p["instances_fv"]
+        key = (fv.data_ptr(), fv._version, tuple(fv.shape))
+        if getattr(self, "_fv_key", None) != key:
+            self._fv_key, self._fv_any = key, fv.any(dim=1).cpu().tolist()
+        return bool(self._fv_any[frame])
+
+    # two-call form of get_gaussians (see RigidNodesEMD.get_geometry)
+    def get_geometry(self, frame: int, step: int):
+        p = self.p
+        if not self._any_visible(frame):
+            return None
+        wm, wq = self.transform_means_and_quats(frame, step)
+        opac, scales, quats = activate_geometry(p["_opacities"], p["_scales"], wq, point_ids=p["point_ids"].reshape(-1),
+                                                inst_valid=p["instances_fv"][frame])
+        return dict(_means=wm, _opacities=opac[:, None], _scales=scales, _quats=quats)
+
+    def get_colors(self, means_world: Tensor, cam_pos, step: int) -> Tensor:
+        n = min(step // self.sh_degree_interval, self.sh_degree)
+        return sh_colors(means_world, self.p["_features_dc"], self.p["_features_rest"], cam_pos, n)

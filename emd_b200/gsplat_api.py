@@ -33,7 +33,7 @@ def rasterization(
     quats: Tensor,  # [N,4]
     scales: Tensor,  # [N,3]
     opacities: Tensor,  # [N]
-    colors: Tensor,  # [(C,)N,D] or [(C,)N,K,3]
+    colors: Tensor,  # [(C,)N,D] or [(C,)N,K,3] (or a callable returning it, evaluated after the projection)
     viewmats: Tensor,  # [C,4,4]
     Ks: Tensor,  # [C,3,3]
     width: int,
@@ -87,6 +87,24 @@ def rasterization(
     if comps is not None:
         opac = opacities[None, :] * comps  # [C,N]
 
+    with_depth = render_mode in ("RGB+D", "RGB+ED", "D", "ED")
+    ed_mode = render_mode in ("RGB+ED", "ED")
+    tw, th, _ = R.tile_grid(width, height)
+    deferred = {}
+    if callable(colors):
+        # extension over gsplat: a zero-argument callable is evaluated AFTER the projection -- while the host waits
+        # for the intersection count -- so (a) the GPU is not idle during that readback and (b) the colour node sits
+        # after the projection node in the autograd graph: its backward (the SH-coefficient gradient, 75 % of the
+        # bytes a data-parallel all-reduce moves) runs before the projection's
+        colors_fn = colors
+
+        def _eval_colors():
+            deferred["colors"] = colors_fn()
+    tpg, isect_ids, flatten_ids, cum_tiles = R.isect_tiles(means2d.detach(), radii, depths.detach(), tpg, width, height,
+                                                           between=_eval_colors if callable(colors) else None)
+    if callable(colors):
+        colors = deferred["colors"]
+    isect_offsets = R.isect_offset_encode(isect_ids, C, width, height)
     if sh_degree is not None:
         # colors are SH coefficients [(C,)N,K,3]; directions from the camera centres
         camtoworlds = torch.linalg.inv(viewmats)
@@ -95,8 +113,6 @@ def rasterization(
         cols = spherical_harmonics(sh_degree, dirs.reshape(-1, 3), coeffs.reshape(C * N, -1, 3)).reshape(C, N, 3)
         colors = torch.clamp_min(cols + 0.5, 0.0)
 
-    with_depth = render_mode in ("RGB+D", "RGB+ED", "D", "ED")
-    ed_mode = render_mode in ("RGB+ED", "ED")
     ras_colors = None if render_mode in ("D", "ED") else colors
     d_color = 0 if ras_colors is None else ras_colors.shape[-1]
     if d_color + (1 if with_depth else 0) > 4:
@@ -106,9 +122,6 @@ def rasterization(
         bg = torch.cat([bg, torch.zeros(C, 1, device=bg.device, dtype=bg.dtype)], dim=-1) if ras_colors is not None \
             else torch.zeros(C, 1, device=bg.device, dtype=bg.dtype)
 
-    tw, th, _ = R.tile_grid(width, height)
-    tpg, isect_ids, flatten_ids, cum_tiles = R.isect_tiles(means2d.detach(), radii, depths.detach(), tpg, width, height)
-    isect_offsets = R.isect_offset_encode(isect_ids, C, width, height)
     render_colors, render_alphas, last_ids = R.rasterize_to_pixels(
         means2d, conics, ras_colors, opac, depths, bg, radii, cum_tiles, isect_offsets, flatten_ids, width, height,
         with_depth=with_depth, ed_mode=ed_mode, absgrad=absgrad)

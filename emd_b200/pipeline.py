@@ -16,7 +16,7 @@ from . import scenes
 from .emd_rigid import RigidNodesEMD
 from .emd_smpl import SMPLNodesEMD
 from .gsplat_api import rasterization
-from .sh_ops import activate_gaussians
+from .sh_ops import activate_gaussians, activate_geometry, sh_colors
 
 
 class StreetScene:
@@ -86,19 +86,53 @@ class StreetScene:
         return dict(_means=cat("_means", 0), _scales=cat("_scales", 0), _quats=cat("_quats", 0),
                     _opacities=cat("_opacities", 0), _rgbs=cat("_rgbs", 1 if multi else 0))
 
+    def collect_geometry(self, frame: int, step: int):
+        """Geometry half of ``collect_gaussians`` -> (concatenated dict without ``_rgbs``, per-class colour thunks).
+        The colours are evaluated later (``collect_colors``), after the projection, so that in the backward pass the
+        SH-coefficient gradient is complete -- and its all-reduce in flight -- before the projection / EMD backward."""
+        b = self.bg
+        opac, sc, qn = activate_geometry(b["opacities"], b["scales"], b["quats"])
+        parts = [dict(_means=b["means"], _opacities=opac[:, None], _scales=sc, _quats=qn)]
+        n = min(step // 1000, 3)
+        thunks = [lambda cams: sh_colors(b["means"], b["features_dc"], b["features_rest"], cams, n)]
+        for node in (self.rigid, self.smpl):
+            if node is None:
+                continue
+            gs = node.get_geometry(frame, step)
+            if gs is not None:
+                parts.append(gs)
+                thunks.append(lambda cams, node=node, wm=gs["_means"]: node.get_colors(wm, cams, step))
+        cat = lambda k: torch.cat([p[k] for p in parts], dim=0)  # noqa: E731
+        return dict(_means=cat("_means"), _scales=cat("_scales"), _quats=cat("_quats"),
+                    _opacities=cat("_opacities")), thunks
+
+    @staticmethod
+    def collect_colors(thunks, cam_centers) -> Tensor:
+        multi = isinstance(cam_centers[0], (list, tuple))
+        return torch.cat([f(cam_centers) for f in thunks], dim=1 if multi else 0)
+
     def render(self, camtoworlds: Tensor, Ks: Tensor, width: int, height: int, frame: int, step: int,
                viewmats: Optional[Tensor] = None, cam_centers=None, near_plane: float = 0.1, far_plane: float = 1e10,
-               absgrad: bool = True):
+               absgrad: bool = True, colors_after_projection: bool = True):
         """-> (rgb[C,H,W,3] clamped at 1, depth[C,H,W,1], opacity[C,H,W,1], info) as ``render_gaussians``
-        (base.py:385-432) returns them, for all C cameras of the timestep."""
+        (base.py:385-432) returns them, for all C cameras of the timestep.
+
+        ``colors_after_projection`` only changes the ORDER of two independent stages (SH colours after the projection
+        and tile binning instead of before): results are identical; the backward pass then produces the
+        SH-coefficient gradient first (see ``dist.GradReducer``)."""
         if cam_centers is None:
             cam_centers = camtoworlds[:, :3, 3].detach().cpu().tolist()
         if viewmats is None:
             viewmats = torch.linalg.inv(camtoworlds)
-        gs = self.collect_gaussians(cam_centers, frame, step)
+        if colors_after_projection:
+            gs, thunks = self.collect_geometry(frame, step)
+            colors = lambda: self.collect_colors(thunks, cam_centers)  # noqa: E731
+        else:
+            gs = self.collect_gaussians(cam_centers, frame, step)
+            colors = gs["_rgbs"]
         renders, alphas, info = rasterization(
             means=gs["_means"], quats=gs["_quats"], scales=gs["_scales"], opacities=gs["_opacities"].squeeze(-1),
-            colors=gs["_rgbs"], viewmats=viewmats, Ks=Ks, width=width, height=height, packed=False, absgrad=absgrad,
+            colors=colors, viewmats=viewmats, Ks=Ks, width=width, height=height, packed=False, absgrad=absgrad,
             sparse_grad=False, rasterize_mode="classic", near_plane=near_plane, far_plane=far_plane,
             render_mode="RGB+ED", radius_clip=0.0)
         rgb, depth = torch.split(renders, [3, 1], dim=-1)

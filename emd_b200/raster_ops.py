@@ -112,9 +112,11 @@ def fully_fused_projection(means, quats, scales, viewmats, Ks, width, height, ep
 
 
 @torch.no_grad()
-def cumsum_tiles(tiles_per_gauss: Tensor) -> Tuple[Tensor, int]:
+def cumsum_tiles(tiles_per_gauss: Tensor, between=None) -> Tuple[Tensor, int]:
     """Inclusive int64 cumulative sum + the total (one pinned-memory readback: the
-    only host sync of the pipeline, as in gsplat)."""
+    only host sync of the pipeline, as in gsplat).  ``between`` (optional callable) runs after the
+    readback has been issued and before the host waits for it: work it launches keeps the GPU busy
+    while the count travels, so the stages that need the count start without a bubble."""
     L = _C.lib()
     flat = tiles_per_gauss.reshape(-1)
     n = flat.numel()
@@ -127,7 +129,14 @@ def cumsum_tiles(tiles_per_gauss: Tensor) -> Tuple[Tensor, int]:
                                   _C.stream()), "emd_cumsum_i32_i64")
     host = _pinned_i64(dev)
     host.copy_(total, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
+    if between is None:
+        torch.cuda.current_stream().synchronize()
+    else:
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.enable_grad():
+            between()
+        ev.synchronize()
     return cum, int(host.item())
 
 
@@ -153,12 +162,13 @@ def radix_sort_pairs(keys: Tensor, vals: Tensor, begin_bit: int, end_bit: int) -
 
 @torch.no_grad()
 def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, width: int, height: int,
-                sort: bool = True):
-    """-> tiles_per_gauss, isect_ids[P] i64 (sorted), flatten_ids[P] i32 (sorted), cum_tiles[C*N] i64."""
+                sort: bool = True, between=None):
+    """-> tiles_per_gauss, isect_ids[P] i64 (sorted), flatten_ids[P] i32 (sorted), cum_tiles[C*N] i64.
+    ``between``: see ``cumsum_tiles``."""
     L = _C.lib()
     C, N = radii.shape
     tw, th, bits = tile_grid(width, height)
-    cum, P = cumsum_tiles(tiles_per_gauss)
+    cum, P = cumsum_tiles(tiles_per_gauss, between)
     dev = radii.device
     isect_ids = torch.empty(P, dtype=torch.int64, device=dev)
     flatten_ids = torch.empty(P, dtype=torch.int32, device=dev)

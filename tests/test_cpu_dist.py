@@ -34,6 +34,31 @@ def _worker(rank, world, port, ret):
         D.allreduce_densify_stats(a, b, c)
         assert torch.equal(a, torch.full((4,), 3.0)) and torch.equal(b, torch.full((4,), 4.0))
         assert torch.equal(c, torch.tensor([2.0, 5.0]))
+        # GradReducer: hook-driven early all-reduce during backward + the rest at finish(); a parameter that gets no
+        # gradient on ONE rank only (rank 1 skips `skip`) must not desynchronise the sequence
+        gr = torch.Generator().manual_seed(7)
+        big = torch.randn(400000, 3, generator=gr).requires_grad_(True)      # early
+        mid = torch.randn(300000, 1, generator=gr).requires_grad_(True)      # >= 1 MB, reduced at finish
+        tiny = torch.randn(6, 6, generator=gr).requires_grad_(True)          # flat bucket
+        skip = torch.randn(9, generator=gr).requires_grad_(True)             # no grad on rank 1
+        ps = [big, mid, tiny, skip]
+        red = D.GradReducer(ps, early=[[big], [mid, tiny]])
+        for it in range(2):
+            for q in ps:
+                q.grad = None
+            loss = (big * (rank + 1.0)).sum() + (mid * mid).sum() * (rank + 2.0) + (tiny.sum() * (it + 1.0))
+            if rank == 0:
+                loss = loss + (skip * 3.0).sum()
+            loss.backward()
+            if it == 0:
+                assert red.early_bytes == (big.numel() + mid.numel() + tiny.numel()) * 4, "early groups were not reduced from their hooks"
+            n = red.finish()
+            assert n == sum(q.numel() * 4 for q in ps)
+            assert torch.equal(big.grad, torch.full_like(big, 3.0))
+            assert torch.allclose(mid.grad, 2 * mid.detach() * 5.0)
+            assert torch.equal(tiny.grad, torch.full_like(tiny, 2.0 * (it + 1)))
+            assert torch.equal(skip.grad, torch.full_like(skip, 3.0))
+        red.close()
         views = D.shard_views(11, rank, world)
         gathered = [None] * world
         dist.all_gather_object(gathered, views)

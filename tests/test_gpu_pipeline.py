@@ -63,3 +63,52 @@ def test_street_scene_step():
             continue
         e, l2 = rel_err(gg, gr), rel_l2(gg, gr)
         assert e <= 2e-3 and l2 <= 1e-3, f"grad {k}: max-rel {e}, l2-rel {l2}"
+
+
+def test_two_call_activation_is_the_fused_one():
+    """``activate_geometry`` + ``sh_colors`` (two autograd nodes, colour backward first) == ``activate_gaussians``
+    bit for bit, forward and backward; and the step with the colours evaluated after the projection == the step in
+    the reference's order (``colors_after_projection=False``), bit for bit."""
+    from emd_b200 import pipeline as P, scenes
+    from emd_b200.sh_ops import activate_gaussians, activate_geometry, sh_colors
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(5)
+    N = 5003
+    mk = lambda *s: torch.randn(*s, generator=g).to(dev)  # noqa: E731
+    means = mk(N, 3) * 10
+    leaves_a = [mk(N, 3).requires_grad_(), (0.1 * mk(N, 15, 3)).requires_grad_(), mk(N, 1).requires_grad_(),
+                (0.3 * mk(N, 3)).requires_grad_(), mk(N, 4).requires_grad_()]
+    leaves_b = [t.detach().clone().requires_grad_() for t in leaves_a]
+    cams = [[0.0, 0.0, 1.5], [3.0, -2.0, 1.0], [-4.0, 1.0, 2.0]]
+    ids = torch.randint(0, 7, (N,), generator=g).to(dev)
+    valid = (torch.rand(7, generator=g) > 0.3).to(dev)
+    cot = [mk(3, N, 3), mk(N), mk(N, 3), mk(N, 4)]
+    for deg in (0, 2, 3):
+        for a in leaves_a + leaves_b:
+            a.grad = None
+        dc, rest, op, sc, q = leaves_a
+        rgbs, opac, scl, qn = activate_gaussians(means, dc, rest, op, sc, q, cams, deg, point_ids=ids, inst_valid=valid)
+        sum((o * c).sum() for o, c in zip((rgbs, opac, scl, qn), cot)).backward()
+        dc2, rest2, op2, sc2, q2 = leaves_b
+        opac2, scl2, qn2 = activate_geometry(op2, sc2, q2, point_ids=ids, inst_valid=valid)
+        rgbs2 = sh_colors(means, dc2, rest2, cams, deg)
+        for x, y in ((rgbs, rgbs2), (opac, opac2), (scl, scl2), (qn, qn2)):
+            assert torch.equal(x, y)
+        sum((o * c).sum() for o, c in zip((rgbs2, opac2, scl2, qn2), cot)).backward()
+        for a, b in zip(leaves_a, leaves_b):
+            assert torch.equal(a.grad, b.grad)
+
+    W, H = 192, 128
+    bg, rigid, smpl = P.make_street_scene(n_bg=6000, rigid_instances=3, pts_per_rigid=400, smpl_instances=2,
+                                          smpl_V=500, seed=3, num_frames=20)
+    viewmats, Ks, c2w = scenes.cameras((0.0, 35.0), W, H)
+    outs = []
+    for after in (False, True):
+        scene = P.StreetScene(bg, rigid, smpl, dev)
+        rgb, depth, alpha, info = scene.render(c2w.to(dev), Ks.to(dev), W, H, 7, 2500, colors_after_projection=after)
+        (rgb.sum() + 0.1 * depth.sum() + alpha.sum()).backward()
+        outs.append((rgb, depth, alpha, [p.grad for p in scene.parameters()]))
+    for x, y in zip(outs[0][:3], outs[1][:3]):
+        assert torch.equal(x, y)
+    for x, y in zip(outs[0][3], outs[1][3]):
+        assert (x is None and y is None) or torch.equal(x, y)
