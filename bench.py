@@ -144,14 +144,13 @@ def run_ours(args):
     (bg, rigid, smpl), host = build_inputs(args, rank, world)
     scene = P.StreetScene(bg, rigid, smpl, dev)
     params = scene.parameters()
-    # gradient exchange: the big per-Gaussian tensors of the classes present in every step go out from autograd
-    # hooks while the backward pass is still running; the rest (SMPL: absent on frames without pedestrians, and the
-    # small EMD tensors) at the end of the step
-    bgp = scene.bg
-    early = [[bgp["features_rest"]], [bgp["features_dc"]], [bgp["means"], bgp["quats"], bgp["scales"], bgp["opacities"]]]
-    if scene.rigid is not None:
-        early[1] += [scene.rigid.p["_features_dc"], scene.rigid.p["_features_rest"]]
-    reducer = D.GradReducer(params, early=early)
+    # gradient exchange: the background SH coefficients (2/3 of the bytes) go out from an autograd hook while the
+    # backward pass is still running; everything else in one grouped launch at the end of the step
+    groups = {"rest": [[scene.bg["features_rest"]]],
+              "rest+dc": [[scene.bg["features_rest"]], [scene.bg["features_dc"]]]}
+    early = groups[os.environ.get("EMD_BENCH_EARLY", "rest")]
+    ar_mode = os.environ.get("EMD_BENCH_ALLREDUCE", "hooks")   # experiments only: "finish" = no overlap, "none" = skip
+    reducer = D.GradReducer(params, early=early if ar_mode == "hooks" else None)
     C = len(YAWS)
     cam_centers = host["c2w"][:, :3, 3].tolist()
     n_frames = 150
@@ -200,7 +199,7 @@ def run_ours(args):
                 prefetch(i + 1)   # intersection-count readback on the copy engines) and hidden under the backward
         loss = (rgb * v_rgb).sum() + (depth * v_d).sum() + (alpha * v_a).sum()
         loss.backward()
-        if world > 1:
+        if world > 1 and ar_mode != "none":
             stats["allreduce_early_bytes"] = reducer.early_bytes
             stats["allreduce_bytes"] = reducer.finish()
         if e2e:  # device -> host read of the step's result

@@ -98,9 +98,10 @@ class GradReducer:
     long as the early parameters are used by every rank's step; that is the contract of ``early``."""
 
     def __init__(self, params: Sequence[Tensor], early: Optional[Sequence[Sequence[Tensor]]] = None,
-                 average: bool = False):
+                 average: bool = False, pack_below: int = 4 << 20):
         self.params = list(params)
         self.average = average
+        self.pack_below = pack_below
         self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.groups: List[List[Tensor]] = [list(g) for g in (early or []) if len(g)]
         self._group_of = {id(p): gi for gi, g in enumerate(self.groups) for p in g}
@@ -147,11 +148,21 @@ class GradReducer:
             if not self._group_launched[gi]:
                 self._group_launched[gi] = True
                 self._launch([grad_of(q) for q in g])
+        # everything else: ONE grouped launch; tensors below `pack_below` bytes travel inside one flat buffer (a
+        # collective per 100-byte tensor costs a full cross-GPU latency each: 31 tensors ~ 0.5 ms at 8 GPUs)
         rest = [grad_of(p) for p in self.params if p.requires_grad and id(p) not in self._group_of]
-        if rest:
-            self._launch(rest)
+        big = [g for g in rest if g.numel() * g.element_size() >= self.pack_below]
+        small = [g for g in rest if g.numel() * g.element_size() < self.pack_below]
+        flat = None
+        if small:
+            flat = torch.cat([g.reshape(-1) for g in small])
+            big.append(flat)
+        if big:
+            self._launch(big)
         for w in self._works:
             w.wait()
+        if flat is not None:
+            torch._foreach_copy_(small, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in small]), small)])
         if self.average:
             for p in self.params:
                 if p.grad is not None:
