@@ -46,6 +46,11 @@ _SIGS = {
     "emd_linear_bwd_tc": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),
     "emd_temb_fwd": (c_int, [P, c_int, c_int, P, c_int, P, P]),
     "emd_temb_bwd": (c_int, [P, c_int, c_int, P, c_int, P, P, P, P]),
+    "emd_hexplane_fwd": (c_int, [P, ctypes.POINTER(c_int64), ctypes.POINTER(c_int), c_int, c_int, ctypes.POINTER(c_float),
+                                 P, P, c_int, c_int64, P, P]),
+    "emd_hexplane_bwd_workspace_bytes": (c_size_t, [c_int64]),
+    "emd_hexplane_bwd": (c_int, [P, ctypes.POINTER(c_int64), ctypes.POINTER(c_int), c_int, c_int, ctypes.POINTER(c_float),
+                                 P, P, c_int, c_int64, P, P, P, P, P, c_size_t, P]),
     "emd_tile_order": (c_int, [P, c_int64, c_int64, P, P, P, P]),
     "emd_raster_segment_size": (c_int, []),
     "emd_raster_checkpoint_floats": (c_int, []),

@@ -80,7 +80,7 @@ def build_hostmath(force: bool = False) -> Path:
     CPU test-suite can check the product's canonical op order against the oracle
     without a GPU.  Not used by the product path."""
     src = PKG / "csrc" / "hostmath.cpp"
-    deps = [src, CSRC / "proj_math.cuh"]
+    deps = [src] + list(CSRC.glob("*.cuh"))
     if not force and not _stale(HOSTLIB, deps):
         return HOSTLIB
     cmd = ["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC", "-shared", "-x", "c++",

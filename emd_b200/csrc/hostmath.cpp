@@ -136,3 +136,72 @@ extern "C" void emd_host_dg_preprocess_fwd(const float* means, const float* scal
         rects[n * 4] = vis ? o.x0 : 0; rects[n * 4 + 1] = vis ? o.y0 : 0; rects[n * 4 + 2] = vis ? o.x1 : 0; rects[n * 4 + 3] = vis ? o.y1 : 0;
     }
 }
+
+// ---- HexPlane (hexplane_math.cuh): scalar host loop over the same tap arithmetic the kernels use ------------
+#include "hexplane_math.cuh"
+
+struct HostHexGeom {
+    const float* planes;
+    const int64_t* off;
+    const int* reso;
+    float a0[3], k[3];
+};
+
+static void host_hex_eval(const HostHexGeom& G, int s, const float u[4], int ch, float val[HEX_PLANES], float dvx[HEX_PLANES],
+                          float dvy[HEX_PLANES], HexAxis ax[4]) {
+    for (int c = 0; c < 4; ++c) ax[c] = hex_axis(u[c], G.reso[s * 4 + c]);
+    for (int p = 0; p < HEX_PLANES; ++p) {
+        const HexAxis X = ax[HEX_AX(p)], Y = ax[HEX_AY(p)];
+        const int W = G.reso[s * 4 + HEX_AX(p)];
+        const float* base = G.planes + G.off[s * HEX_PLANES + p] + ch;
+        const float nw = base[((int64_t)Y.i0 * W + X.i0) * HEX_F], ne = base[((int64_t)Y.i0 * W + X.i1) * HEX_F];
+        const float sw = base[((int64_t)Y.i1 * W + X.i0) * HEX_F], se = base[((int64_t)Y.i1 * W + X.i1) * HEX_F];
+        const float top = nw + X.w1 * (ne - nw), bot = sw + X.w1 * (se - sw);
+        val[p] = top + Y.w1 * (bot - top);
+        dvx[p] = (ne - nw) + Y.w1 * ((se - sw) - (ne - nw));
+        dvy[p] = bot - top;
+    }
+}
+
+extern "C" void emd_host_hexplane(const float* planes, const int64_t* plane_offsets, const int* reso, int S,
+                                  const float* aabb, const float* pts, const float* t, int t_stride, int64_t N,
+                                  float* feat, const float* v_feat, float* v_planes, float* v_pts, float* v_t) {
+    HostHexGeom G;
+    G.planes = planes; G.off = plane_offsets; G.reso = reso;
+    for (int a = 0; a < 3; ++a) { G.a0[a] = aabb[a]; G.k[a] = 2.0f / (aabb[3 + a] - aabb[a]); }
+    for (int64_t n = 0; n < N; ++n) {
+        float u[4];
+        for (int a = 0; a < 3; ++a) u[a] = hex_normalize(pts[n * 3 + a], G.a0[a], G.k[a]);
+        u[3] = t[n * t_stride];
+        float g[4] = {0, 0, 0, 0};
+        for (int s = 0; s < S; ++s) {
+            for (int ch = 0; ch < HEX_F; ++ch) {
+                float val[HEX_PLANES], dvx[HEX_PLANES], dvy[HEX_PLANES], ex[HEX_PLANES];
+                HexAxis ax[4];
+                host_hex_eval(G, s, u, ch, val, dvx, dvy, ax);
+                float prod = 1.0f;
+                for (int p = 0; p < HEX_PLANES; ++p) prod *= val[p];
+                feat[n * (int64_t)(S * HEX_F) + s * HEX_F + ch] = prod;
+                if (!v_feat) continue;
+                const float go = v_feat[n * (int64_t)(S * HEX_F) + s * HEX_F + ch];
+                hex_excl_products(val, ex);
+                for (int p = 0; p < HEX_PLANES; ++p) {
+                    const float e = go * ex[p];
+                    const HexAxis X = ax[HEX_AX(p)], Y = ax[HEX_AY(p)];
+                    const int W = reso[s * 4 + HEX_AX(p)];
+                    float* gb = v_planes + plane_offsets[s * HEX_PLANES + p] + ch;
+                    gb[((int64_t)Y.i0 * W + X.i0) * HEX_F] += e * ((1.f - X.w1) * (1.f - Y.w1));
+                    gb[((int64_t)Y.i0 * W + X.i1) * HEX_F] += e * (X.w1 * (1.f - Y.w1));
+                    gb[((int64_t)Y.i1 * W + X.i0) * HEX_F] += e * ((1.f - X.w1) * Y.w1);
+                    gb[((int64_t)Y.i1 * W + X.i1) * HEX_F] += e * (X.w1 * Y.w1);
+                    g[HEX_AX(p)] += X.dmul * (e * dvx[p]);
+                    g[HEX_AY(p)] += Y.dmul * (e * dvy[p]);
+                }
+            }
+        }
+        if (v_feat) {
+            for (int a = 0; a < 3; ++a) v_pts[n * 3 + a] = g[a] * G.k[a];
+            if (t_stride) v_t[n] = g[3]; else v_t[0] += g[3];
+        }
+    }
+}

@@ -3,9 +3,10 @@
 (``--no_ds --no_dr --no_fine_hexplane_features``; ``feat_head``, ``defor_depth 1``, ``net_width 64``).
 
 Weights keep their ``state_dict`` names (below ``deformation_net.``), so a checkpoint of the reference
-loads by key.  The HexPlane features of the coarse pass are passed in (``hex_feat[N,128]``, produced by the
-reference's own ``HexPlaneField`` in PyTorch -- SURVEY.md 8f-1); everything after them runs in the
-C-ABI kernels: temporal embedding, the 22 Linear layers with their ReLUs, residual application.
+loads by key.  The HexPlane features of the coarse pass come from ``emd_b200.hexplane.HexPlaneField`` (K1e, one
+gather kernel over all 24 planes; pass it as ``hexplane=``) or are passed in precomputed (``hex_feat[N,128]``);
+everything after them runs in the C-ABI kernels too: temporal embedding, the 22 Linear layers with their
+ReLUs, residual application.
 
 The temporal embedding is the same for every Gaussian, so its columns of the first layers are folded into
 the bias (``b' = b + W[:, temb] @ temb``): the per-Gaussian GEMM input shrinks from 164 to 132 (coarse) and
@@ -24,8 +25,9 @@ from .mlp_ops import linear, temporal_embed
 
 class S3GDeformation:
     def __init__(self, weights: Dict[str, Tensor], min_embeddings: int = 30, max_embeddings: int = 150,
-                 c2f_temporal_iter: int = 25000, temporal_dim: int = 32, hex_dim: int = 128):
+                 c2f_temporal_iter: int = 25000, temporal_dim: int = 32, hex_dim: int = 128, hexplane=None):
         self.w = weights
+        self.grid = hexplane          # ``Deformation.grid`` (deformation.py:41)
         self.min_embeddings, self.max_embeddings, self.c2f = min_embeddings, max_embeddings, c2f_temporal_iter
         self.td, self.hd = temporal_dim, hex_dim
 
@@ -46,12 +48,17 @@ class S3GDeformation:
                     dshs=self._head("shs_deform" + sfx, hidden).reshape(N, 16, 3), feat=self._dino(hidden))
 
     def forward(self, point: Tensor, scales: Tensor, rotations: Tensor, opacity: Tensor, shs: Tensor, time,
-                embeddings: Tensor, iteration: int, cam_no: int, hex_feat: Tensor):
+                embeddings: Tensor, iteration: int, cam_no: int, hex_feat: Optional[Tensor] = None):
         """-> (means3D, scales, rotations, opacity, shs, ddict) as ``deform_network.forward`` returns them.
-        ``time`` is the normalised timestamp (python float or 0-d tensor)."""
+        ``time`` is the normalised timestamp (python float or 0-d tensor).  ``hex_feat=None`` queries ``self.grid``
+        at ``(point, time + time_offset[cam_no])`` as ``query_hexplane`` does (deformation.py:187-199)."""
         w, td, hd = self.w, self.td, self.hd
         N = point.shape[0]
         t = torch.as_tensor(time, dtype=torch.float32, device=point.device) + w["time_offset"][cam_no, 0]
+        if hex_feat is None:
+            if self.grid is None:
+                raise ValueError("S3GDeformation: pass hex_feat or construct with hexplane=HexPlaneField(...)")
+            hex_feat = self.grid(point, t.reshape(1))
         temb_c = temporal_embed(w["weight"], t, self.min_embeddings)
         cur = int_lininterp(iteration, self.min_embeddings, self.max_embeddings, self.c2f)
         temb_f = temporal_embed(w["weight"], t, cur)

@@ -32,10 +32,15 @@ def _dino(w, hidden):  # Sequential(Linear, ReLU, Linear, ReLU, Linear)
 
 def deform(w: Dict[str, Tensor], point: Tensor, opacity: Tensor, shs: Tensor, embeddings: Tensor, hex_feat: Tensor,
            time: float, iteration: int, cam_no: int, min_embeddings: int = 30, max_embeddings: int = 150,
-           c2f_temporal_iter: int = 25000):
-    """-> means3D_final, opacity_final, shs_final, ddict {coarse,fine} x {dx, do, dshs, feat}."""
+           c2f_temporal_iter: int = 25000, grids=None, aabb=None):
+    """-> means3D_final, opacity_final, shs_final, ddict {coarse,fine} x {dx, do, dshs, feat}.
+    ``hex_feat=None``: the coarse HexPlane features are evaluated from ``grids`` / ``aabb`` (oracle.hexplane) at
+    ``(point, time + time_offset[cam_no])`` as ``query_hexplane`` does (deformation.py:187-199)."""
     N = point.shape[0]
     t = time + w["time_offset"][cam_no, 0]
+    if hex_feat is None:
+        from . import hexplane as _hex
+        hex_feat = _hex.hexplane_features(grids, aabb, point, t.reshape(1, 1).expand(N, 1))
     temb_c = get_temporal_embed(t, min_embeddings, w["weight"])
     cur = int_lininterp(iteration, min_embeddings, max_embeddings, c2f_temporal_iter)
     temb_f = get_temporal_embed(t, cur, w["weight"])

@@ -180,7 +180,7 @@ def main():
     print("golden fixtures written to", HERE)
 
 
-if __name__ == "__main__" and "--s3g" not in sys.argv:
+if __name__ == "__main__" and "--s3g" not in sys.argv and "--hexplane" not in sys.argv:
     main()
 
 
@@ -242,3 +242,58 @@ def make_s3g_golden():
 
 if __name__ == "__main__" and "--s3g" in sys.argv:
     make_s3g_golden()
+
+
+def make_hexplane_golden():
+    """HexPlaneField (S3Gaussian/scene/hexplane.py) run on the CPU: features and gradients w.r.t. points, times and
+    planes -> tests/golden/hexplane.npz.  Plane contents come from oracle.hexplane.hash_planes (exact integer hash),
+    so the fixture stores only points, cotangents and the reference's outputs."""
+    ref = load_file("ref_hexplane", f"{REF}/S3Gaussian/scene/hexplane.py")
+    from oracle import hexplane as OH
+    out = {}
+    cases = [
+        # name, resolution, multires, bounds, set_aabb (max, min) or None, N, per-point times?
+        ("a", [8, 8, 8, 5], [1, 2], 1.6, None, 300, True),
+        ("b", [16, 16, 16, 25], [1, 2, 4, 8], 1.6, ([30.0, 12.0, 9.0], [-20.0, -14.0, -3.0]), 400, False),
+    ]
+    for name, reso, mr, bounds, box, N, per_point_t in cases:
+        cfg = {"grid_dimensions": 2, "input_coordinate_dim": 4, "output_coordinate_dim": 32, "resolution": reso}
+        field = ref.HexPlaneField(bounds, cfg, mr)
+        if box is not None:
+            field.set_aabb(*box)
+        grids = OH.hash_planes(reso, mr, salt=len(name) + ord(name[0]))
+        for s in range(len(mr)):
+            for p in range(6):
+                assert field.grids[s][p].shape == grids[s][p].shape
+                field.grids[s][p].data = grids[s][p].clone()
+        g = torch.Generator().manual_seed(3 + ord(name[0]))
+        lo, hi = field.aabb.data.min(0).values, field.aabb.data.max(0).values
+        pts = lo + (hi - lo) * (torch.rand(N, 3, generator=g) * 1.3 - 0.15)      # ~25 % outside the box (border clamp)
+        pts[0] = hi; pts[1] = lo; pts[2] = 0.5 * (lo + hi)                         # exact corners / centre
+        pts[3, 0] = lo[0] + (hi[0] - lo[0]) * 0.25                                 # lands on a grid node
+        t = torch.full((N, 1), 0.37)
+        if per_point_t:
+            t[5:60, 0] = torch.rand(55, generator=g) * 2.6 - 1.3
+            t[60, 0], t[61, 0] = 1.0, -1.0
+        pts.requires_grad_(True); t.requires_grad_(True)
+        feat = field(pts, t)
+        cot = torch.randn(feat.shape, generator=g)
+        (feat * cot).sum().backward()
+        out[f"{name}_resolution"], out[f"{name}_multires"] = np.array(reso), np.array(mr)
+        out[f"{name}_salt"] = np.array(len(name) + ord(name[0]))
+        out[f"{name}_aabb"] = field.aabb.data.numpy().copy()
+        out[f"{name}_pts"], out[f"{name}_t"], out[f"{name}_cot"] = pts.detach().numpy(), t.detach().numpy(), cot.numpy()
+        out[f"{name}_feat"] = feat.detach().numpy()
+        out[f"{name}_v_pts"], out[f"{name}_v_t"] = pts.grad.numpy(), t.grad.numpy()
+        gg = [field.grids[s][p].grad for s in range(len(mr)) for p in range(6)]
+        out[f"{name}_v_plane_sum"] = np.array([x.double().sum().item() for x in gg])
+        out[f"{name}_v_plane_l2"] = np.array([x.double().pow(2).sum().sqrt().item() for x in gg])
+        if name == "a":
+            for k, x in enumerate(gg):
+                out[f"a_v_plane{k}"] = x.numpy()
+    np.savez_compressed(f"{HERE}/hexplane.npz", **out)
+    print("wrote hexplane.npz with", len(out), "arrays")
+
+
+if __name__ == "__main__" and "--hexplane" in sys.argv:
+    make_hexplane_golden()

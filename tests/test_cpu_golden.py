@@ -97,3 +97,26 @@ def test_emd_s3g_golden():
         for br in ("coarse", "fine"):
             for key in ("dx", "do", "dshs", "feat"):
                 assert torch.allclose(dd[br][key], _t(z[f"c{ci}_{br}_{key}"]), atol=2e-6), (ci, br, key)
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_hexplane_oracle_matches_reference(name):
+    """oracle/hexplane.py against features and gradients of the reference's own HexPlaneField
+    (S3Gaussian/scene/hexplane.py), tests/golden/hexplane.npz."""
+    from oracle import hexplane as OH
+    from tests.hex_util import oracle_run
+    z = np.load(f"{G}/hexplane.npz")
+    grids = OH.hash_planes(list(z[f"{name}_resolution"]), list(z[f"{name}_multires"]), salt=int(z[f"{name}_salt"]))
+    feat, v_pts, v_t, v_g = oracle_run(grids, _t(z[f"{name}_aabb"]), _t(z[f"{name}_pts"]), _t(z[f"{name}_t"]),
+                                       _t(z[f"{name}_cot"]))
+    assert np.abs(feat.numpy() - z[f"{name}_feat"]).max() <= 1e-6
+    assert np.abs(v_pts.numpy() - z[f"{name}_v_pts"]).max() <= 2e-5 * max(1.0, np.abs(z[f"{name}_v_pts"]).max())
+    assert np.abs(v_t.numpy() - z[f"{name}_v_t"]).max() <= 2e-5 * max(1.0, np.abs(z[f"{name}_v_t"]).max())
+    flat = [g for row in v_g for g in row]
+    sums = np.array([g.double().sum().item() for g in flat])
+    l2 = np.array([g.double().pow(2).sum().sqrt().item() for g in flat])
+    assert np.allclose(sums, z[f"{name}_v_plane_sum"], rtol=1e-4, atol=1e-4)
+    assert np.allclose(l2, z[f"{name}_v_plane_l2"], rtol=1e-5)
+    if name == "a":
+        for k, g in enumerate(flat):
+            assert np.abs(g.numpy() - z[f"a_v_plane{k}"]).max() <= 2e-6 * max(1.0, np.abs(z[f"a_v_plane{k}"]).max())

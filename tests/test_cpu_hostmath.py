@@ -173,3 +173,42 @@ def test_dg_preprocess_bit_exact(hostlib):
     assert np.array_equal(d2.view(np.int32), depths.numpy().view(np.int32))
     assert np.array_equal(c2.view(np.int32), conics.numpy().view(np.int32))
     assert np.array_equal(rc, torch.stack(rect, -1).numpy().astype(np.int32))
+
+
+@pytest.mark.parametrize("per_point_t", [False, True])
+def test_hexplane_host_math_matches_oracle(hostlib, per_point_t):
+    """hexplane_math.cuh (the tap arithmetic the CUDA kernels include) against the oracle: features, plane /
+    point / time gradients, with points outside the box, on grid nodes and on the box corners."""
+    from oracle import hexplane as OH
+    from tests.hex_util import flatten_planes, oracle_run, unflatten_like
+    reso, mr = [8, 6, 10, 5], [1, 2, 4]
+    grids = OH.hash_planes(reso, mr, salt=5)
+    aabb = torch.tensor([[3.0, 2.0, 1.5], [-2.0, -2.5, -0.5]])
+    g = torch.Generator().manual_seed(17)
+    N = 400
+    lo, hi = aabb.min(0).values, aabb.max(0).values
+    pts = lo + (hi - lo) * (torch.rand(N, 3, generator=g) * 1.3 - 0.15)
+    pts[0], pts[1], pts[2] = hi, lo, 0.5 * (lo + hi)
+    t = torch.rand(N, 1, generator=g) * 2.4 - 1.2 if per_point_t else torch.full((N, 1), 0.37)
+    cot = torch.randn(N, 32 * len(mr), generator=g)
+    feat_o, vp_o, vt_o, vg_o = oracle_run(grids, aabb, pts, t, cot)
+    flat, offsets, rs = flatten_planes(grids)
+    feat = np.zeros((N, 32 * len(mr)), np.float32); v_planes = np.zeros(flat.numel(), np.float32)
+    v_pts = np.zeros((N, 3), np.float32); v_t = np.zeros(N if per_point_t else 1, np.float32)
+    t_in = t.reshape(-1).contiguous() if per_point_t else t[:1].reshape(-1).contiguous()
+    f = hostlib.emd_host_hexplane
+    f.argtypes = [P, P, P, ctypes.c_int, P, P, P, ctypes.c_int, ctypes.c_int64] + [P] * 5
+    f.restype = None
+    f(_fp(flat), offsets.ctypes.data_as(P), rs.ctypes.data_as(P), len(mr), _fp(aabb), _fp(pts), _fp(t_in),
+      1 if per_point_t else 0, N, feat.ctypes.data_as(P), _fp(cot), v_planes.ctypes.data_as(P), v_pts.ctypes.data_as(P),
+      v_t.ctypes.data_as(P))
+    assert np.abs(feat - feat_o.numpy()).max() <= 1e-6
+    assert np.abs(v_pts - vp_o.numpy()).max() <= 2e-5 * max(1.0, vp_o.abs().max().item())
+    if per_point_t:
+        assert np.abs(v_t - vt_o.reshape(-1).numpy()).max() <= 2e-5 * max(1.0, vt_o.abs().max().item())
+    else:
+        assert abs(v_t[0] - vt_o.sum().item()) <= 1e-4 * max(1.0, abs(vt_o.sum().item()))
+    got = unflatten_like(torch.from_numpy(v_planes), grids, offsets)
+    for row_g, row_o in zip(got, vg_o):
+        for a, b in zip(row_g, row_o):
+            assert (a - b).abs().max().item() <= 5e-6 * max(1.0, b.abs().max().item())

@@ -17,6 +17,8 @@ GROUPS = [
                                                          "emd_smpl_deform_bwd"]),
     ("K1b  spherical harmonics + node activations", ["emd_sh_fwd", "emd_sh_bwd", "emd_activate_fwd", "emd_activate_bwd"]),
     ("K1d  S3Gaussian EMD deformation MLP", ["emd_linear_bwd_workspace_bytes", "emd_linear_fwd", "emd_linear_fwd_tc", "emd_linear_bwd", "emd_linear_bwd_tc", "emd_temb_fwd", "emd_temb_bwd"]),
+    ("K1e  HexPlane feature gather (input of the S3Gaussian EMD MLP)", ["emd_hexplane_fwd", "emd_hexplane_bwd_workspace_bytes",
+                                                                       "emd_hexplane_bwd"]),
     ("K2   projection", ["emd_projection_fwd", "emd_projection_bwd", "emd_dg_preprocess_fwd", "emd_dg_preprocess_bwd"]),
     ("K3   tile intersection", ["emd_scan_workspace_bytes", "emd_cumsum_i32_i64", "emd_exclusive_scan_u32",
                                 "emd_isect_emit", "emd_dg_isect_emit"]),
@@ -83,6 +85,16 @@ DOC = {
     "emd_temb_fwd": "get_temporal_embed (deformation.py:208-221 / rigid.py:150-164): resample table[E,d] to `cur` rows and "
                     "sample at time t -> emb[d].  t is a DEVICE scalar (time + learnable time_offset, deformation.py:325-328).",
     "emd_temb_bwd": "VJP of emd_temb_fwd w.r.t. the table (ADDS into v_table) and t.",
+    "emd_hexplane_fwd": "Replaces HexPlaneField.forward -> interpolate_ms_features -> 24 x F.grid_sample(bilinear, border, "
+                        "align_corners=True) (S3Gaussian/scene/hexplane.py:73-106, 165-187; call deformation.py:187-199): "
+                        "feat[N, S*F] = concat over scales of the product over the 6 planes (xy,xz,xt,yz,yt,zt).  planes: ONE flat "
+                        "device buffer, plane (s,p) stored feature-last [H][W][F] at float offset plane_offsets[s*6+p] (HOST "
+                        "array); reso: HOST int[S*4] grid size per coordinate (x,y,z,t) and scale; aabb: HOST float[6] = "
+                        "{aabb[0], aabb[1]} (hexplane.py:19-20); t: DEVICE, one shared value (t_stride 0) or one per point (1).",
+    "emd_hexplane_bwd_workspace_bytes": "Workspace bytes of emd_hexplane_bwd (per-block partials of the shared-time gradient).",
+    "emd_hexplane_bwd": "VJP of emd_hexplane_fwd: v_planes (layout of planes, ADDED into, caller zero-fills; 16-byte vector "
+                        "reductions), v_pts[N,3] (may be NULL), v_t (N values written for t_stride 1, one value ADDED into for "
+                        "t_stride 0 in a fixed order; may be NULL).",
     "emd_scan_workspace_bytes": "Workspace bytes of the scans for n elements.",
     "emd_cumsum_i32_i64": "Inclusive cumulative sum (torch.cumsum of tiles_per_gauss in gsplat's isect_tiles); total -> device scalar.",
     "emd_exclusive_scan_u32": "Exclusive scan (radix-sort tables); in-place allowed.",
