@@ -51,6 +51,9 @@ _SIGS = {
     "emd_hexplane_bwd_workspace_bytes": (c_size_t, [c_int64]),
     "emd_hexplane_bwd": (c_int, [P, ctypes.POINTER(c_int64), ctypes.POINTER(c_int), c_int, c_int, ctypes.POINTER(c_float),
                                  P, P, c_int, c_int64, P, P, P, P, P, c_size_t, P]),
+    "emd_adam_max_tensors": (c_int, []),
+    "emd_adam_step": (c_int, [ctypes.POINTER(P)] * 4 + [ctypes.POINTER(c_int64)] + [ctypes.POINTER(ctypes.c_double)] * 5
+                      + [ctypes.POINTER(c_int64), c_int, ctypes.c_double, P]),
     "emd_tile_order": (c_int, [P, c_int64, c_int64, P, P, P, P]),
     "emd_raster_segment_size": (c_int, []),
     "emd_raster_checkpoint_floats": (c_int, []),

@@ -14,6 +14,8 @@ tensor is not on a CUDA device.
 """
 from . import _C  # noqa: F401
 from .gsplat_api import rasterization  # noqa: F401
+from .hexplane import HexPlaneField  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
 from .sh_ops import activate_gaussians, spherical_harmonics  # noqa: F401
 
-__all__ = ["rasterization", "spherical_harmonics", "activate_gaussians"]
+__all__ = ["rasterization", "spherical_harmonics", "activate_gaussians", "HexPlaneField", "FusedAdam"]

@@ -205,3 +205,12 @@ extern "C" void emd_host_hexplane(const float* planes, const int64_t* plane_offs
         }
     }
 }
+
+// ---- Adam (adam_math.cuh) -----------------------------------------------------------------------------------
+#include "adam_math.cuh"
+
+extern "C" void emd_host_adam_step(float* p, const float* g, float* m, float* v, int64_t numel, double lr, double beta1,
+                                   double beta2, double eps, double weight_decay, int64_t step, double grad_scale) {
+    const AdamScalars s = adam_scalars(lr, beta1, beta2, eps, weight_decay, step, grad_scale);
+    for (int64_t i = 0; i < numel; ++i) adam_update(p[i], g[i], m[i], v[i], s);
+}

@@ -212,3 +212,34 @@ def test_hexplane_host_math_matches_oracle(hostlib, per_point_t):
     for row_g, row_o in zip(got, vg_o):
         for a, b in zip(row_g, row_o):
             assert (a - b).abs().max().item() <= 5e-6 * max(1.0, b.abs().max().item())
+
+
+@pytest.mark.parametrize("wd,scale", [(0.0, 1.0), (0.01, 0.125)])
+def test_adam_host_math_matches_torch(hostlib, wd, scale):
+    """adam_math.cuh (what emd_adam_step runs per element) against torch.optim.Adam as the reference configures it
+    (eps=1e-15, lr written per step by a scheduler) over 25 steps, including all-zero gradients (invisible Gaussians)."""
+    g = torch.Generator().manual_seed(3)
+    n = 5003
+    p0 = torch.randn(n, generator=g)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=0.0, eps=1e-15, weight_decay=wd, foreach=False)
+    p = p0.numpy().copy(); m = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
+    f = hostlib.emd_host_adam_step
+    f.argtypes = [P, P, P, P, ctypes.c_int64] + [ctypes.c_double] * 5 + [ctypes.c_int64, ctypes.c_double]
+    f.restype = None
+    for step in range(1, 26):
+        grad = torch.randn(n, generator=g) * (10.0 ** float(torch.randint(-4, 2, (1,), generator=g)))
+        grad[::7] = 0.0
+        if step > 5:
+            grad[:500] = 0.0
+        lr = 1.6e-4 * 0.97 ** step
+        opt.param_groups[0]["lr"] = lr
+        ref.grad = (grad * scale).clone()
+        opt.step()
+        gn = grad.numpy().copy()
+        f(p.ctypes.data_as(P), gn.ctypes.data_as(P), m.ctypes.data_as(P), v.ctypes.data_as(P), n, lr, 0.9, 0.999, 1e-15, wd,
+          step, scale)
+        st = opt.state[ref]
+        assert np.abs(m - st["exp_avg"].numpy()).max() <= 2e-6 * max(1e-30, float(st["exp_avg"].abs().max()))
+        assert np.abs(v - st["exp_avg_sq"].numpy()).max() <= 2e-6 * max(1e-30, float(st["exp_avg_sq"].abs().max()))
+        assert np.abs(p - ref.detach().numpy()).max() <= 5e-7 * step

@@ -19,6 +19,7 @@ GROUPS = [
     ("K1d  S3Gaussian EMD deformation MLP", ["emd_linear_bwd_workspace_bytes", "emd_linear_fwd", "emd_linear_fwd_tc", "emd_linear_bwd", "emd_linear_bwd_tc", "emd_temb_fwd", "emd_temb_bwd"]),
     ("K1e  HexPlane feature gather (input of the S3Gaussian EMD MLP)", ["emd_hexplane_fwd", "emd_hexplane_bwd_workspace_bytes",
                                                                        "emd_hexplane_bwd"]),
+    ("Next (SURVEY 8f-2): fused Adam step", ["emd_adam_max_tensors", "emd_adam_step"]),
     ("K2   projection", ["emd_projection_fwd", "emd_projection_bwd", "emd_dg_preprocess_fwd", "emd_dg_preprocess_bwd"]),
     ("K3   tile intersection", ["emd_scan_workspace_bytes", "emd_cumsum_i32_i64", "emd_exclusive_scan_u32",
                                 "emd_isect_emit", "emd_dg_isect_emit"]),
@@ -95,6 +96,12 @@ DOC = {
     "emd_hexplane_bwd": "VJP of emd_hexplane_fwd: v_planes (layout of planes, ADDED into, caller zero-fills; 16-byte vector "
                         "reductions), v_pts[N,3] (may be NULL), v_t (N values written for t_stride 1, one value ADDED into for "
                         "t_stride 0 in a fixed order; may be NULL).",
+    "emd_adam_max_tensors": "Tensors one emd_adam_step call can take (the table travels in the kernel parameter space).",
+    "emd_adam_step": "torch.optim.Adam(groups, lr=0.0, eps=1e-15).step() as the reference configures it "
+                     "(OmniRe/models/trainers/base.py:190-226, S3Gaussian/scene/gaussian_model.py:186-200): ONE launch over up to "
+                     "emd_adam_max_tensors() fp32 tensors.  All arrays are HOST arrays [n_tensors]; params/grads/exp_avg/exp_avg_sq "
+                     "hold DEVICE pointers; step[i] is the 1-based count after this update; grad_scale multiplies the gradients "
+                     "(1/world_size after a sum all-reduce); L2 weight decay as in torch (g += wd * p).",
     "emd_scan_workspace_bytes": "Workspace bytes of the scans for n elements.",
     "emd_cumsum_i32_i64": "Inclusive cumulative sum (torch.cumsum of tiles_per_gauss in gsplat's isect_tiles); total -> device scalar.",
     "emd_exclusive_scan_u32": "Exclusive scan (radix-sort tables); in-place allowed.",
