@@ -48,7 +48,13 @@ EMD_HD HexAxis hex_axis(float u, int size) {
 }
 
 // p -> u = (p - a0) * (2 / (a1 - a0)) - 1 ; k = 2 / (a1 - a0) precomputed in fp32 on the host
+// (two rounded operations like the reference's `(pts - aabb[0]) * k - 1.0`: a contracted FMA moves the tap coordinate by
+// up to half an ulp of (p - a0) * k, which the fine planes (512 texels) amplify to ~2e-6 in the features)
+#ifdef __CUDA_ARCH__
+EMD_HD float hex_normalize(float p, float a0, float k) { return __fsub_rn(__fmul_rn(__fsub_rn(p, a0), k), 1.0f); }
+#else
 EMD_HD float hex_normalize(float p, float a0, float k) { return (p - a0) * k - 1.0f; }
+#endif
 
 // out[p] = product of v[q] over q != p (prefix/suffix products: planes may hold exact zeros)
 EMD_HD void hex_excl_products(const float v[HEX_PLANES], float out[HEX_PLANES]) {
