@@ -54,6 +54,9 @@ _SIGS = {
     "emd_adam_max_tensors": (c_int, []),
     "emd_adam_step": (c_int, [ctypes.POINTER(P)] * 4 + [ctypes.POINTER(c_int64)] + [ctypes.POINTER(ctypes.c_double)] * 5
                       + [ctypes.POINTER(c_int64), c_int, ctypes.c_double, P]),
+    "emd_image_loss_partials_floats": (c_int64, [c_int, c_int, c_int]),
+    "emd_image_loss_fwd": (c_int, [P] * 8 + [c_int, c_int, c_int, P, ctypes.POINTER(c_float)] + [P] * 4 + [P]),
+    "emd_image_loss_bwd": (c_int, [P] * 8 + [c_int, c_int, c_int, P, ctypes.POINTER(c_float)] + [P] * 7 + [P]),
     "emd_tile_order": (c_int, [P, c_int64, c_int64, P, P, P, P]),
     "emd_raster_segment_size": (c_int, []),
     "emd_raster_checkpoint_floats": (c_int, []),

@@ -214,3 +214,172 @@ extern "C" void emd_host_adam_step(float* p, const float* g, float* m, float* v,
     const AdamScalars s = adam_scalars(lr, beta1, beta2, eps, weight_decay, step, grad_scale);
     for (int64_t i = 0; i < numel; ++i) adam_update(p[i], g[i], m[i], v[i], s);
 }
+
+// ---- fused image losses (loss_math.cuh) ----------------------------------------------------------------------
+// Same per-pixel functions, same formulas and normalisers as image_loss.cu, as plain loops (windowed sums taken directly,
+// no tiling): terms[C][EMD_LOSS_TERMS] and, when v_terms is given, the cotangents.
+#include <vector>
+#include "loss_math.cuh"
+
+namespace {
+struct HostLoss {
+    const float *rgb, *depth, *alpha, *sky, *gt, *valid_mask, *sky_mask, *lidar;
+    int C, H, W;
+    EmdImageLossConfig g;
+    const float* win;
+    bool in(int y, int x) const { return y >= 0 && y < H && x >= 0 && x < W; }
+    bool in_map(int y, int x) const {
+        if (!in(y, x)) return false;
+        return g.ssim_pad ? true : (y >= SSIM_R && y < H - SSIM_R && x >= SSIM_R && x < W - SSIM_R);
+    }
+    float valid(int c, int y, int x) const { return valid_mask ? valid_mask[((int64_t)c * H + y) * W + x] : 1.0f; }
+    LossBlend blend(int c, int y, int x, int ch) const {
+        const int64_t pix = (int64_t)y * W + x;
+        const float rg = rgb[c * g.rgb_vs + pix * g.rgb_ps + ch * g.rgb_cs];
+        const float al = sky ? alpha[(int64_t)c * H * W + pix] : 0.0f;
+        const float sk = sky ? sky[c * g.sky_vs + pix * g.sky_ps + ch * g.sky_cs] : 0.0f;
+        return loss_blend(rg, al, sk, sky != nullptr, g.blend);
+    }
+    void pg(int c, int y, int x, int ch, float& p, float& q) const {
+        p = q = 0.0f;
+        if (!in(y, x)) return;
+        const float v = valid(c, y, x);
+        p = blend(c, y, x, ch).p * v;
+        q = gt[c * g.gt_vs + ((int64_t)y * W + x) * g.gt_ps + ch * g.gt_cs] * v;
+    }
+    void gt3(int c, int y, int x, float o[3]) const {
+        for (int ch = 0; ch < 3; ++ch) o[ch] = gt[c * g.gt_vs + ((int64_t)y * W + x) * g.gt_ps + ch * g.gt_cs];
+    }
+    float dep(int c, int y, int x) const { return depth[c * g.depth_vs + ((int64_t)y * W + x) * g.depth_ps]; }
+    float hit(int c, int y, int x, float li) const {
+        const int64_t vpix = ((int64_t)c * H + y) * W + x;
+        if (g.depth_mask_mode == 0) return (li > 0.0f ? 1.0f : 0.0f) * valid(c, y, x);
+        return sky_mask ? 1.0f - sky_mask[vpix] : 1.0f;
+    }
+};
+}  // namespace
+
+extern "C" void emd_host_image_loss(const float* rgb, const float* depth, const float* alpha, const float* sky,
+                                    const float* gt, const float* valid_mask, const float* sky_mask, const float* lidar,
+                                    int C, int H, int W, const EmdImageLossConfig* cfg, const float* window, float* terms,
+                                    const float* v_terms, float* v_rgb, float* v_depth, float* v_alpha, float* v_sky) {
+    HostLoss A{rgb, depth, alpha, sky, gt, valid_mask, sky_mask, lidar, C, H, W, *cfg, window};
+    const EmdImageLossConfig& g = A.g;
+    const double n_l1 = 3.0 * H * W, n_hw = (double)H * W, n_sx = (double)H * (W - 1), n_sy = (double)(H - 1) * W;
+    const double n_ss = g.ssim_pad ? 3.0 * H * W : 3.0 * (H - 2 * SSIM_R) * (W - 2 * SSIM_R);
+    const int64_t HW = (int64_t)H * W;
+    for (int c = 0; c < C; ++c) {
+        double S[EMD_LOSS_SUMS] = {0, 0, 0, 0, 0, 0, 0, 0};
+        std::vector<float> maps((size_t)9 * HW, 0.0f);
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                const int64_t pix = (int64_t)y * W + x, vpix = (int64_t)c * HW + pix;
+                for (int ch = 0; ch < 3; ++ch) {
+                    float p, q;
+                    A.pg(c, y, x, ch, p, q);
+                    S[0] += fabsf(q - p);
+                    if (!A.in_map(y, x)) continue;
+                    float m[5] = {0, 0, 0, 0, 0};
+                    for (int j = 0; j < EMD_SSIM_TAPS; ++j) {
+                        float h[5] = {0, 0, 0, 0, 0};
+                        for (int k = 0; k < EMD_SSIM_TAPS; ++k) {
+                            float pp, qq;
+                            A.pg(c, y + j - SSIM_R, x + k - SSIM_R, ch, pp, qq);
+                            const float w = window[k];
+                            h[0] += w * pp; h[1] += w * qq; h[2] += w * pp * pp; h[3] += w * qq * qq; h[4] += w * pp * qq;
+                        }
+                        for (int i = 0; i < 5; ++i) m[i] += window[j] * h[i];
+                    }
+                    const SsimPoint s = ssim_point(m[0], m[1], m[2], m[3], m[4]);
+                    S[1] += s.m;
+                    maps[(ch * 3 + 0) * HW + pix] = s.d_mu;
+                    maps[(ch * 3 + 1) * HW + pix] = s.d_pp;
+                    maps[(ch * 3 + 2) * HW + pix] = s.d_pg;
+                }
+                const float v = A.valid(c, y, x), al = alpha[vpix];
+                float l, d;
+                if (sky_mask) {
+                    loss_opacity(al * v, (1.0f - sky_mask[vpix]) * v, g.opacity_loss, g.bce_limit, l, d);
+                    S[2] += l;
+                }
+                loss_entropy(al, l, d);
+                S[5] += l;
+                if (depth) {
+                    const float de = A.dep(c, y, x);
+                    if (lidar) {
+                        const float li = lidar[vpix], h = A.hit(c, y, x, li);
+                        float e, dd;
+                        if (loss_depth(de * h, li * h, g, e, dd)) { S[3] += e; S[4] += 1.0; }
+                    }
+                    const float id = loss_inv_depth(de);
+                    float g0[3], g1[3];
+                    A.gt3(c, y, x, g0);
+                    if (x + 1 < W) { A.gt3(c, y, x + 1, g1); S[6] += fabsf(id - loss_inv_depth(A.dep(c, y, x + 1))) * loss_edge_weight(g0, g1); }
+                    if (y + 1 < H) { A.gt3(c, y + 1, x, g1); S[7] += fabsf(id - loss_inv_depth(A.dep(c, y + 1, x))) * loss_edge_weight(g0, g1); }
+                }
+            }
+        float* T = terms + c * EMD_LOSS_TERMS;
+        T[0] = (float)(g.w_l1 * (S[0] / n_l1));
+        T[1] = (float)(g.w_ssim * (1.0 - S[1] / n_ss));
+        T[2] = sky_mask ? (float)(g.w_opacity * (S[2] / n_hw)) : 0.f;
+        T[3] = (depth && lidar && g.w_depth != 0.f) ? (float)(g.w_depth * (S[3] / S[4])) : 0.f;
+        T[4] = (float)(g.w_entropy * (S[5] / n_hw));
+        T[5] = depth ? (float)(g.w_smooth * (S[6] / n_sx + S[7] / n_sy)) : 0.f;
+        if (!v_terms) continue;
+        const float* vt = v_terms + c * EMD_LOSS_TERMS;
+        const float g_l1 = (float)(vt[0] * g.w_l1 / n_l1), g_ss = (float)(-(double)vt[1] * g.w_ssim / n_ss);
+        const float g_op = (float)(vt[2] * g.w_opacity / n_hw), g_dp = S[4] > 0 ? (float)(vt[3] * g.w_depth / S[4]) : 0.f;
+        const float g_en = (float)(vt[4] * g.w_entropy / n_hw);
+        const float g_sx = (float)(vt[5] * g.w_smooth / n_sx), g_sy = (float)(vt[5] * g.w_smooth / n_sy);
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                const int64_t pix = (int64_t)y * W + x, vpix = (int64_t)c * HW + pix;
+                const float v = A.valid(c, y, x), al = alpha[vpix];
+                float d_alpha = 0.0f;
+                for (int ch = 0; ch < 3; ++ch) {
+                    float s[3] = {0, 0, 0};
+                    for (int j = 0; j < EMD_SSIM_TAPS; ++j) {
+                        float h[3] = {0, 0, 0};
+                        for (int k = 0; k < EMD_SSIM_TAPS; ++k) {
+                            const int yy = y + j - SSIM_R, xx = x + k - SSIM_R;
+                            if (!A.in(yy, xx)) continue;
+                            for (int i = 0; i < 3; ++i) h[i] += window[k] * maps[(ch * 3 + i) * HW + (int64_t)yy * W + xx];
+                        }
+                        for (int i = 0; i < 3; ++i) s[i] += window[j] * h[i];
+                    }
+                    const LossBlend b = A.blend(c, y, x, ch);
+                    const float p = b.p * v, q = gt[c * g.gt_vs + pix * g.gt_ps + ch * g.gt_cs] * v;
+                    const float dp = g_l1 * loss_sign(p - q) + g_ss * (s[0] + 2.0f * p * s[1] + q * s[2]);
+                    const float db = dp * v;
+                    v_rgb[c * g.rgb_vs + pix * g.rgb_ps + ch * g.rgb_cs] = db * b.d_rgb;
+                    d_alpha += db * b.d_alpha;
+                    if (v_sky) v_sky[c * g.sky_vs + pix * g.sky_ps + ch * g.sky_cs] = db * b.d_sky;
+                }
+                float l, d;
+                if (sky_mask) {
+                    loss_opacity(al * v, (1.0f - sky_mask[vpix]) * v, g.opacity_loss, g.bce_limit, l, d);
+                    d_alpha += g_op * d * v;
+                }
+                loss_entropy(al, l, d);
+                d_alpha += g_en * d;
+                v_alpha[vpix] = d_alpha;
+                if (!depth) continue;
+                const float de = A.dep(c, y, x);
+                float vd = 0.0f;
+                if (lidar) {
+                    const float li = lidar[vpix], h = A.hit(c, y, x, li);
+                    float e, dd;
+                    if (loss_depth(de * h, li * h, g, e, dd)) vd += g_dp * dd * h;
+                }
+                const float id = loss_inv_depth(de);
+                float g0[3], g1[3], did = 0.0f;
+                A.gt3(c, y, x, g0);
+                if (x + 1 < W) { A.gt3(c, y, x + 1, g1); did += g_sx * loss_sign(id - loss_inv_depth(A.dep(c, y, x + 1))) * loss_edge_weight(g0, g1); }
+                if (x > 0) { A.gt3(c, y, x - 1, g1); did -= g_sx * loss_sign(loss_inv_depth(A.dep(c, y, x - 1)) - id) * loss_edge_weight(g1, g0); }
+                if (y + 1 < H) { A.gt3(c, y + 1, x, g1); did += g_sy * loss_sign(id - loss_inv_depth(A.dep(c, y + 1, x))) * loss_edge_weight(g0, g1); }
+                if (y > 0) { A.gt3(c, y - 1, x, g1); did -= g_sy * loss_sign(loss_inv_depth(A.dep(c, y - 1, x)) - id) * loss_edge_weight(g1, g0); }
+                vd += did * (-id * id);
+                v_depth[c * g.depth_vs + pix * g.depth_ps] = vd;
+            }
+    }
+}

@@ -180,7 +180,7 @@ def main():
     print("golden fixtures written to", HERE)
 
 
-if __name__ == "__main__" and "--s3g" not in sys.argv and "--hexplane" not in sys.argv:
+if __name__ == "__main__" and not any(a in sys.argv for a in ("--s3g", "--hexplane", "--losses")):
     main()
 
 
@@ -297,3 +297,50 @@ def make_hexplane_golden():
 
 if __name__ == "__main__" and "--hexplane" in sys.argv:
     make_hexplane_golden()
+
+
+def make_losses_golden():
+    """The reference's own loss code on the CPU -> tests/golden/losses.npz: OmniRe/models/losses.py (DepthLoss,
+    binary_cross_entropy, safe_binary_cross_entropy; values and input gradients) and S3Gaussian/utils/loss_utils.py
+    (l1_loss, ssim, compute_depth).  pytorch_msssim and kornia are absent, so the OmniRe SSIM / smoothness terms have no
+    fixture (oracle/losses.py says so)."""
+    _stub(["sklearn", "sklearn.cluster"])
+    RL = load_file("ref_omnire_losses", f"{REF}/OmniRe/models/losses.py")
+    SL = load_file("ref_s3g_loss_utils", f"{REF}/S3Gaussian/utils/loss_utils.py")
+    from tests.loss_util import loss_inputs
+    H, W = 40, 56
+    d = loss_inputs(11, H, W)
+    out = {"H": np.array(H), "W": np.array(W), "seed": np.array(11)}
+
+    def grad_of(fn, x):
+        x = x.clone().requires_grad_(True)
+        y = fn(x)
+        y.backward()
+        return y.detach().numpy(), x.grad.numpy()
+
+    valid = 1.0 - d["ego_mask"]
+    hit = (d["lidar"] > 0).float() * valid
+    for name, kw in (("l1_inv", dict(loss_type="l1", normalize=False, use_inverse_depth=True)),
+                     ("l2_norm", dict(loss_type="l2", normalize=True, use_inverse_depth=False)),
+                     ("sl1_norm_inv", dict(loss_type="smooth_l1", normalize=True, use_inverse_depth=True))):
+        fn = RL.DepthLoss(**kw)
+        out[f"depth_{name}"], out[f"depth_{name}_grad"] = grad_of(lambda x: fn(x, d["lidar"], hit), d["depth"])
+    occ_t = (1.0 - d["sky_mask"]) * valid
+    a = d["alpha"][..., 0]
+    out["bce"], out["bce_grad"] = grad_of(lambda x: RL.binary_cross_entropy(x * valid, occ_t, reduction="mean"), a)
+    out["safe_bce"], out["safe_bce_grad"] = grad_of(
+        lambda x: RL.safe_binary_cross_entropy(x * valid, occ_t, limit=0.1, reduction="mean"), a)
+    # S3Gaussian: CHW
+    img = d["rgb"].permute(2, 0, 1).contiguous()
+    gt = d["gt"].permute(2, 0, 1).contiguous()
+    out["s3g_l1"], out["s3g_l1_grad"] = grad_of(lambda x: SL.l1_loss(x, gt), img)
+    out["s3g_ssim"], out["s3g_ssim_grad"] = grad_of(lambda x: SL.ssim(x, gt), img)
+    mask = (1.0 - d["sky_mask"])[None]
+    dep = d["depth"].permute(2, 0, 1).contiguous()
+    out["s3g_depth"], out["s3g_depth_grad"] = grad_of(lambda x: SL.compute_depth("l2", x * mask, d["lidar"][None] * mask), dep)
+    np.savez_compressed(f"{HERE}/losses.npz", **out)
+    print("wrote losses.npz with", len(out), "arrays")
+
+
+if __name__ == "__main__" and "--losses" in sys.argv:
+    make_losses_golden()

@@ -120,3 +120,43 @@ def test_hexplane_oracle_matches_reference(name):
     if name == "a":
         for k, g in enumerate(flat):
             assert np.abs(g.numpy() - z[f"a_v_plane{k}"]).max() <= 2e-6 * max(1.0, np.abs(z[f"a_v_plane{k}"]).max())
+
+
+def test_losses_golden():
+    """oracle/losses.py against the reference's own OmniRe/models/losses.py and S3Gaussian/utils/loss_utils.py
+    (values and input gradients)."""
+    from oracle import losses as OL
+    from tests.loss_util import loss_inputs
+    z = np.load(f"{G}/losses.npz")
+    d = loss_inputs(int(z["seed"]), int(z["H"]), int(z["W"]))
+
+    def grad_of(fn, x):
+        x = x.clone().requires_grad_(True)
+        y = fn(x)
+        y.backward()
+        return y.detach(), x.grad
+
+    def check(name, fn, x, tol=1e-6):
+        y, g = grad_of(fn, x)
+        assert abs(float(y) - float(z[name])) <= tol * max(1.0, abs(float(z[name]))), name
+        ref = _t(z[name + "_grad"])
+        assert float((g - ref).abs().max()) <= tol * max(1e-12, float(ref.abs().max())), name
+
+    valid = 1.0 - d["ego_mask"]
+    hit = (d["lidar"] > 0).float() * valid
+    for name, kw in (("l1_inv", dict(loss_type="l1", normalize=False, use_inverse_depth=True)),
+                     ("l2_norm", dict(loss_type="l2", normalize=True, use_inverse_depth=False)),
+                     ("sl1_norm_inv", dict(loss_type="smooth_l1", normalize=True, use_inverse_depth=True))):
+        check(f"depth_{name}", lambda x: OL.depth_loss(x, d["lidar"], hit, **kw), d["depth"])
+    occ_t = (1.0 - d["sky_mask"]) * valid
+    a = d["alpha"][..., 0]
+    check("bce", lambda x: OL.binary_cross_entropy(x * valid, occ_t), a)
+    check("safe_bce", lambda x: OL.safe_binary_cross_entropy(x * valid, occ_t, limit=0.1), a)
+    img, gt = d["rgb"].permute(2, 0, 1).contiguous(), d["gt"].permute(2, 0, 1).contiguous()
+    check("s3g_l1", lambda x: (x - gt).abs().mean(), img)
+    check("s3g_ssim", lambda x: OL.ssim_s3g(x, gt), img, tol=1e-5)
+    mask = (1.0 - d["sky_mask"])[None]
+    check("s3g_depth", lambda x: OL.compute_depth_s3g("l2", x * mask, d["lidar"][None] * mask),
+          d["depth"].permute(2, 0, 1).contiguous())
+    # the two window constructions (loss_utils.py:56-58 vs pytorch_msssim) agree to an ulp
+    assert float((OL.gaussian_window_s3g() - OL.gaussian_window_msssim()).abs().max()) <= 2e-8

@@ -20,6 +20,8 @@ GROUPS = [
     ("K1e  HexPlane feature gather (input of the S3Gaussian EMD MLP)", ["emd_hexplane_fwd", "emd_hexplane_bwd_workspace_bytes",
                                                                        "emd_hexplane_bwd"]),
     ("Next (SURVEY 8f-2): fused Adam step", ["emd_adam_max_tensors", "emd_adam_step"]),
+    ("Next (SURVEY 8f-3): fused image losses between the rasterizer forward and backward",
+     ["emd_image_loss_partials_floats", "emd_image_loss_fwd", "emd_image_loss_bwd"]),
     ("K2   projection", ["emd_projection_fwd", "emd_projection_bwd", "emd_dg_preprocess_fwd", "emd_dg_preprocess_bwd"]),
     ("K3   tile intersection", ["emd_scan_workspace_bytes", "emd_cumsum_i32_i64", "emd_exclusive_scan_u32",
                                 "emd_isect_emit", "emd_dg_isect_emit"]),
@@ -102,6 +104,21 @@ DOC = {
                      "emd_adam_max_tensors() fp32 tensors.  All arrays are HOST arrays [n_tensors]; params/grads/exp_avg/exp_avg_sq "
                      "hold DEVICE pointers; step[i] is the 1-based count after this update; grad_scale multiplies the gradients "
                      "(1/world_size after a sum all-reduce); L2 weight decay as in torch (g += wd * p).",
+    "emd_image_loss_partials_floats": "Floats of the `partials` scratch buffer of emd_image_loss_fwd.",
+    "emd_image_loss_fwd": "Replaces the image terms of BasicTrainer.compute_losses (OmniRe/models/trainers/base.py:518-587: rgb L1, "
+                          "pytorch_msssim SSIM, sky-opacity BCE / SafeBCE of models/losses.py:33-83, DepthLoss :91-172, opacity "
+                          "entropy, kornia inverse-depth smoothness) together with render_fn's clamp (:415) and forward()'s sky "
+                          "blend (:486-493); with blend=1 / ssim_pad=1 the S3Gaussian flavour (gaussian_renderer/__init__.py:299-300, "
+                          "train.py:226, 348-363, utils/loss_utils.py:24-96).  rgb / depth / gt / sky are addressed through the "
+                          "strides in cfg (gsplat renders[C,H,W,4]: rgb = base, depth = base + 3, pixel stride 4; diff_gauss CHW: "
+                          "pixel stride 1, channel stride H*W); alpha, valid_mask (1 - egocar mask), sky_mask (1 = sky), lidar "
+                          "are dense [C,H,W]; depth, sky, valid_mask, sky_mask, lidar may be NULL.  cfg and window (the 11 "
+                          "normalised Gaussian taps) are HOST pointers.  Outputs: ssim_maps [C,3,3,H,W] and sums "
+                          "[C,EMD_LOSS_SUMS] (kept for the backward), partials (scratch), terms [C,EMD_LOSS_TERMS] = weighted "
+                          "loss terms per view; fixed-order reductions.",
+    "emd_image_loss_bwd": "VJP of emd_image_loss_fwd: v_rgb (rgb strides), v_depth (depth strides; NULL iff depth is), v_alpha "
+                          "[C,H,W], v_sky (sky strides; may be NULL) from v_terms [C,EMD_LOSS_TERMS] on the DEVICE -- the "
+                          "cotangents the rasterizer backward consumes, every pixel written.",
     "emd_scan_workspace_bytes": "Workspace bytes of the scans for n elements.",
     "emd_cumsum_i32_i64": "Inclusive cumulative sum (torch.cumsum of tiles_per_gauss in gsplat's isect_tiles); total -> device scalar.",
     "emd_exclusive_scan_u32": "Exclusive scan (radix-sort tables); in-place allowed.",
@@ -138,6 +155,16 @@ def prototypes():
             name = re.search(r"(\w+)\s*\(", p).group(1)
             out[name] = (p, f.name)
     return out
+
+
+def abi_types():
+    """Struct / constant definitions shared with the sources: the text between the ABI-types markers of the .cuh files."""
+    out = []
+    for f in sorted((ROOT / "emd_b200" / "csrc").glob("*.cuh")):
+        m = re.search(r"// >>> ABI types[^\n]*\n(.*?)// <<< ABI types", f.read_text(), re.S)
+        if m:
+            out.append(f"/* ---- types (from emd_b200/csrc/{f.name}) ---- */\n" + m.group(1))
+    return "\n".join(out)
 
 
 def wrap(text, width=100, indent=" * "):
@@ -181,6 +208,7 @@ def render():
 #define EMD_ERR_CUDA -4
 #define EMD_ERR_UNSUPPORTED -5
 
+''' + abi_types() + '''
 #ifdef __cplusplus
 extern "C" {
 #endif
