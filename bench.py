@@ -8,7 +8,9 @@ Workload (BASELINE.json configs[1]): synthetic Waymo-shaped street scene, 1.30 M
 30 x 5 000 rigid + 8 x 6 890 SMPL Gaussians (~1.505 M), 3 cameras 640x960 of one timestep per
 step.  A step = EMD deformation (rigid + SMPL) -> activations + SH colour per camera ->
 projection -> tile intersection + radix sort + tile ranges -> rasterization (RGB + expected
-depth + alpha), then the backward of all of it for seeded per-pixel cotangents.  With N GPUs
+depth + alpha) -> the reference's image losses against that step's ground-truth images (sky blend, L1,
+SSIM, sky-opacity BCE, lidar depth, opacity entropy, inverse-depth smoothness; base.py:518-587), then the
+backward of all of it.  EMD_BENCH_LOSS=cotangents restores the earlier stand-in (seeded per-pixel cotangents).  With N GPUs
 every rank renders its own timestep (weak scaling) and the parameter gradients are
 all-reduced over NCCL inside the timed region.
 
@@ -34,6 +36,8 @@ import torch  # noqa: E402
 W_IMG, H_IMG = 960, 640
 YAWS = (0.0, 45.0, -45.0)
 STEP0 = 20000  # training step fed to the c2f / SH-degree schedules (degree 3, full temporal table)
+LOSS_MODE = os.environ.get("EMD_BENCH_LOSS", "losses")   # "losses" (reference's image losses) | "cotangents" (stand-in)
+STEP_KEYS = ("pixels", "sky_masks", "lidar") if LOSS_MODE != "cotangents" else ("v_rgb", "v_depth", "v_alpha")
 METRIC = "fwd+bwd megapixels/s per train step"
 UNIT = "Mpix/s"
 
@@ -51,8 +55,10 @@ def workload_cfg(args):
         "smpl": f"{args.smpl_instances}x6890", "cameras": len(YAWS), "height": H_IMG, "width": W_IMG,
         "render_mode": "RGB+ED", "frames": 150, "train_step": STEP0, "seed": 0,
         "parallelism": "view-sharded data parallel (one timestep per rank), NCCL all-reduce of parameter grads",
+        "loss": "reference image losses (sky blend, L1, SSIM, sky BCE, lidar depth, entropy, smoothness) inside the step"
+                if LOSS_MODE != "cotangents" else "stand-in: seeded per-pixel cotangents",
         "l2_policy": "working set >> L2: 379 MB of parameters + 0.5 GB of per-step intermediates vs 126 MB L2; "
-                     "frame and cotangents change every step",
+                     "frame and supervision change every step",
     }
 
 
@@ -114,20 +120,32 @@ def build_inputs(args, rank, world):
     viewmats, Ks, c2w = scenes.cameras(YAWS, W_IMG, H_IMG)
     C = len(YAWS)
     g = torch.Generator().manual_seed(1234 + rank)
-    n_sets = 4  # cotangent sets cycled through so consecutive steps never reuse one
-    host = {
-        "c2w": c2w.pin_memory(), "viewmats": viewmats.pin_memory(), "Ks": Ks.pin_memory(),
-        "v_rgb": [(torch.randn(C, H_IMG, W_IMG, 3, generator=g) / (H_IMG * W_IMG)).pin_memory() for _ in range(n_sets)],
-        "v_depth": [(0.02 * torch.randn(C, H_IMG, W_IMG, 1, generator=g) / (H_IMG * W_IMG)).pin_memory() for _ in range(n_sets)],
-        "v_alpha": [(torch.randn(C, H_IMG, W_IMG, 1, generator=g) / (H_IMG * W_IMG)).pin_memory() for _ in range(n_sets)],
-    }
+    n_sets = 4  # per-step supervision sets cycled through so consecutive steps never reuse one
+    host = {"c2w": c2w.pin_memory(), "viewmats": viewmats.pin_memory(), "Ks": Ks.pin_memory()}
+    if LOSS_MODE == "cotangents":
+        host.update({
+            "v_rgb": [(torch.randn(C, H_IMG, W_IMG, 3, generator=g) / (H_IMG * W_IMG)).pin_memory() for _ in range(n_sets)],
+            "v_depth": [(0.02 * torch.randn(C, H_IMG, W_IMG, 1, generator=g) / (H_IMG * W_IMG)).pin_memory() for _ in range(n_sets)],
+            "v_alpha": [(torch.randn(C, H_IMG, W_IMG, 1, generator=g) / (H_IMG * W_IMG)).pin_memory() for _ in range(n_sets)],
+        })
+    else:
+        # what the reference's data loader hands the trainer per view (image_infos: pixels, sky_masks, lidar_depth_map)
+        yy = torch.linspace(0, 1, H_IMG)[None, :, None].expand(C, H_IMG, W_IMG)
+        host["pixels"], host["sky_masks"], host["lidar"] = [], [], []
+        for _ in range(n_sets):
+            host["pixels"].append(torch.rand(C, H_IMG, W_IMG, 3, generator=g).pin_memory())
+            host["sky_masks"].append((yy + 0.1 * torch.randn(C, H_IMG, W_IMG, generator=g) < 0.3).float().pin_memory())
+            lidar = 2.0 + 70.0 * torch.rand(C, H_IMG, W_IMG, generator=g)
+            lidar[torch.rand(C, H_IMG, W_IMG, generator=g) < 0.9] = 0.0          # ~10 % of the pixels carry a lidar return
+            host["lidar"].append(lidar.pin_memory())
+        host["rgb_sky"] = torch.rand(C, H_IMG, W_IMG, 3, generator=g)             # sky model output (model side, resident)
     return (bg, rigid, smpl), host
 
 
 def run_ours(args):
     import torch.distributed as dist
 
-    from emd_b200 import _C, dist as D, pipeline as P
+    from emd_b200 import _C, dist as D, losses as LS, optim as OPT, pipeline as P
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -154,10 +172,12 @@ def run_ours(args):
     C = len(YAWS)
     cam_centers = host["c2w"][:, :3, 3].tolist()
     n_frames = 150
-    n_sets = len(host["v_rgb"])
+    n_sets = len(host[STEP_KEYS[0]])
+    loss_cfg = LS.ImageLossConfig.omnire(step=STEP0)
 
     # device-resident copies for the `value` leg (inputs already in HBM)
     dev_in = {k: (v.to(dev) if isinstance(v, torch.Tensor) else [x.to(dev) for x in v]) for k, v in host.items()}
+    rgb_sky = dev_in["rgb_sky"].requires_grad_(True) if "rgb_sky" in dev_in else None
     loss_host = torch.zeros(1).pin_memory()
     copy_stream = torch.cuda.Stream(device=dev)
     stats = {}
@@ -170,7 +190,7 @@ def run_ours(args):
         s = i % n_sets
         main = torch.cuda.current_stream()
         with torch.cuda.stream(copy_stream):
-            t = [host[k][s].to(dev, non_blocking=True) for k in ("v_rgb", "v_depth", "v_alpha")]
+            t = [host[k][s].to(dev, non_blocking=True) for k in STEP_KEYS]
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         for t_ in t:
@@ -186,18 +206,28 @@ def run_ours(args):
             vm = host["viewmats"].to(dev, non_blocking=True)
             if i not in prefetched:
                 prefetch(i)
-            (v_rgb, v_d, v_a), copied = prefetched.pop(i)
+            sup, copied = prefetched.pop(i)
         else:
             c2w, Ks, vm = dev_in["c2w"], dev_in["Ks"], dev_in["viewmats"]
-            v_rgb, v_d, v_a = dev_in["v_rgb"][s], dev_in["v_depth"][s], dev_in["v_alpha"][s]
+            sup = [dev_in[k][s] for k in STEP_KEYS]
         for p in params:
             p.grad = None
-        rgb, depth, alpha, info = scene.render(c2w, Ks, W_IMG, H_IMG, frame, STEP0, viewmats=vm, cam_centers=cam_centers)
+        if rgb_sky is not None:
+            rgb_sky.grad = None
+        if LOSS_MODE == "cotangents":
+            rgb, depth, alpha, info = scene.render(c2w, Ks, W_IMG, H_IMG, frame, STEP0, viewmats=vm, cam_centers=cam_centers)
+        else:
+            renders, alphas, info = scene.render_raw(c2w, Ks, W_IMG, H_IMG, frame, STEP0, viewmats=vm, cam_centers=cam_centers)
         if e2e:
             torch.cuda.current_stream().wait_event(copied)
-            if not last:   # next step's cotangents: issued after the forward (so the upload never sits in front of the
+            if not last:   # next step's supervision: issued after the forward (so the upload never sits in front of the
                 prefetch(i + 1)   # intersection-count readback on the copy engines) and hidden under the backward
-        loss = (rgb * v_rgb).sum() + (depth * v_d).sum() + (alpha * v_a).sum()
+        if LOSS_MODE == "cotangents":
+            loss = (rgb * sup[0]).sum() + (depth * sup[1]).sum() + (alpha * sup[2]).sum()
+        else:   # compute_losses + backward() of the reference (base.py:502-505, 518-587): total = sum of the dict
+            terms, _ = LS.image_losses_hwc(renders, alphas, sup[0], loss_cfg, rgb_sky=rgb_sky, sky_masks=sup[1],
+                                           lidar_depth_map=sup[2])
+            loss = terms.sum()
         loss.backward()
         if world > 1 and ar_mode != "none":
             stats["allreduce_early_bytes"] = reducer.early_bytes
@@ -213,14 +243,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(k_steps, e2e, first_index):
+    def timed(k_steps, e2e, first_index, fn=None):
+        fn = fn or step
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _C.launch_count()
         t0 = time.perf_counter()
         a.record()
         for i in range(k_steps):
-            step(first_index + i, e2e, last=(i == k_steps - 1))
+            fn(first_index + i, e2e, last=(i == k_steps - 1))
         b.record()
         barrier()
         t1 = time.perf_counter()
@@ -251,11 +282,23 @@ def run_ours(args):
         barrier()
     kern = prof.result()
 
+    # the same step followed by the optimizer: fused Adam over every parameter, 1/world folded in
+    opt = OPT.FusedAdam([{"params": params}], lr=1e-7, eps=1e-15)
+
+    def step_opt(i, e2e, last=False):
+        loss = step(i, e2e, last)
+        opt.step(grad_scale=1.0 / world)
+        return loss
+
+    for i in range(3):
+        step_opt(i, False)
+    ms_opt, launches_opt, _, _ = timed(args.steps, False, args.warmup + 3 * args.steps, fn=step_opt)
+
     pix = C * H_IMG * W_IMG
     ms_step = ms_dev / args.steps
     value = world * pix / (ms_step * 1e-3) / 1e6
     e2e_value = world * pix / (ms_e2e / args.steps * 1e-3) / 1e6
-    h2d = sum(host[k].numel() * 4 for k in ("c2w", "Ks", "viewmats")) + sum(host[k][0].numel() * 4 for k in ("v_rgb", "v_depth", "v_alpha"))
+    h2d = sum(host[k].numel() * 4 for k in ("c2w", "Ks", "viewmats")) + sum(host[k][0].numel() * 4 for k in STEP_KEYS)
 
     # dominant kernel: raster backward.  Algorithmic work = blended-or-tested pixel-Gaussian pairs.
     info = stats["info"]
@@ -309,9 +352,12 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_cfg(args),
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / args.steps, 4),
-                "note": "per step: H2D of camera matrices + per-pixel RGB/depth/alpha cotangents from pinned memory "
-                        "(cotangents prefetched one step ahead on a side stream, inside the timed region), D2H of the loss; Gaussian parameters "
-                        "are model state resident in HBM"},
+                "note": "per step: H2D of camera matrices + that step's supervision (" + ", ".join(STEP_KEYS) + ") from pinned "
+                        "memory (prefetched one step ahead on a side stream, inside the timed region), D2H of the loss; "
+                        "Gaussian parameters and the sky image are model state resident in HBM"},
+        "with_optimizer": {"value": round(world * pix / (ms_opt / args.steps * 1e-3) / 1e6, 2), "unit": UNIT,
+                           "ms_per_step": round(ms_opt / args.steps, 4), "gpu_launches_per_step": launches_opt / args.steps,
+                           "note": "same step + fused Adam (emd_adam_step) over all parameters; reported beside the fwd+bwd metric"},
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
         "n_isects_per_step": P_is, "allreduce_bytes_per_step": stats.get("allreduce_bytes", 0),
         "allreduce_bytes_issued_during_backward": stats.get("allreduce_early_bytes", 0), "fwd_ms_per_frame": None, "clocks": clocks, "roofline": roofline,

@@ -11,14 +11,15 @@
 #include "common.cuh"
 #include "loss_math.cuh"
 
-constexpr int LT = 16;                     // tile edge (pixels); 256 threads, one pixel each
-constexpr int LHALO = LT + 2 * SSIM_R;     // 26
-constexpr int LPITCH = LHALO + 1;          // smem row pitch of the halo tiles
-constexpr int LOSS_THREADS = LT * LT;
+constexpr int LTX = 32, LTY = 16;                       // tile (pixels); 512 threads, one pixel each
+constexpr int LHX = LTX + 2 * SSIM_R, LHY = LTY + 2 * SSIM_R;   // 42 x 26 halo tile
+constexpr int LPITCH = LHX + 1;                         // smem row pitch of the halo tiles
+constexpr int LOSS_THREADS = LTX * LTY;
 
 struct LossArgs {
     const float *rgb, *depth, *alpha, *sky, *gt, *valid_mask, *sky_mask, *lidar;
     int C, H, W, tiles_x, tiles_y;
+    int packed4;             // renders are [.,.,.,4] with the depth in channel 3: one 16-byte load per pixel
     EmdImageLossConfig cfg;
     float win[EMD_SSIM_TAPS];
     // forward outputs / backward inputs
@@ -31,19 +32,35 @@ struct LossArgs {
     float *v_rgb, *v_depth, *v_alpha, *v_sky;
 };
 
-// predicted (blended, masked) and ground-truth (masked) value of channel ch at pixel (y, x) of view c; (0, 0) outside
-__device__ __forceinline__ void loss_load_pg(const LossArgs& A, int c, int y, int x, int ch, float& p, float& g) {
-    p = 0.0f;
-    g = 0.0f;
-    if (y < 0 || y >= A.H || x < 0 || x >= A.W) return;
-    const int64_t pix = (int64_t)y * A.W + x;
+// one pixel's inputs of the colour path
+struct LossPixel {
+    float rgb[3], sky[3], gt[3], alpha, valid, depth;
+};
+
+__device__ __forceinline__ void loss_load_pixel(const LossArgs& A, int c, int64_t pix, LossPixel& P) {
     const int64_t vpix = (int64_t)c * A.H * A.W + pix;
-    const float valid = A.valid_mask ? __ldg(A.valid_mask + vpix) : 1.0f;
-    const float rg = __ldg(A.rgb + c * A.cfg.rgb_vs + pix * A.cfg.rgb_ps + ch * A.cfg.rgb_cs);
-    const float al = A.sky ? __ldg(A.alpha + vpix) : 0.0f;
-    const float sk = A.sky ? __ldg(A.sky + c * A.cfg.sky_vs + pix * A.cfg.sky_ps + ch * A.cfg.sky_cs) : 0.0f;
-    p = loss_blend(rg, al, sk, A.sky != nullptr, A.cfg.blend).p * valid;
-    g = __ldg(A.gt + c * A.cfg.gt_vs + pix * A.cfg.gt_ps + ch * A.cfg.gt_cs) * valid;
+    P.valid = A.valid_mask ? __ldg(A.valid_mask + vpix) : 1.0f;
+    P.alpha = __ldg(A.alpha + vpix);
+    P.depth = 0.0f;
+    if (A.packed4) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(A.rgb + c * A.cfg.rgb_vs) + pix);
+        P.rgb[0] = r.x; P.rgb[1] = r.y; P.rgb[2] = r.z; P.depth = r.w;
+    } else {
+        const float* r = A.rgb + c * A.cfg.rgb_vs + pix * A.cfg.rgb_ps;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) P.rgb[ch] = __ldg(r + ch * A.cfg.rgb_cs);
+        if (A.depth) P.depth = __ldg(A.depth + c * A.cfg.depth_vs + pix * A.cfg.depth_ps);
+    }
+    const float* g = A.gt + c * A.cfg.gt_vs + pix * A.cfg.gt_ps;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) P.gt[ch] = __ldg(g + ch * A.cfg.gt_cs);
+    if (A.sky) {
+        const float* k = A.sky + c * A.cfg.sky_vs + pix * A.cfg.sky_ps;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) P.sky[ch] = __ldg(k + ch * A.cfg.sky_cs);
+    } else {
+        P.sky[0] = P.sky[1] = P.sky[2] = 0.0f;
+    }
 }
 
 __device__ __forceinline__ void loss_load_gt3(const LossArgs& A, int c, int y, int x, float out[3]) {
@@ -69,38 +86,53 @@ __device__ __forceinline__ bool ssim_in_map(const LossArgs& A, int y, int x) {
     return y >= SSIM_R && y < A.H - SSIM_R && x >= SSIM_R && x < A.W - SSIM_R;
 }
 
-__global__ void __launch_bounds__(LOSS_THREADS) image_loss_fwd_kernel(const __grid_constant__ LossArgs A) {
-    __shared__ float sP[LHALO][LPITCH], sG[LHALO][LPITCH];
-    __shared__ float sH[5][LHALO][LT];
+__global__ void __launch_bounds__(LOSS_THREADS, 2) image_loss_fwd_kernel(const __grid_constant__ LossArgs A) {
+    __shared__ float sP[3][LHY][LPITCH], sG[3][LHY][LPITCH];     // predicted / ground-truth colour of the halo tile
+    __shared__ float sH[5][LHY][LTX];                            // row-filtered moments of one channel
     __shared__ float sRed[LOSS_THREADS / 32][EMD_LOSS_SUMS];
-    const int tid = threadIdx.x, tx = tid % LT, ty = tid / LT;
+    const int tid = threadIdx.x, tx = tid % LTX, ty = tid / LTX;
     const int c = blockIdx.z;
-    const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
+    const int x0 = blockIdx.x * LTX, y0 = blockIdx.y * LTY;
     const int x = x0 + tx, y = y0 + ty;
     const bool inside = x < A.W && y < A.H;
     const int64_t pix = (int64_t)y * A.W + x;
     const int64_t vpix = (int64_t)c * A.H * A.W + pix;
+    const bool has_sky = A.sky != nullptr;
     float acc[EMD_LOSS_SUMS];
 #pragma unroll
     for (int k = 0; k < EMD_LOSS_SUMS; ++k) acc[k] = 0.0f;
 
-    // ---- SSIM, one colour channel at a time (the halo tile also yields the thread's own (p, g) for the L1 term) ----
+    // ---- halo tile: blended + masked prediction and masked ground truth, all three channels, one visit per pixel ----
+    for (int i = tid; i < LHY * LHX; i += LOSS_THREADS) {
+        const int r = i / LHX, q = i % LHX;
+        const int yy = y0 + r - SSIM_R, xx = x0 + q - SSIM_R;
+        float p[3] = {0.f, 0.f, 0.f}, g[3] = {0.f, 0.f, 0.f};
+        if (yy >= 0 && yy < A.H && xx >= 0 && xx < A.W) {
+            LossPixel P;
+            loss_load_pixel(A, c, (int64_t)yy * A.W + xx, P);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                p[ch] = loss_blend(P.rgb[ch], P.alpha, P.sky[ch], has_sky, A.cfg.blend).p * P.valid;
+                g[ch] = P.gt[ch] * P.valid;
+            }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            sP[ch][r][q] = p[ch];
+            sG[ch][r][q] = g[ch];
+        }
+    }
+    __syncthreads();
+
+    // ---- SSIM: separable 11-tap moments, one channel at a time --------------------------------------------------------
     const bool in_map = ssim_in_map(A, y, x);
     for (int ch = 0; ch < 3; ++ch) {
-        for (int i = tid; i < LHALO * LHALO; i += LOSS_THREADS) {
-            const int r = i / LHALO, q = i % LHALO;
-            float p, g;
-            loss_load_pg(A, c, y0 + r - SSIM_R, x0 + q - SSIM_R, ch, p, g);
-            sP[r][q] = p;
-            sG[r][q] = g;
-        }
-        __syncthreads();
-        for (int i = tid; i < LHALO * LT; i += LOSS_THREADS) {
-            const int r = i / LT, q = i % LT;
+        for (int i = tid; i < LHY * LTX; i += LOSS_THREADS) {
+            const int r = i / LTX, q = i % LTX;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
 #pragma unroll
             for (int k = 0; k < EMD_SSIM_TAPS; ++k) {
-                const float w = A.win[k], p = sP[r][q + k], g = sG[r][q + k];
+                const float w = A.win[k], p = sP[ch][r][q + k], g = sG[ch][r][q + k];
                 const float wp = w * p, wg = w * g;
                 a0 += wp;
                 a1 += wg;
@@ -112,7 +144,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) image_loss_fwd_kernel(const __gr
         }
         __syncthreads();
         if (inside) {
-            acc[0] += fabsf(sG[ty + SSIM_R][tx + SSIM_R] - sP[ty + SSIM_R][tx + SSIM_R]);
+            acc[0] += fabsf(sG[ch][ty + SSIM_R][tx + SSIM_R] - sP[ch][ty + SSIM_R][tx + SSIM_R]);
             float m[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < EMD_SSIM_TAPS; ++k) {
@@ -242,12 +274,12 @@ __global__ void __launch_bounds__(256) image_loss_finalize_kernel(const __grid_c
     }
 }
 
-__global__ void __launch_bounds__(LOSS_THREADS) image_loss_bwd_kernel(const __grid_constant__ LossArgs A) {
-    __shared__ float sD[3][LHALO][LPITCH];
-    __shared__ float sH[3][LHALO][LT];
-    const int tid = threadIdx.x, tx = tid % LT, ty = tid / LT;
+__global__ void __launch_bounds__(LOSS_THREADS, 2) image_loss_bwd_kernel(const __grid_constant__ LossArgs A) {
+    __shared__ float sD[3][LHY][LPITCH];
+    __shared__ float sH[3][LHY][LTX];
+    const int tid = threadIdx.x, tx = tid % LTX, ty = tid / LTX;
     const int c = blockIdx.z;
-    const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
+    const int x0 = blockIdx.x * LTX, y0 = blockIdx.y * LTY;
     const int x = x0 + tx, y = y0 + ty;
     const bool inside = x < A.W && y < A.H;
     const int64_t HW = (int64_t)A.H * A.W;
@@ -255,6 +287,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) image_loss_bwd_kernel(const __gr
     const int64_t vpix = (int64_t)c * HW + pix;
     const LossNorm n = loss_norm(A);
     const EmdImageLossConfig& g = A.cfg;
+    const bool has_sky = A.sky != nullptr;
     const float* vt = A.v_terms + c * EMD_LOSS_TERMS;
     const float g_l1 = (float)(__ldg(vt + 0) * g.w_l1 / n.l1);
     const float g_ss = (float)(-(double)__ldg(vt + 1) * g.w_ssim / n.ssim);
@@ -265,15 +298,14 @@ __global__ void __launch_bounds__(LOSS_THREADS) image_loss_bwd_kernel(const __gr
     const float g_sx = (float)(__ldg(vt + 5) * g.w_smooth / n.sx);
     const float g_sy = (float)(__ldg(vt + 5) * g.w_smooth / n.sy);
 
-    float valid = 1.0f, al = 0.0f, d_alpha = 0.0f;
-    if (inside) {
-        valid = A.valid_mask ? __ldg(A.valid_mask + vpix) : 1.0f;
-        al = __ldg(A.alpha + vpix);
-    }
+    LossPixel P;
+    P.valid = 1.0f; P.alpha = 0.0f; P.depth = 0.0f;
+    if (inside) loss_load_pixel(A, c, pix, P);
+    float d_alpha = 0.0f, v_rgb[3] = {0.f, 0.f, 0.f};
     for (int ch = 0; ch < 3; ++ch) {
         const float* maps = A.ssim_maps + (((int64_t)c * 3 + ch) * 3) * HW;
-        for (int i = tid; i < LHALO * LHALO; i += LOSS_THREADS) {
-            const int r = i / LHALO, q = i % LHALO;
+        for (int i = tid; i < LHY * LHX; i += LOSS_THREADS) {
+            const int r = i / LHX, q = i % LHX;
             const int yy = y0 + r - SSIM_R, xx = x0 + q - SSIM_R;
             const bool ok = yy >= 0 && yy < A.H && xx >= 0 && xx < A.W;      // maps are zero outside the SSIM map region
             const int64_t o = (int64_t)yy * A.W + xx;
@@ -282,8 +314,8 @@ __global__ void __launch_bounds__(LOSS_THREADS) image_loss_bwd_kernel(const __gr
             sD[2][r][q] = ok ? __ldg(maps + 2 * HW + o) : 0.0f;
         }
         __syncthreads();
-        for (int i = tid; i < LHALO * LT; i += LOSS_THREADS) {
-            const int r = i / LT, q = i % LT;
+        for (int i = tid; i < LHY * LTX; i += LOSS_THREADS) {
+            const int r = i / LTX, q = i % LTX;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
             for (int k = 0; k < EMD_SSIM_TAPS; ++k) {
@@ -304,20 +336,19 @@ __global__ void __launch_bounds__(LOSS_THREADS) image_loss_bwd_kernel(const __gr
                 s1 += w * sH[1][ty + k][tx];
                 s2 += w * sH[2][ty + k][tx];
             }
-            const float rg = __ldg(A.rgb + c * g.rgb_vs + pix * g.rgb_ps + ch * g.rgb_cs);
-            const float sk = A.sky ? __ldg(A.sky + c * g.sky_vs + pix * g.sky_ps + ch * g.sky_cs) : 0.0f;
-            const LossBlend b = loss_blend(rg, al, sk, A.sky != nullptr, g.blend);
-            const float p = b.p * valid;
-            const float gt = __ldg(A.gt + c * g.gt_vs + pix * g.gt_ps + ch * g.gt_cs) * valid;
+            const LossBlend b = loss_blend(P.rgb[ch], P.alpha, P.sky[ch], has_sky, g.blend);
+            const float p = b.p * P.valid;
+            const float gt = P.gt[ch] * P.valid;
             const float dp = g_l1 * loss_sign(p - gt) + g_ss * (s0 + 2.0f * p * s1 + gt * s2);
-            const float db = dp * valid;
-            A.v_rgb[c * g.rgb_vs + pix * g.rgb_ps + ch * g.rgb_cs] = db * b.d_rgb;
+            const float db = dp * P.valid;
+            v_rgb[ch] = db * b.d_rgb;
             d_alpha += db * b.d_alpha;
             if (A.v_sky) A.v_sky[c * g.sky_vs + pix * g.sky_ps + ch * g.sky_cs] = db * b.d_sky;
         }
-        __syncthreads();
+        // the next channel's loads overwrite sD only: sH is rewritten after the next barrier
     }
     if (!inside) return;
+    const float valid = P.valid, al = P.alpha;
     if (A.sky_mask && g.w_opacity != 0.f) {
         const float t = (1.0f - __ldg(A.sky_mask + vpix)) * valid;
         float l, d;
@@ -330,9 +361,9 @@ __global__ void __launch_bounds__(LOSS_THREADS) image_loss_bwd_kernel(const __gr
         d_alpha += g_en * d;
     }
     A.v_alpha[vpix] = d_alpha;
+    float v = 0.0f;
     if (A.depth) {
-        const float dep = loss_load_depth(A, c, y, x);
-        float v = 0.0f;
+        const float dep = P.depth;
         if (A.lidar && g.w_depth != 0.f) {
             const float li = __ldg(A.lidar + vpix);
             const float hit = loss_hit(A, vpix, li, valid);
@@ -341,28 +372,33 @@ __global__ void __launch_bounds__(LOSS_THREADS) image_loss_bwd_kernel(const __gr
         }
         if (g.w_smooth != 0.f) {
             const float id = loss_inv_depth(dep);
-            float g0[3], g1[3];
-            loss_load_gt3(A, c, y, x, g0);
+            float g1[3];
             float did = 0.0f;
             if (x + 1 < A.W) {
                 loss_load_gt3(A, c, y, x + 1, g1);
-                did += g_sx * loss_sign(id - loss_inv_depth(loss_load_depth(A, c, y, x + 1))) * loss_edge_weight(g0, g1);
+                did += g_sx * loss_sign(id - loss_inv_depth(loss_load_depth(A, c, y, x + 1))) * loss_edge_weight(P.gt, g1);
             }
             if (x > 0) {
                 loss_load_gt3(A, c, y, x - 1, g1);
-                did -= g_sx * loss_sign(loss_inv_depth(loss_load_depth(A, c, y, x - 1)) - id) * loss_edge_weight(g1, g0);
+                did -= g_sx * loss_sign(loss_inv_depth(loss_load_depth(A, c, y, x - 1)) - id) * loss_edge_weight(g1, P.gt);
             }
             if (y + 1 < A.H) {
                 loss_load_gt3(A, c, y + 1, x, g1);
-                did += g_sy * loss_sign(id - loss_inv_depth(loss_load_depth(A, c, y + 1, x))) * loss_edge_weight(g0, g1);
+                did += g_sy * loss_sign(id - loss_inv_depth(loss_load_depth(A, c, y + 1, x))) * loss_edge_weight(P.gt, g1);
             }
             if (y > 0) {
                 loss_load_gt3(A, c, y - 1, x, g1);
-                did -= g_sy * loss_sign(loss_inv_depth(loss_load_depth(A, c, y - 1, x)) - id) * loss_edge_weight(g1, g0);
+                did -= g_sy * loss_sign(loss_inv_depth(loss_load_depth(A, c, y - 1, x)) - id) * loss_edge_weight(g1, P.gt);
             }
             v += did * (-id * id);
         }
-        A.v_depth[c * g.depth_vs + pix * g.depth_ps] = v;
+    }
+    if (A.packed4) {
+        reinterpret_cast<float4*>(A.v_rgb + c * g.rgb_vs)[pix] = make_float4(v_rgb[0], v_rgb[1], v_rgb[2], v);
+    } else {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) A.v_rgb[c * g.rgb_vs + pix * g.rgb_ps + ch * g.rgb_cs] = v_rgb[ch];
+        if (A.depth) A.v_depth[c * g.depth_vs + pix * g.depth_ps] = v;
     }
 }
 
@@ -382,8 +418,10 @@ static int loss_fill_args(LossArgs& A, const char* what, const float* rgb, const
     A.rgb = rgb; A.depth = depth; A.alpha = alpha; A.sky = sky; A.gt = gt;
     A.valid_mask = valid_mask; A.sky_mask = sky_mask; A.lidar = lidar;
     A.C = C; A.H = H; A.W = W;
-    A.tiles_x = (int)emd_cdiv(W, LT);
-    A.tiles_y = (int)emd_cdiv(H, LT);
+    A.tiles_x = (int)emd_cdiv(W, LTX);
+    A.tiles_y = (int)emd_cdiv(H, LTY);
+    A.packed4 = depth && depth == rgb + 3 && cfg->rgb_ps == 4 && cfg->rgb_cs == 1 && cfg->depth_ps == 4 &&
+                cfg->depth_vs == cfg->rgb_vs && cfg->rgb_vs % 4 == 0 && emd_aligned(rgb, 16);
     A.cfg = *cfg;
     for (int k = 0; k < EMD_SSIM_TAPS; ++k) A.win[k] = window[k];
     A.ssim_maps = nullptr; A.partials = nullptr; A.sums = nullptr; A.terms = nullptr;
@@ -393,7 +431,7 @@ static int loss_fill_args(LossArgs& A, const char* what, const float* rgb, const
 
 // floats of the `partials` scratch buffer
 extern "C" int64_t emd_image_loss_partials_floats(int C, int H, int W) {
-    return (int64_t)C * emd_cdiv(W, LT) * emd_cdiv(H, LT) * EMD_LOSS_SUMS;
+    return (int64_t)C * emd_cdiv(W, LTX) * emd_cdiv(H, LTY) * EMD_LOSS_SUMS;
 }
 
 // Forward.  rgb / depth / gt / sky are addressed through the strides in cfg; alpha, valid_mask, sky_mask, lidar are dense
@@ -437,6 +475,7 @@ extern "C" int emd_image_loss_bwd(const float* rgb, const float* depth, const fl
     A.sums = const_cast<float*>(sums);
     A.v_terms = v_terms;
     A.v_rgb = v_rgb; A.v_depth = v_depth; A.v_alpha = v_alpha; A.v_sky = v_sky;
+    A.packed4 = A.packed4 && v_depth == v_rgb + 3 && emd_aligned(v_rgb, 16);
     const dim3 grid(A.tiles_x, A.tiles_y, C);
     EMD_LAUNCH(EK_LOSS_BWD, stream, (image_loss_bwd_kernel<<<grid, LOSS_THREADS, 0, stream>>>(A)));
     EMD_CHECK_LAUNCH("emd_image_loss_bwd");

@@ -120,6 +120,16 @@ class StreetScene:
         ``colors_after_projection`` only changes the ORDER of two independent stages (SH colours after the projection
         and tile binning instead of before): results are identical; the backward pass then produces the
         SH-coefficient gradient first (see ``dist.GradReducer``)."""
+        renders, alphas, info = self.render_raw(camtoworlds, Ks, width, height, frame, step, viewmats, cam_centers,
+                                                near_plane, far_plane, absgrad, colors_after_projection)
+        rgb, depth = torch.split(renders, [3, 1], dim=-1)
+        return torch.clamp(rgb, max=1.0), depth, alphas, info
+
+    def render_raw(self, camtoworlds: Tensor, Ks: Tensor, width: int, height: int, frame: int, step: int,
+                   viewmats: Optional[Tensor] = None, cam_centers=None, near_plane: float = 0.1, far_plane: float = 1e10,
+                   absgrad: bool = True, colors_after_projection: bool = True):
+        """The rasterizer's own outputs ``(renders[C,H,W,4], alphas[C,H,W,1], info)`` (base.py:393-408), which
+        ``emd_b200.losses.omnire_image_losses`` consumes directly (the clamp / split of base.py:412-418 is fused there)."""
         if cam_centers is None:
             cam_centers = camtoworlds[:, :3, 3].detach().cpu().tolist()
         if viewmats is None:
@@ -135,8 +145,7 @@ class StreetScene:
             colors=colors, viewmats=viewmats, Ks=Ks, width=width, height=height, packed=False, absgrad=absgrad,
             sparse_grad=False, rasterize_mode="classic", near_plane=near_plane, far_plane=far_plane,
             render_mode="RGB+ED", radius_clip=0.0)
-        rgb, depth = torch.split(renders, [3, 1], dim=-1)
-        return torch.clamp(rgb, max=1.0), depth, alphas, info
+        return renders, alphas, info
 
 
 def make_street_scene(n_bg: int = 1_300_000, rigid_instances: int = 30, pts_per_rigid: int = 5000,
