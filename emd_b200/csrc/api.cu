@@ -51,7 +51,8 @@ static const char* kKernelNames[EK_COUNT] = {
     "projection_fwd", "projection_bwd", "scan", "isect_emit", "sort_hist", "sort_scatter", "isect_offsets",
     "raster_pack", "raster_fwd", "raster_bwd", "raster_gather", "sh_fwd", "sh_bwd", "activate_fwd", "activate_bwd",
     "rigid_fwd", "rigid_bwd", "smpl_fwd", "smpl_bwd", "mlp_fwd", "mlp_bwd", "dg_preprocess_fwd", "dg_preprocess_bwd",
-    "hexplane_fwd", "hexplane_bwd", "adam", "image_loss_fwd", "image_loss_bwd", "misc"};
+    "hexplane_fwd", "hexplane_bwd", "adam", "image_loss_fwd", "image_loss_bwd", "voxel_lbs_fwd", "voxel_lbs_bwd",
+    "dense_fwd", "dense_bwd", "deform_input", "misc"};
 
 void emd_prof_begin(int id, cudaStream_t stream) {
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -40,7 +40,8 @@ enum EmdKernelId {
     EK_PROJ_FWD = 0, EK_PROJ_BWD, EK_SCAN, EK_ISECT_EMIT, EK_SORT_HIST, EK_SORT_SCATTER, EK_ISECT_OFFSETS,
     EK_RASTER_PACK, EK_RASTER_FWD, EK_RASTER_BWD, EK_RASTER_GATHER, EK_SH_FWD, EK_SH_BWD, EK_ACT_FWD, EK_ACT_BWD,
     EK_RIGID_FWD, EK_RIGID_BWD, EK_SMPL_FWD, EK_SMPL_BWD, EK_MLP_FWD, EK_MLP_BWD, EK_DG_PREP_FWD, EK_DG_PREP_BWD,
-    EK_HEX_FWD, EK_HEX_BWD, EK_ADAM, EK_LOSS_FWD, EK_LOSS_BWD, EK_MISC, EK_COUNT
+    EK_HEX_FWD, EK_HEX_BWD, EK_ADAM, EK_LOSS_FWD, EK_LOSS_BWD, EK_VOX_FWD, EK_VOX_BWD, EK_DENSE_FWD, EK_DENSE_BWD,
+    EK_DEFORM_IN, EK_MISC, EK_COUNT
 };
 void emd_prof_begin(int id, cudaStream_t stream);
 void emd_prof_end(int id, cudaStream_t stream);

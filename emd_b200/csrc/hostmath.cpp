@@ -206,6 +206,110 @@ extern "C" void emd_host_hexplane(const float* planes, const int64_t* plane_offs
     }
 }
 
+// ---- Voxel LBS weights (voxel_math.cuh): scalar host loop over the same tap arithmetic the kernels use -----------
+#include "voxel_math.cuh"
+
+// grids channel-last [B,D,H,W,J]; out[B,V,J]; when v_out != NULL also the VJP: v_corr (added into), v_xc[B,V,3]
+extern "C" void emd_host_voxel_lbs(const float* base, const float* corr, const float* offset, const float* scale, float ratio,
+                                   int ratio_dim, int B, int D, int H, int W, int J, const float* xc, int64_t V, float* out,
+                                   const float* v_out, float* v_corr, float* v_xc) {
+    VoxGeom G;
+    G.D = D; G.H = H; G.W = W; G.J = J; G.ratio = ratio; G.ratio_dim = ratio_dim;
+    for (int64_t n = 0; n < (int64_t)B * V; ++n) {
+        const int b = (int)(n / V);
+        VoxTap T;
+        vox_tap(G, xc + n * 3, offset + b * 3, scale[b], T);
+        float gx[3] = {0.f, 0.f, 0.f};
+        for (int c = 0; c < J; ++c) {
+            float acc = 0.f;
+            for (int k = 0; k < 8; ++k) {
+                const int64_t e = vox_corner_index(G, T, b, k) * J + c;
+                const float g = base[e] + (corr ? corr[e] : 0.f);
+                const float w = vox_corner_weight(T, k);
+                acc += w * g;
+                if (v_out) {
+                    const float go = v_out[n * J + c];
+                    if (v_corr) v_corr[e] += go * w;
+                    for (int a = 0; a < 3; ++a) gx[a] += vox_corner_dweight(T, a, k) * (go * g);
+                }
+            }
+            out[n * J + c] = acc;
+        }
+        if (v_out && v_xc)
+            for (int a = 0; a < 3; ++a) v_xc[n * 3 + a] = gx[a] * vox_coord_chain(G, T, a, scale[b]);
+    }
+}
+
+// ---- strided GEMM of the DeformableNodes network (dense_math.cuh): the kernel's tile logic run thread by thread ------
+#include <vector>
+#include "dense_math.cuh"
+
+template <bool TA, bool TB>
+static void host_sgemm(const GemmArgs& g, int splits) {
+    static float As[DG_BK][DG_PITCH], Bs[DG_BK][DG_PITCH];
+    static float ra[DG_THREADS][8], rb[DG_THREADS][8], acc[DG_THREADS][8][8];
+    for (int64_t bz = 0; bz < splits; ++bz)
+        for (int64_t by = 0; by < dg_cdiv(g.N, DG_BN); ++by)
+            for (int64_t bx = 0; bx < dg_cdiv(g.M, DG_BM); ++bx) {
+                const int64_t m0 = bx * DG_BM, n0 = by * DG_BN;
+                const int64_t kbeg = bz * g.k_per_split;
+                const int64_t kend = g.K < kbeg + g.k_per_split ? g.K : kbeg + g.k_per_split;
+                float* C = g.C + bz * g.split_stride;
+                for (int t = 0; t < DG_THREADS; ++t)
+                    for (int i = 0; i < 8; ++i)
+                        for (int j = 0; j < 8; ++j) acc[t][i][j] = 0.f;
+                if (kbeg < kend)
+                    for (int t = 0; t < DG_THREADS; ++t) gemm_load<TA, TB>(g, t, m0, n0, kbeg, kend, ra[t], rb[t]);
+                for (int64_t k0 = kbeg; k0 < kend; k0 += DG_BK) {
+                    for (int t = 0; t < DG_THREADS; ++t) gemm_store<TA, TB>(t, ra[t], rb[t], As, Bs);
+                    if (k0 + DG_BK < kend)
+                        for (int t = 0; t < DG_THREADS; ++t) gemm_load<TA, TB>(g, t, m0, n0, k0 + DG_BK, kend, ra[t], rb[t]);
+                    for (int t = 0; t < DG_THREADS; ++t) gemm_compute(t, As, Bs, acc[t]);
+                }
+                for (int t = 0; t < DG_THREADS; ++t) gemm_epilogue(g, t, m0, n0, C, acc[t]);
+            }
+}
+
+extern "C" void emd_host_dense_fwd(const float* X, int64_t ldx, const float* W, const float* b, int64_t M, int K, int Nout,
+                                   int relu_out, float* Y, int64_t ldy) {
+    host_sgemm<false, true>(dense_fwd_args(X, ldx, W, b, M, K, Nout, relu_out, Y, ldy), 1);
+}
+
+extern "C" void emd_host_dense_bwd(const float* X, int64_t ldx, const float* W, const float* dZ, int64_t lddz, int64_t M, int K,
+                                   int Nout, float* dX, int64_t lddx, int col0, int ncols, const float* mask, int64_t ldmask,
+                                   float* dW, float* db) {
+    if (dX) host_sgemm<false, false>(dense_dgrad_args(W, dZ, lddz, M, K, Nout, dX, lddx, col0, ncols, mask, ldmask), 1);
+    const DenseSplit s = dense_split(M, K, Nout);
+    if (dW) {
+        std::vector<float> wpart((size_t)s.splits * Nout * K + 4, -777.0f);   // poisoned: every element must be written
+        float* wp = wpart.data();
+        while (!dg_aligned16(wp)) ++wp;
+        host_sgemm<true, false>(dense_wgrad_args(X, ldx, dZ, lddz, M, K, Nout, s, wp), s.splits);
+        const int64_t n = (int64_t)Nout * K;
+        for (int64_t i = 0; i < n; ++i) {
+            float a = 0.f;
+            for (int z = 0; z < s.splits; ++z) a += wp[(int64_t)z * n + i];
+            dW[i] = a;
+        }
+    }
+    if (db) {
+        std::vector<float> bpart((size_t)s.col_chunks * Nout);
+        for (int ch = 0; ch < s.col_chunks; ++ch) {
+            const int64_t r0 = ch * s.rows_per_chunk, r1 = M < r0 + s.rows_per_chunk ? M : r0 + s.rows_per_chunk;
+            for (int c = 0; c < Nout; ++c) {
+                float a = 0.f;
+                for (int64_t r = r0; r < r1; ++r) a += dZ[r * lddz + c];
+                bpart[(size_t)ch * Nout + c] = a;
+            }
+        }
+        for (int c = 0; c < Nout; ++c) {
+            float a = 0.f;
+            for (int ch = 0; ch < s.col_chunks; ++ch) a += bpart[(size_t)ch * Nout + c];
+            db[c] = a;
+        }
+    }
+}
+
 // ---- Adam (adam_math.cuh) -----------------------------------------------------------------------------------
 #include "adam_math.cuh"
 

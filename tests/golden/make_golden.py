@@ -180,7 +180,7 @@ def main():
     print("golden fixtures written to", HERE)
 
 
-if __name__ == "__main__" and not any(a in sys.argv for a in ("--s3g", "--hexplane", "--losses")):
+if __name__ == "__main__" and not any(a in sys.argv for a in ("--s3g", "--hexplane", "--losses", "--modules")):
     main()
 
 
@@ -344,3 +344,58 @@ def make_losses_golden():
 
 if __name__ == "__main__" and "--losses" in sys.argv:
     make_losses_golden()
+
+
+def make_modules_golden():
+    """OmniRe/models/modules.py run on the CPU -> tests/golden/omnire_modules.npz: ``VoxelDeformer`` (weights at
+    canonical points, gradients w.r.t. the voxel correction and the points, get_tv / get_mag) and
+    ``ConditionalDeformNetwork`` (outputs and gradients w.r.t. every parameter and the condition)."""
+    _stub(["pytorch3d", "pytorch3d.ops", "nvdiffrast", "nvdiffrast.torch", "utils", "utils.geometry"])
+    M = load_file("ref_omnire_modules", f"{REF}/OmniRe/models/modules.py")
+    out = {}
+    # ---- VoxelDeformer: B = 3 instances, J = 24 bones, grid [D,H,W] = [4, 12, 10] (short axis z, as human_body.py:117-125)
+    g = torch.Generator().manual_seed(41)
+    B, V, J, res = 3, 200, 24, [4, 12, 10]
+    vtx = torch.randn(B, 150, 3, generator=g) * torch.tensor([0.35, 0.25, 0.8]) + torch.tensor([0.1, -0.05, 0.2])
+    feats = torch.softmax(torch.randn(B, 150, J, generator=g), dim=-1)
+    torch.manual_seed(1234)
+    vd = M.VoxelDeformer(vtx=vtx, vtx_features=feats, resolution_dhw=res, is_resume=True)   # random volume, no knn
+    vd.enable_voxel_correction()
+    vd.voxel_w_correction.data = 0.1 * torch.randn(vd.lbs_voxel_base.shape, generator=g)
+    lo, hi = vd.bbox[:, 0], vd.bbox[:, 1]                                                    # [B,3]
+    xc = lo[:, None] + (hi - lo)[:, None] * (torch.rand(B, V, 3, generator=g) * 1.3 - 0.15)  # ~25 % outside the box
+    xc[:, 0], xc[:, 1], xc[:, 2] = hi, lo, 0.5 * (lo + hi)
+    xc.requires_grad_(True)
+    w = vd(xc)
+    cot = torch.randn(w.shape, generator=g)
+    (w * cot).sum().backward()
+    out.update(vox_res=np.array(res), vox_base=vd.lbs_voxel_base.numpy(), vox_corr=vd.voxel_w_correction.detach().numpy(),
+               vox_offset=vd.offset.numpy(), vox_scale=vd.scale.numpy(), vox_ratio=np.array(float(vd.ratio)),
+               vox_ratio_dim=np.array(vd.ratio_dim), vox_xc=xc.detach().numpy(), vox_cot=cot.numpy(), vox_w=w.detach().numpy(),
+               vox_v_xc=xc.grad.numpy(), vox_v_corr=vd.voxel_w_correction.grad.numpy(),
+               vox_tv=vd.get_tv("dc").detach().numpy(), vox_mag=vd.get_mag("dc").detach().numpy())
+    # ---- ConditionalDeformNetwork: the config's structure (D = 8, one skip, x/t multires 10, embed_dim 16, quaternion
+    #      head, no scale head: omnire.yaml:159-166) at width 32 so the fixture stays small
+    torch.manual_seed(77)
+    net = M.ConditionalDeformNetwork(D=8, W=32, input_ch=3, embed_dim=16, x_multires=10, t_multires=10, deform_quat=True,
+                                     deform_scale=False)
+    N = 300
+    x = torch.rand(N, 3, generator=g) * 2 - 1
+    t = torch.full((N, 1), 0.4375)
+    cond = torch.rand(N, 16, generator=g).requires_grad_(True)
+    d_xyz, rot, scl = net(x, t, cond)
+    assert scl is None
+    c1, c2 = torch.randn(d_xyz.shape, generator=g), torch.randn(rot.shape, generator=g)
+    ((d_xyz * c1).sum() + (rot * c2).sum()).backward()
+    for k, v in net.state_dict().items():
+        out[f"net_sd.{k}"] = v.numpy()
+    for k, p in net.named_parameters():
+        out[f"net_grad.{k}"] = p.grad.numpy()
+    out.update(net_x=x.numpy(), net_t=t.numpy(), net_cond=cond.detach().numpy(), net_c1=c1.numpy(), net_c2=c2.numpy(),
+               net_d_xyz=d_xyz.detach().numpy(), net_rot=rot.detach().numpy(), net_v_cond=cond.grad.numpy())
+    np.savez_compressed(f"{HERE}/omnire_modules.npz", **out)
+    print("wrote omnire_modules.npz with", len(out), "arrays")
+
+
+if __name__ == "__main__" and "--modules" in sys.argv:
+    make_modules_golden()

@@ -160,3 +160,38 @@ def test_losses_golden():
           d["depth"].permute(2, 0, 1).contiguous())
     # the two window constructions (loss_utils.py:56-58 vs pytorch_msssim) agree to an ulp
     assert float((OL.gaussian_window_s3g() - OL.gaussian_window_msssim()).abs().max()) <= 2e-8
+
+
+def test_voxel_deformer_golden():
+    """oracle/voxel_deformer.py against the reference's own VoxelDeformer (weights, gradients w.r.t. the correction
+    volume and the canonical points, get_tv / get_mag)."""
+    from oracle import voxel_deformer as OV
+    z = np.load(f"{G}/omnire_modules.npz")
+    base, corr = _t(z["vox_base"]), _t(z["vox_corr"]).requires_grad_(True)
+    xc = _t(z["vox_xc"]).requires_grad_(True)
+    w = OV.voxel_weights(base + corr, _t(z["vox_offset"]), _t(z["vox_scale"]), float(z["vox_ratio"]), int(z["vox_ratio_dim"]), xc)
+    assert torch.allclose(w, _t(z["vox_w"]), atol=2e-6)
+    (w * _t(z["vox_cot"])).sum().backward()
+    assert torch.allclose(corr.grad, _t(z["vox_v_corr"]), atol=2e-6)
+    ref = _t(z["vox_v_xc"])
+    assert (xc.grad - ref).abs().max() <= 2e-5 * max(1.0, ref.abs().max().item())
+    assert (ref == 0).any() and (ref != 0).any()      # clipped and interior points are both covered
+    assert torch.allclose(OV.get_tv(corr.detach()), _t(z["vox_tv"]), rtol=1e-6)
+    assert torch.allclose(OV.get_mag(corr.detach()), _t(z["vox_mag"]), rtol=1e-6)
+
+
+def test_conditional_deform_network_golden():
+    """oracle/deform_network.py against the reference's own ConditionalDeformNetwork: outputs, gradients w.r.t. every
+    parameter and the condition (instance embedding)."""
+    from oracle import deform_network as ON
+    z = np.load(f"{G}/omnire_modules.npz")
+    sd = {k[len("net_sd."):]: _t(z[k]).requires_grad_(True) for k in z.files if k.startswith("net_sd.")}
+    cond = _t(z["net_cond"]).requires_grad_(True)
+    d_xyz, rot, scl = ON.conditional_deform_network(sd, _t(z["net_x"]), _t(z["net_t"]), cond, D=8)
+    assert scl is None
+    assert torch.allclose(d_xyz, _t(z["net_d_xyz"]), atol=1e-6) and torch.allclose(rot, _t(z["net_rot"]), atol=1e-6)
+    ((d_xyz * _t(z["net_c1"])).sum() + (rot * _t(z["net_c2"])).sum()).backward()
+    assert torch.allclose(cond.grad, _t(z["net_v_cond"]), atol=1e-6)
+    for k, p in sd.items():
+        ref = _t(z[f"net_grad.{k}"])
+        assert (p.grad - ref).abs().max() <= 1e-5 * max(1.0, ref.abs().max().item()), k

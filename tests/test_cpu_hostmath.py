@@ -243,3 +243,81 @@ def test_adam_host_math_matches_torch(hostlib, wd, scale):
         assert np.abs(m - st["exp_avg"].numpy()).max() <= 2e-6 * max(1e-30, float(st["exp_avg"].abs().max()))
         assert np.abs(v - st["exp_avg_sq"].numpy()).max() <= 2e-6 * max(1e-30, float(st["exp_avg_sq"].abs().max()))
         assert np.abs(p - ref.detach().numpy()).max() <= 5e-7 * step
+
+
+def test_voxel_lbs_host_math_matches_oracle(hostlib):
+    """voxel_math.cuh (the tap arithmetic the voxel-LBS kernels include) against the oracle on the golden case: weights,
+    correction-volume gradient, point gradient; channel-last layout in, reference layout compared."""
+    import os
+    from oracle import voxel_deformer as OV
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "omnire_modules.npz"))
+    base, corr = torch.from_numpy(z["vox_base"]), torch.from_numpy(z["vox_corr"])
+    B, J, D, H, W = base.shape
+    xc, cot = torch.from_numpy(z["vox_xc"]), torch.from_numpy(z["vox_cot"])
+    V = xc.shape[1]
+    cl = lambda v: v.permute(0, 2, 3, 4, 1).contiguous()  # noqa: E731
+    ratio_dim = int(z["vox_ratio_dim"]) % 3
+    out = np.zeros((B, V, J), np.float32); v_corr = np.zeros((B, D, H, W, J), np.float32); v_xc = np.zeros((B, V, 3), np.float32)
+    f = hostlib.emd_host_voxel_lbs
+    f.argtypes = [P] * 4 + [ctypes.c_float] + [ctypes.c_int] * 6 + [P, ctypes.c_int64] + [P] * 4
+    f.restype = None
+    off, scl = torch.from_numpy(z["vox_offset"]).reshape(B, 3), torch.from_numpy(z["vox_scale"]).reshape(B)
+    f(_fp(cl(base)), _fp(cl(corr)), _fp(off), _fp(scl), float(z["vox_ratio"]), ratio_dim, B, D, H, W, J, _fp(xc), V,
+      out.ctypes.data_as(P), _fp(cot), v_corr.ctypes.data_as(P), v_xc.ctypes.data_as(P))
+    assert np.abs(out - z["vox_w"]).max() <= 2e-6
+    assert np.abs(v_corr.transpose(0, 4, 1, 2, 3) - z["vox_v_corr"]).max() <= 2e-6
+    assert np.abs(v_xc - z["vox_v_xc"]).max() <= 2e-5 * max(1.0, np.abs(z["vox_v_xc"]).max())
+    # and against the oracle on a second volume shape with the stretch on another axis
+    g = torch.Generator().manual_seed(5)
+    B, J, D, H, W, V = 2, 8, 6, 3, 5, 64
+    base, corr = torch.randn(B, J, D, H, W, generator=g), torch.randn(B, J, D, H, W, generator=g).requires_grad_(True)
+    off, scl = torch.randn(B, 1, 3, generator=g) * 0.2, torch.rand(B, 1, 1, generator=g) + 0.5
+    xc = (torch.rand(B, V, 3, generator=g) * 2.6 - 1.3).requires_grad_(True)
+    cot = torch.randn(B, V, J, generator=g)
+    w = OV.voxel_weights(base + corr, off, scl, 2.0, -2, xc)
+    (w * cot).sum().backward()
+    out = np.zeros((B, V, J), np.float32); v_corr = np.zeros((B, D, H, W, J), np.float32); v_xc = np.zeros((B, V, 3), np.float32)
+    f(_fp(cl(base)), _fp(cl(corr)), _fp(off.reshape(B, 3)), _fp(scl.reshape(B)), 2.0, 1, B, D, H, W, J, _fp(xc), V,
+      out.ctypes.data_as(P), _fp(cot), v_corr.ctypes.data_as(P), v_xc.ctypes.data_as(P))
+    assert np.abs(out - w.detach().numpy()).max() <= 2e-6
+    assert np.abs(v_corr.transpose(0, 4, 1, 2, 3) - corr.grad.numpy()).max() <= 5e-6
+    assert np.abs(v_xc - xc.grad.numpy()).max() <= 2e-5 * max(1.0, xc.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("M,K,Nout,ldx,ldy,relu", [(300, 100, 256, 100, 256, 1), (517, 356, 256, 356, 356, 1),
+                                                    (130, 256, 7, 256, 7, 0), (1, 20, 33, 24, 40, 1)])
+def test_dense_tile_logic_matches_torch(hostlib, M, K, Nout, ldx, ldy, relu):
+    """dense_math.cuh (the per-thread tile logic of sgemm_kernel, run thread by thread on the host) against torch:
+    forward with strided operands, data gradient on a column window with the producer's ReLU mask, split weight gradient,
+    bias gradient."""
+    g = torch.Generator().manual_seed(M + K)
+    Xb = torch.randn(M, ldx, generator=g)
+    Wt, b = torch.randn(Nout, K, generator=g) / K ** 0.5, torch.randn(Nout, generator=g)
+    Yb = np.full((M, ldy), 123.0, np.float32)
+    I64, I32 = ctypes.c_int64, ctypes.c_int
+    f = hostlib.emd_host_dense_fwd
+    f.argtypes = [P, I64, P, P, I64, I32, I32, I32, P, I64]
+    f.restype = None
+    off = ldy - Nout                                   # write into the LAST Nout columns of a wider buffer
+    f(_fp(Xb), ldx, _fp(Wt), _fp(b), M, K, Nout, relu, ctypes.c_void_p(Yb.ctypes.data + 4 * off), ldy)
+    ref = Xb[:, :K] @ Wt.T + b
+    ref = torch.relu(ref) if relu else ref
+    assert np.abs(Yb[:, off:] - ref.numpy()).max() <= 2e-5
+    assert (Yb[:, :off] == 123.0).all()                # nothing outside the window is touched
+    # backward
+    dZ = torch.randn(M, Nout, generator=g)
+    col0, ncols = (K - 16, 16) if K >= 32 else (0, K)
+    mask = torch.randn(M, ncols, generator=g)
+    dX = np.full((M, ncols + 3), -5.0, np.float32)
+    dW = np.zeros((Nout, K), np.float32); db = np.zeros(Nout, np.float32)
+    fb = hostlib.emd_host_dense_bwd
+    fb.argtypes = [P, I64, P, P, I64, I64, I32, I32, P, I64, I32, I32, P, I64, P, P]
+    fb.restype = None
+    fb(_fp(Xb), ldx, _fp(Wt), _fp(dZ), Nout, M, K, Nout, dX.ctypes.data_as(P), ncols + 3, col0, ncols, _fp(mask), ncols,
+       dW.ctypes.data_as(P), db.ctypes.data_as(P))
+    ref_dX = (dZ @ Wt[:, col0:col0 + ncols]) * (mask > 0)
+    assert np.abs(dX[:, :ncols] - ref_dX.numpy()).max() <= 2e-5 * max(1.0, ref_dX.abs().max().item())
+    assert (dX[:, ncols:] == -5.0).all()
+    ref_dW = dZ.T @ Xb[:, :K]
+    assert np.abs(dW - ref_dW.numpy()).max() <= 2e-5 * max(1.0, ref_dW.abs().max().item())
+    assert np.abs(db - dZ.sum(0).numpy()).max() <= 2e-5 * max(1.0, dZ.sum(0).abs().max().item())
