@@ -51,6 +51,16 @@ _SIGS = {
     "emd_hexplane_bwd_workspace_bytes": (c_size_t, [c_int64]),
     "emd_hexplane_bwd": (c_int, [P, ctypes.POINTER(c_int64), ctypes.POINTER(c_int), c_int, c_int, ctypes.POINTER(c_float),
                                  P, P, c_int, c_int64, P, P, P, P, P, c_size_t, P]),
+    "emd_voxel_lbs_fwd": (c_int, [P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int64, P, P]),
+    "emd_voxel_lbs_bwd": (c_int, [P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int64, P, P, P, P]),
+    "emd_dense_fwd": (c_int, [P, c_int64, P, P, c_int64, c_int, c_int, c_int, P, c_int64, P]),
+    "emd_dense_bwd_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "emd_dense_bwd": (c_int, [P, c_int64, P, P, c_int64, c_int64, c_int, c_int, P, c_int64, c_int, c_int, P, c_int64, P, P,
+                              P, c_size_t, P]),
+    "emd_deform_input_fwd": (c_int, [P, P, P, P, c_float, c_int, c_int, c_int, c_int64, P, c_int64, P, c_int64, P]),
+    "emd_deform_embed_grad": (c_int, [P, P, c_int, P, P, c_int, P, P]),
+    "emd_deform_apply_fwd": (c_int, [P, P, P, c_int, c_int64, P, P, P]),
+    "emd_deform_apply_bwd": (c_int, [P, P, P, c_int, c_int64, P, P, P, P]),
     "emd_adam_max_tensors": (c_int, []),
     "emd_adam_step": (c_int, [ctypes.POINTER(P)] * 4 + [ctypes.POINTER(c_int64)] + [ctypes.POINTER(ctypes.c_double)] * 5
                       + [ctypes.POINTER(c_int64), c_int, ctypes.c_double, P]),
@@ -85,6 +95,7 @@ _SIGS = {
     "emd_smpl_reduce_width": (c_int, []),
     "emd_smpl_deform_fwd": (c_int, [P] * 12 + [c_int] * 5 + [c_float, c_int, c_int] + [P] * 5 + [P]),
     "emd_smpl_deform_bwd": (c_int, [P] * 11 + [c_int] * 5 + [c_float, c_int, c_int] + [P] * 14 + [P]),
+    "emd_smpl_weight_grad": (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P]),
     "emd_rasterize_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_int, P, P, P, P, P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
 }

@@ -115,7 +115,7 @@ extern "C" int emd_dense_bwd(const float* X, int64_t ldx, const float* W, const 
                              float* dW, float* db, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     EMD_CHECK_ARG(M >= 0 && K >= 1 && Nout >= 1 && ldx >= K && lddz >= Nout, "emd_dense_bwd: M=%lld K=%d Nout=%d ldx=%lld lddz=%lld",
                   (long long)M, K, Nout, (long long)ldx, (long long)lddz);
-    EMD_CHECK_ARG(X && W && dZ, "emd_dense_bwd: null argument");
+    EMD_CHECK_ARG(M == 0 || (X && W && dZ), "emd_dense_bwd: null argument");
     if (dX) {
         EMD_CHECK_ARG(col0 >= 0 && ncols >= 1 && col0 + ncols <= K && lddx >= ncols && (!mask || ldmask >= ncols),
                       "emd_dense_bwd: column window [%d, %d) of K=%d, lddx=%lld ldmask=%lld", col0, col0 + ncols, K,

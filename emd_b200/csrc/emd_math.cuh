@@ -491,3 +491,35 @@ EMD_HD void mat_to_quat_vjp(const float* m, const float* v_q_in, float* v_m) {
     else if (best == 2) { v_m[2] += v_num[0]; v_m[6] -= v_num[0]; v_m[3] += v_num[1]; v_m[1] += v_num[1]; v_m[5] += v_num[3]; v_m[7] += v_num[3]; }
     else { v_m[3] += v_num[0]; v_m[1] -= v_num[0]; v_m[6] += v_num[1]; v_m[2] += v_num[1]; v_m[7] += v_num[2]; v_m[5] += v_num[2]; }
 }
+
+// d loss / d W[n, :] of one skinned point (needed when the LBS weights come from the trainable voxel deformer,
+// human_body.py:174-179): T = sum_j W_j A_j, x' = T.R x + T.t, q' = normalize(mat2quat(T.R)) (x) normalize(q).
+// v_T is formed exactly as smpl_points_bwd_kernel forms it; v_W[j] = <v_T, A_j>.  A_j = [R row-major (9) | t (3)].
+EMD_HD void smpl_point_weight_grad(const float* Wn, const float* Ab, const float* x, const float* q, const float* g,
+                                   const float* vg, float* v_W) {
+    float T[12];
+    for (int k = 0; k < 12; ++k) T[k] = 0.f;
+    for (int j = 0; j < SMPL_J; ++j) {
+        const float w = Wn[j];
+        if (w == 0.f) continue;
+        for (int k = 0; k < 12; ++k) T[k] += w * Ab[j * 12 + k];
+    }
+    float vT[12];
+    vT[0] = g[0] * x[0]; vT[1] = g[0] * x[1]; vT[2] = g[0] * x[2];
+    vT[3] = g[1] * x[0]; vT[4] = g[1] * x[1]; vT[5] = g[1] * x[2];
+    vT[6] = g[2] * x[0]; vT[7] = g[2] * x[1]; vT[8] = g[2] * x[2];
+    vT[9] = g[0]; vT[10] = g[1]; vT[11] = g[2];
+    float qR[4], qRn[4], qn[4], v_qRn[4], v_qR[4], v_m[9];
+    mat_to_quat(T, qR);
+    const float invR = qnormalize(qR, qRn);
+    qnormalize(q, qn);
+    qmul_vjp(qRn, qn, vg, v_qRn, nullptr);
+    qnormalize_vjp(qRn, invR, v_qRn, v_qR);
+    mat_to_quat_vjp(T, v_qR, v_m);
+    for (int k = 0; k < 9; ++k) vT[k] += v_m[k];
+    for (int j = 0; j < SMPL_J; ++j) {
+        float s = 0.f;
+        for (int k = 0; k < 12; ++k) s += vT[k] * Ab[j * 12 + k];
+        v_W[j] = s;
+    }
+}

@@ -558,3 +558,49 @@ extern "C" int emd_smpl_deform_bwd(const float* means, const float* quats, const
     EMD_CHECK_LAUNCH("smpl_deform_bwd");
     return EMD_OK;
 }
+
+// ---- gradient of the LBS weights (only when they come from the trainable voxel deformer) ------------------
+__global__ void __launch_bounds__(SM_THREADS) smpl_weight_grad_kernel(const float* __restrict__ means, const float* __restrict__ quats,
+                                                                      const uint8_t* __restrict__ visible, const float* __restrict__ W,
+                                                                      const float* __restrict__ A, int V, int64_t N,
+                                                                      const float* __restrict__ v_world_means,
+                                                                      const float* __restrict__ v_world_quats, float* __restrict__ v_W) {
+    const int64_t n = (int64_t)blockIdx.x * SM_THREADS + threadIdx.x;
+    if (n >= N) return;
+    const int b = (int)(n / V);
+    float out[SMPL_J];
+    if (!visible[b]) {
+#pragma unroll
+        for (int j = 0; j < SMPL_J; ++j) out[j] = 0.f;
+    } else {
+        const float x[3] = {means[n * 3], means[n * 3 + 1], means[n * 3 + 2]};
+        const float g[3] = {v_world_means[n * 3], v_world_means[n * 3 + 1], v_world_means[n * 3 + 2]};
+        const float4 q4 = __ldg(reinterpret_cast<const float4*>(quats) + n);
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(v_world_quats) + n);
+        const float q[4] = {q4.x, q4.y, q4.z, q4.w}, vg[4] = {g4.x, g4.y, g4.z, g4.w};
+        smpl_point_weight_grad(W + n * SMPL_J, A + (int64_t)b * SM_AOUT, x, q, g, vg, out);
+    }
+    float4* dst = reinterpret_cast<float4*>(v_W + n * SMPL_J);   // 96 B per point: 16-byte aligned rows
+#pragma unroll
+    for (int j4 = 0; j4 < SMPL_J / 4; ++j4) dst[j4] = make_float4(out[j4 * 4], out[j4 * 4 + 1], out[j4 * 4 + 2], out[j4 * 4 + 3]);
+}
+
+// v_W[I,V,24] = d loss / d W of emd_smpl_deform_fwd (W is the output of VoxelDeformer.forward when
+// `use_voxel_deformer` is on: OmniRe/models/human_body.py:174-179).  A[I,24,12]: the skinning matrices the forward wrote.
+extern "C" int emd_smpl_weight_grad(const float* means, const float* quats, const uint8_t* visible, const float* W,
+                                    const float* A, int I, int V, const float* v_world_means, const float* v_world_quats,
+                                    float* v_W, cudaStream_t stream) {
+    EMD_CHECK_ARG(I >= 0 && V >= 0, "smpl_weight_grad: I=%d V=%d", I, V);
+    const int64_t N = (int64_t)I * V;
+    if (N == 0) return EMD_OK;
+    EMD_CHECK_ARG(means && quats && visible && W && A && v_world_means && v_world_quats && v_W, "smpl_weight_grad: null argument");
+    if (!emd_aligned(quats, 16) || !emd_aligned(v_world_quats, 16) || !emd_aligned(v_W, 16)) {
+        emd_set_error("smpl_weight_grad: quats / v_world_quats / v_W must be 16-B aligned");
+        return EMD_ERR_ALIGN;
+    }
+    EMD_LAUNCH(EK_SMPL_BWD, stream,
+               (smpl_weight_grad_kernel<<<(unsigned)emd_cdiv(N, SM_THREADS), SM_THREADS, 0, stream>>>(
+                   means, quats, visible, W, A, V, N, v_world_means, v_world_quats, v_W)));
+    EMD_CHECK_LAUNCH("smpl_weight_grad");
+    return EMD_OK;
+}

@@ -310,6 +310,13 @@ extern "C" void emd_host_dense_bwd(const float* X, int64_t ldx, const float* W, 
     }
 }
 
+// ---- SMPL LBS-weight gradient (emd_math.cuh: smpl_point_weight_grad), one point per row ---------------------------------
+extern "C" void emd_host_smpl_weight_grad(const float* Wn, const float* A, const float* x, const float* q, const float* g,
+                                          const float* vg, int64_t N, float* v_W) {
+    for (int64_t n = 0; n < N; ++n)
+        smpl_point_weight_grad(Wn + n * SMPL_J, A, x + n * 3, q + n * 4, g + n * 3, vg + n * 4, v_W + n * SMPL_J);
+}
+
 // ---- Adam (adam_math.cuh) -----------------------------------------------------------------------------------
 #include "adam_math.cuh"
 

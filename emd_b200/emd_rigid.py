@@ -28,11 +28,11 @@ def int_lininterp(t, init_val, final_val, until):
 def segment_index(point_ids: Tensor, num_instances: int):
     """Points sorted by instance (stable) + segment boundaries + chunk count.  The
     topology only changes at densification, so the result is cached on the
-    tensor's identity and version."""
+    tensor's identity (address, size) and version."""
     key = (point_ids.data_ptr(), point_ids._version, point_ids.numel(), num_instances)
     hit = _seg_cache.get(key)
     if hit is not None:
-        return hit
+        return hit[:3]
     ids = point_ids.reshape(-1)
     order = torch.sort(ids, stable=True).indices.contiguous()
     counts = torch.bincount(ids, minlength=num_instances)[:num_instances]
@@ -42,8 +42,10 @@ def segment_index(point_ids: Tensor, num_instances: int):
     max_chunks = max(1, int((int(counts.max()) + chunk - 1) // chunk)) if ids.numel() > 0 else 1
     if len(_seg_cache) > 64:
         _seg_cache.clear()
-    _seg_cache[key] = (order, seg_start.contiguous(), max_chunks)
-    return _seg_cache[key]
+    # the entry keeps `point_ids` alive: its storage cannot be freed and handed to another tensor while the key
+    # (address, version, size) is in the cache
+    _seg_cache[key] = (order, seg_start.contiguous(), max_chunks, point_ids)
+    return _seg_cache[key][:3]
 
 
 def _heads_array(heads):

@@ -4,9 +4,12 @@
 kinematic chain (``human_body.py:167-172``), the ``einsum`` skinning (``:489-496``)
 and ``matrix_to_quaternion`` (``:522``) become one C-ABI call each way.
 
-The LBS weights ``W[I,V,24]`` and the template buffers ``J_canonical[I,24,3]``,
-``A0_inv[I,24,4,4]`` are inputs (what ``SMPLTemplate`` holds); producing ``W``
-with the voxel deformer (``modules.py:612``) is listed as "next" in SURVEY.md 8f.
+The template buffers ``J_canonical[I,24,3]``, ``A0_inv[I,24,4,4]`` are inputs (what
+``SMPLTemplate`` holds).  The LBS weights are either the static ``W[I,V,24]`` or, with
+``use_voxel_deformer`` (``human_body.py:174-179``), the output of
+``emd_b200.voxel_deformer.VoxelDeformer`` queried at the canonical means every step
+(``template["voxel_deformer"]``); their gradient (``emd_smpl_weight_grad``) then flows
+into the voxel correction and the means.
 """
 from __future__ import annotations
 
@@ -101,7 +104,12 @@ class _SmplDeform(torch.autograd.Function):
                 n *= s
             vh.append(v_params[off:off + n].reshape(shp))
             off += n
-        return (v_means, v_quats, v_emb, v_table, v_theta, v_trans) + (None,) * 8 + tuple(vh)
+        v_W = None
+        if ctx.needs_input_grad[9]:   # W produced by the voxel deformer (trainable correction, canonical means)
+            v_W = torch.empty(I, V, 24, dtype=torch.float32, device=dev)
+            _C.check(L.emd_smpl_weight_grad(_C.ptr(means), _C.ptr(quats), _C.ptr(vis), _C.ptr(W), _C.ptr(A), I, V,
+                                            _C.ptr(v_wm), _C.ptr(v_wq), _C.ptr(v_W), _C.stream()), "emd_smpl_weight_grad")
+        return (v_means, v_quats, v_emb, v_table, v_theta, v_trans, None, None, None, v_W) + (None,) * 4 + tuple(vh)
 
 
 def smpl_deform(means, quats, embeddings, weight, theta, trans, visible, J_canonical, A0_inv, W, t, cur_coarse,
@@ -142,7 +150,16 @@ class SMPLNodesEMD:
         cf = int_lininterp(step, self.num_down_emb, self.max_embeddings, self.c2f_temporal_iter)
         return smpl_deform(p["_means"], p["_quats"], p["_embeddings"], p["weight"], theta, trans,
                            p["instances_fv"][frame], self.template["J_canonical"], self.template["A0_inv"],
-                           self.template["W"], t, self.num_down_emb, cf, self.track)
+                           self.lbs_weights(), t, self.num_down_emb, cf, self.track)
+
+    def lbs_weights(self) -> Tensor:
+        """``SMPLTemplate.forward``'s ``W`` (human_body.py:174-179): the voxel deformer queried at the canonical
+        means when present (``use_voxel_deformer``), else the static template weights."""
+        vd = self.template.get("voxel_deformer")
+        if vd is None:
+            return self.template["W"]
+        I = self.p["instances_trans"].shape[1]
+        return vd(self.p["_means"].reshape(I, -1, 3))
 
     def get_gaussians(self, cam_pos, frame: int, step: int):
         p = self.p

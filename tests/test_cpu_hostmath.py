@@ -321,3 +321,31 @@ def test_dense_tile_logic_matches_torch(hostlib, M, K, Nout, ldx, ldy, relu):
     ref_dW = dZ.T @ Xb[:, :K]
     assert np.abs(dW - ref_dW.numpy()).max() <= 2e-5 * max(1.0, ref_dW.abs().max().item())
     assert np.abs(db - dZ.sum(0).numpy()).max() <= 2e-5 * max(1.0, dZ.sum(0).abs().max().item())
+
+
+def test_smpl_weight_grad_host_math(hostlib):
+    """emd_math.cuh:smpl_point_weight_grad (d loss / d LBS weights, used when W comes from the voxel deformer) against
+    autograd through the oracle's skinning arithmetic."""
+    from oracle.quat import matrix_to_quaternion, quat_act, quat_mult, quat_to_rotmat
+    g = torch.Generator().manual_seed(23)
+    N, J = 64, 24
+    # near-rigid blend: joints = small rotations about a common pose, sparse-ish positive weights
+    qj = quat_act(torch.tensor([1.0, 0.0, 0.0, 0.0]) + 0.3 * torch.randn(J, 4, generator=g))
+    A = torch.cat([quat_to_rotmat(qj).reshape(J, 9), 0.2 * torch.randn(J, 3, generator=g)], dim=1)   # [J,12]
+    W = torch.rand(N, J, generator=g) ** 4
+    W[:, 5:9] = 0.0
+    W = (W / W.sum(-1, keepdim=True)).requires_grad_(True)
+    x, q = torch.randn(N, 3, generator=g), torch.randn(N, 4, generator=g)
+    cg, cq = torch.randn(N, 3, generator=g), torch.randn(N, 4, generator=g)
+    T = W @ A
+    R, t = T[:, :9].reshape(N, 3, 3), T[:, 9:]
+    xw = torch.einsum("nij,nj->ni", R, x) + t
+    qw = quat_mult(quat_act(matrix_to_quaternion(R)), quat_act(q))
+    ((xw * cg).sum() + (qw * cq).sum()).backward()
+    out = np.zeros((N, J), np.float32)
+    f = hostlib.emd_host_smpl_weight_grad
+    f.argtypes = [P] * 6 + [ctypes.c_int64, P]
+    f.restype = None
+    f(_fp(W), _fp(A), _fp(x), _fp(q), _fp(cg), _fp(cq), N, out.ctypes.data_as(P))
+    ref = W.grad.numpy()
+    assert np.abs(out - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())

@@ -22,6 +22,11 @@ GROUPS = [
     ("Next (SURVEY 8f-2): fused Adam step", ["emd_adam_max_tensors", "emd_adam_step"]),
     ("Next (SURVEY 8f-3): fused image losses between the rasterizer forward and backward",
      ["emd_image_loss_partials_floats", "emd_image_loss_fwd", "emd_image_loss_bwd"]),
+    ("Next (SURVEY 8f-4): voxel LBS weights of the SMPL nodes (K1f)",
+     ["emd_voxel_lbs_fwd", "emd_voxel_lbs_bwd", "emd_smpl_weight_grad"]),
+    ("Next (SURVEY 8f-4): DeformableNodes deformation network (K1g)",
+     ["emd_deform_input_fwd", "emd_dense_fwd", "emd_dense_bwd_workspace_bytes", "emd_dense_bwd", "emd_deform_apply_fwd",
+      "emd_deform_apply_bwd", "emd_deform_embed_grad"]),
     ("K2   projection", ["emd_projection_fwd", "emd_projection_bwd", "emd_dg_preprocess_fwd", "emd_dg_preprocess_bwd"]),
     ("K3   tile intersection", ["emd_scan_workspace_bytes", "emd_cumsum_i32_i64", "emd_exclusive_scan_u32",
                                 "emd_isect_emit", "emd_dg_isect_emit"]),
@@ -119,6 +124,31 @@ DOC = {
     "emd_image_loss_bwd": "VJP of emd_image_loss_fwd: v_rgb (rgb strides), v_depth (depth strides; NULL iff depth is), v_alpha "
                           "[C,H,W], v_sky (sky strides; may be NULL) from v_terms [C,EMD_LOSS_TERMS] on the DEVICE -- the "
                           "cotangents the rasterizer backward consumes, every pixel written.",
+    "emd_voxel_lbs_fwd": "Replaces VoxelDeformer.forward (OmniRe/models/modules.py:612-625: normalize :627-632 + 5-D F.grid_sample, "
+                         "trilinear / border / align_corners=True) and get_voxel_weight's full-volume add (:575-582), queried by "
+                         "SMPLTemplate.forward (OmniRe/models/human_body.py:174-179, `use_voxel_deformer: true`): out[B,V,J] from "
+                         "xc[B,V,3].  base / corr: DEVICE volumes stored channel-LAST [B,D,H,W,J] (corr may be NULL); offset[B,3], "
+                         "scale[B] DEVICE; ratio_dim: 0 = x, 1 = y, 2 = z (the reference's -1 - short_dim_dhw, modulo 3).",
+    "emd_voxel_lbs_bwd": "VJP of emd_voxel_lbs_fwd: v_corr (layout of corr, ADDED into, caller zero-fills; 16-byte vector "
+                         "reductions; may be NULL), v_xc[B,V,3] (may be NULL).",
+    "emd_smpl_weight_grad": "d loss / d W[I,V,24] of emd_smpl_deform_fwd -- needed only when the LBS weights come from the voxel "
+                            "deformer (human_body.py:174-179).  A[I,24,12]: the skinning matrices the forward wrote.",
+    "emd_deform_input_fwd": "Input of ConditionalDeformNetwork as DeformableNodes.get_deformation builds it "
+                            "(OmniRe/models/nodes/deformable.py:40-46, OmniRe/models/modules.py:341-366, 436-438): "
+                            "x = means / instances_size[id, 2] * 2; columns [x, sin/cos(2^f x) ..., t, sin/cos(2^f t) ..., "
+                            "instances_embedding[id]] written to out0 (row stride ld0) and, when out1 != NULL, to out1 (row "
+                            "stride ld1: the head of the skip layer's operand).",
+    "emd_dense_fwd": "One nn.Linear (+ F.relu) of ConditionalDeformNetwork.forward (modules.py:438-455) on strided operands: "
+                     "Y[M,0:Nout] (row stride ldy) = act(X[M,0:K] (row stride ldx) W[Nout,K]^T + b).  fp32 SIMT GEMM.",
+    "emd_dense_bwd_workspace_bytes": "Workspace bytes of emd_dense_bwd (split-K weight-gradient partials + bias partials).",
+    "emd_dense_bwd": "VJP of emd_dense_fwd given dZ = dL/d(pre-activation): dX on the column window [col0, col0+ncols) of the "
+                     "operand, multiplied by (mask > 0) where mask is the operand's producer's ReLU output (may be NULL); "
+                     "dW[Nout,K], db[Nout] by fixed-order reductions.  dX, dW, db may each be NULL.",
+    "emd_deform_apply_fwd": "deformable.py:57-68: means + d_xyz and get_quats + delta_quat (get_quats = quats / |quats|, "
+                            "vanilla.py:142-146) from the heads' output d[N,dcols] (3, or 7 with the quaternion head).",
+    "emd_deform_apply_bwd": "VJP of emd_deform_apply_fwd: v_d[N,dcols], v_means (NULL when stop_optimizing_canonical_xyz), v_quats.",
+    "emd_deform_embed_grad": "VJP of the instances_embedding[point_ids] gather (deformable.py:40): per-instance fixed-order sum of "
+                             "the embedding-column gradients g0 (+ g1) over the instance-sorted index (order, seg_start).",
     "emd_scan_workspace_bytes": "Workspace bytes of the scans for n elements.",
     "emd_cumsum_i32_i64": "Inclusive cumulative sum (torch.cumsum of tiles_per_gauss in gsplat's isect_tiles); total -> device scalar.",
     "emd_exclusive_scan_u32": "Exclusive scan (radix-sort tables); in-place allowed.",
