@@ -337,9 +337,18 @@ def run_ours(args):
             gbs = b / (ms_total / cnt * 1e-3) / 1e9
             ent.update({"bound": "hbm", "achieved_gbs": round(gbs, 1), "frac_of_measured_hbm": round(gbs / hbm_peak, 4)})
         per_kernel[name] = ent
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same command
+    # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/ncu_traffic.json names the capture it came from)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as fh:
+            ent = json.load(fh)["raster_bwd"]
+        traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {
         "kernel": "raster_bwd", "bound": "fp32", "achieved": round(achieved, 3), "peak": round(FP32_PEAK_TFLOPS, 2),
-        "unit": "TFLOP/s", "frac": round(achieved / FP32_PEAK_TFLOPS, 4), "traffic": None,
+        "unit": "TFLOP/s", "frac": round(achieved / FP32_PEAK_TFLOPS, 4), "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": "nominal 148 SM x 128 FMA lanes x 1.965 GHz (MEASURED_PEAKS.json holds HBM and bf16 only)",
         "algorithmic": f"{pairs_bwd} pixel-Gaussian pairs x {FLOP_PER_PAIR_BWD:.0f} flop per launch (3 cameras)",
         "avg_launch_ms": round(rb_ms, 4), "pairs_per_launch": pairs_bwd,

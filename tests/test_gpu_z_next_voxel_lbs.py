@@ -80,7 +80,9 @@ def test_smpl_nodes_with_voxel_deformer():
     m = cpu["means"].detach().reshape(I, V, 3)
     lo, hi = m.min(1).values, m.max(1).values
     off = (0.5 * (lo + hi))[:, None]
-    scl = ((hi - lo).max(-1).values / 2 * 1.1)[:, None, None]      # a few points fall outside the volume along z
+    # the stretched axis (z, x4) of the synthetic figure is its longest: scale so that most points stay inside the volume
+    # along z and a few fall outside (border clamp, zero coordinate gradient)
+    scl = ((hi - lo).max(-1).values / 2 * 2.75)[:, None, None]
     ratio, ratio_dim = res[1] / res[0], -1
     p.W = OV.voxel_weights(base + cor, off, scl, ratio, ratio_dim, cpu["means"].reshape(I, V, 3))
     cam_pos = torch.tensor([0.0, 0.0, 1.6])
