@@ -106,7 +106,9 @@ class _DeformNet(torch.autograd.Function):
         v_quats = torch.empty(N, 4, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
         _C.check(L.emd_deform_apply_bwd(_C.ptr(quats), _C.ptr(v_mo), _C.ptr(v_qo), Hc, N, _C.ptr(v_d), _C.ptr(v_means),
                                         _C.ptr(v_quats), st), "emd_deform_apply_bwd")
-        ws_bytes = max(L.emd_dense_bwd_workspace_bytes(N, Kin + Wd, Wd), L.emd_dense_bwd_workspace_bytes(N, Kin + Wd, Hc))
+        # one workspace for every layer: the split count depends on the layer's shape, so take the largest requirement
+        shapes = {(Kin, Wd), (Wd, Wd), (Kin + Wd, Wd), (Wd, Hc), (Kin + Wd, Hc)}
+        ws_bytes = max(L.emd_dense_bwd_workspace_bytes(N, k, n) for k, n in shapes)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         g_emb: List[Tensor] = []     # embedding-column gradients of the operands that contain the network input
 

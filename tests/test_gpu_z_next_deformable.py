@@ -97,30 +97,67 @@ def _network(D, Wd, E, g, quat_head=True):
     return sd
 
 
-@pytest.mark.parametrize("frame,step,stop_xyz", [(13, 8000, True), (0, 3001, False), (5, 100, True)])
-def test_deformable_nodes_get_gaussians(frame, step, stop_xyz):
-    """DeformableNodes.get_gaussians at the config's network size (omnire.yaml:159-166): deformation network -> rigid EMD
-    transform -> activations + SH, values and every gradient (network, instance embedding, Gaussians, EMD heads, poses)
-    against the oracle; step 100 <= use_deformgs_after takes the plain rigid route."""
-    from emd_b200.deformable import DeformableNodesEMD
+def _check_grads(pairs):
+    """pairs: (name, fp32-oracle grad, fp64-oracle grad, GPU grad).  The bar is 1e-3 relative against the fp64 oracle --
+    except where the reference arithmetic itself cannot hold it: a ReLU network's gradient is discontinuous in the
+    pre-activations, and an fp32 evaluation (the reference's, ours) flips the sign of a few of the ~10^6 pre-activations
+    that lie within rounding of zero.  Each flip moves a per-instance / per-column gradient SUM by one sample's worth
+    (the fp32 oracle deviates from the fp64 one by up to ~1e-2 on early-layer biases at this size), so a tensor's bar is
+    max(1e-3, 4 x the fp32 oracle's own deviation from the fp64 oracle)."""
+    for k, g32, g64, gg in pairs:
+        if g64 is None or float(g64.abs().max()) == 0.0:
+            assert gg is None or float(gg.abs().max()) == 0.0, k
+            continue
+        assert gg is not None, k
+        tol_e, tol_l2 = max(1e-3, 4 * rel_err(g32, g64)), max(1e-3, 4 * rel_l2(g32, g64))
+        e, l2 = rel_err(gg, g64), rel_l2(gg, g64)
+        assert e <= tol_e and l2 <= tol_l2, f"grad {k}: max-rel {e} (bar {tol_e}), l2-rel {l2} (bar {tol_l2})"
+
+
+def _oracle_nodes(dt, rs, cpu, sd, size, ts, frame, step, stop_xyz, D, cot):
+    """DeformableNodes.get_gaussians through the oracle in dtype dt -> (outputs, leaf grads, network grads)."""
     from oracle import deform_network as ON
     from oracle import emd_rigid as ER
+    from tests.test_gpu_emd_rigid import HEADS
+    torch.set_default_dtype(dt)
+    try:
+        c = {k: v.detach().to(dt).requires_grad_(True) for k, v in cpu.items()}
+        net = {k: v.detach().to(dt).requires_grad_(True) for k, v in sd.items()}
+        p = ER.RigidEMD(point_ids=rs.point_ids[:, 0], embeddings=c["embeddings"], weight=c["weight"],
+                        instances_quats=c["instances_quats"], instances_trans=c["instances_trans"],
+                        instances_fv=rs.instances_fv, **{k: c[k] for k in HEADS})
+        if step > 3000:
+            m, q = ON.deformed_canonical(net, c["means"], c["quats"], rs.point_ids, size.to(dt), c["instances_embedding"],
+                                         ts[frame], D=D, stop_optimizing_canonical_xyz=stop_xyz)
+        else:
+            m, q = c["means"], c["quats"]
+        ref = ER.get_gaussians(p, m, q, c["scales"], c["opacities"], c["features_dc"], c["features_rest"], frame, step,
+                               torch.tensor([0.3, -0.2, 1.6], dtype=dt))
+        sum((ref[k] * cot[k].to(dt)).sum() for k in cot).backward()
+        return {k: v.detach() for k, v in ref.items()}, {k: v.grad for k, v in c.items()}, {k: v.grad for k, v in net.items()}
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+
+@pytest.mark.parametrize("frame,step,stop_xyz,Wd", [(13, 8000, True, 256), (0, 3001, False, 64), (5, 100, True, 64)])
+def test_deformable_nodes_get_gaussians(frame, step, stop_xyz, Wd):
+    """DeformableNodes.get_gaussians (network of the config's shape, omnire.yaml:159-166, at full width 256 and at 64):
+    deformation network -> rigid EMD transform -> activations + SH, values and every gradient (network, instance
+    embedding, Gaussians, EMD heads, poses) against the oracle; step 100 <= use_deformgs_after takes the plain rigid
+    route."""
+    from emd_b200.deformable import DeformableNodesEMD
     from tests.test_gpu_emd_rigid import HEADS, _setup
-    I, pts, frames, D, Wd, E = 6, 500, 40, 8, 256, 16
+    I, pts, frames, D, E = 6, 400, 40, 8, 16
     rs, cpu, p, g = _setup(11, I, pts, frames)
+    N = I * pts
     size = torch.tensor([0.8, 0.8, 1.7]) + 0.2 * torch.rand(I, 3, generator=g)
     cpu["instances_embedding"] = torch.rand(I, E, generator=g).requires_grad_(True)
     sd = _network(D, Wd, E, g)
-    net_cpu = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     ts = torch.linspace(0, 1, frames).tolist()
     cam_pos = torch.tensor([0.3, -0.2, 1.6])
-    if step > 3000:
-        m_ref, q_ref = ON.deformed_canonical(net_cpu, cpu["means"], cpu["quats"], rs.point_ids, size, cpu["instances_embedding"],
-                                             ts[frame], D=D, stop_optimizing_canonical_xyz=stop_xyz)
-    else:
-        m_ref, q_ref = cpu["means"], cpu["quats"]
-    ref = ER.get_gaussians(p, m_ref, q_ref, cpu["scales"], cpu["opacities"], cpu["features_dc"], cpu["features_rest"], frame,
-                           step, cam_pos)
+    cot = {k: torch.randn(N, n, generator=g) for k, n in (("_means", 3), ("_opacities", 1), ("_rgbs", 3), ("_scales", 3), ("_quats", 4))}
+    ref, g32, n32 = _oracle_nodes(torch.float32, rs, cpu, sd, size, ts, frame, step, stop_xyz, D, cot)
+    ref64, g64, n64 = _oracle_nodes(torch.float64, rs, cpu, sd, size, ts, frame, step, stop_xyz, D, cot)
     dev = "cuda"
     gpu = {k: v.detach().to(dev).requires_grad_(True) for k, v in cpu.items()}
     net_gpu = {k: v.detach().to(dev).requires_grad_(True) for k, v in sd.items()}
@@ -132,23 +169,16 @@ def test_deformable_nodes_get_gaussians(frame, step, stop_xyz):
              instances_embedding=gpu["instances_embedding"], instances_size=size.to(dev)),
         {k: gpu[k] for k in HEADS}, net_gpu, ts, D=D, stop_optimizing_canonical_xyz=stop_xyz)
     out = node.get_gaussians(cam_pos.tolist(), frame, step)
-    cot = {}
-    for k in ("_means", "_opacities", "_rgbs", "_scales", "_quats"):
+    for k in cot:
         assert out[k].shape == ref[k].shape, k
-        err = float((out[k].detach().cpu() - ref[k].detach()).abs().max())
-        tol = 3e-5 * max(1.0, float(ref[k].detach().abs().max()))
+        err = float((out[k].detach().cpu() - ref[k]).abs().max())
+        tol = 3e-5 * max(1.0, float(ref[k].abs().max()))
         assert err <= tol, f"{k}: {err} > {tol}"
-        cot[k] = torch.randn(ref[k].shape, generator=g)
-    sum((ref[k] * cot[k]).sum() for k in cot).backward()
     sum((out[k] * cot[k].to(dev)).sum() for k in cot).backward()
-    pairs = [(k, cpu[k].grad, gpu[k].grad) for k in cpu] + [(k, net_cpu[k].grad, net_gpu[k].grad) for k in sd]
-    for k, gr, gg in pairs:
-        if gr is None or float(gr.abs().max()) == 0.0:
-            assert gg is None or float(gg.abs().max()) == 0.0, k
-            continue
-        assert gg is not None, k
-        e, l2 = rel_err(gg, gr), rel_l2(gg, gr)
-        assert e <= 1e-3 and l2 <= 1e-3, f"grad {k}: max-rel {e}, l2-rel {l2}"
+    _check_grads([(k, g32[k], g64[k], gpu[k].grad) for k in cpu] + [(k, n32[k], n64[k], net_gpu[k].grad) for k in sd])
     if step > 3000:
-        assert float(net_cpu["linear.0.weight"].grad.abs().max()) > 0 and float(cpu["instances_embedding"].grad.abs().max()) > 0
+        assert float(n64["linear.0.weight"].abs().max()) > 0 and float(g64["instances_embedding"].abs().max()) > 0
+        assert net_gpu["linear.0.weight"].grad is not None and gpu["instances_embedding"].grad is not None
         assert node._gs_cache["local_xyz_deformed"] is not None
+        if stop_xyz:     # stop_optimizing_canonical_xyz: the canonical means receive no gradient at all (deformable.py:57-58)
+            assert gpu["means"].grad is None and g64["means"] is None
