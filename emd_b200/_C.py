@@ -58,7 +58,8 @@ _SIGS = {
     "emd_dense_bwd": (c_int, [P, c_int64, P, P, c_int64, c_int64, c_int, c_int, P, c_int64, c_int, c_int, P, c_int64, P, P,
                               P, c_size_t, P]),
     "emd_deform_input_fwd": (c_int, [P, P, P, P, c_float, c_int, c_int, c_int, c_int64, P, c_int64, P, c_int64, P]),
-    "emd_deform_embed_grad": (c_int, [P, P, c_int, P, P, c_int, P, P]),
+    "emd_deform_embed_grad_workspace_bytes": (c_size_t, [c_int, c_int, c_int64]),
+    "emd_deform_embed_grad": (c_int, [P, P, c_int, P, P, c_int, c_int64, P, c_size_t, P, P]),
     "emd_deform_apply_fwd": (c_int, [P, P, P, c_int, c_int64, P, P, P]),
     "emd_deform_apply_bwd": (c_int, [P, P, P, c_int, c_int64, P, P, P, P]),
     "emd_adam_max_tensors": (c_int, []),

@@ -20,16 +20,27 @@
 // CTA tiles, 8x8 register micro-tiles split 4+4 so every shared-memory read is a conflict-free LDS.128, global
 // loads of the next k-tile in flight under the FMAs of the current one.  FP32-pipe bound; moving these 256-wide
 // layers onto tcgen05 (3xTF32 like csrc/mlp_tc.cu, which is limited to K <= 136, Nout <= 64) is the open step.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "dense_math.cuh"
+
+#ifndef DG_DEFAULT_MINB
+#define DG_DEFAULT_MINB 2
+#endif
 
 namespace {
 
 // C[m,n] = sum_k A(m,k) B(k,n) -- tile logic in dense_math.cuh (shared with the host emulation the CPU tests run)
-template <bool TA, bool TB>
-__global__ void __launch_bounds__(DG_THREADS, 2) sgemm_kernel(const GemmArgs g) {
-    __shared__ __align__(16) float As[DG_BK][DG_PITCH];
-    __shared__ __align__(16) float Bs[DG_BK][DG_PITCH];
+// MINB = resident CTAs per SM the register allocation targets: 2 (128 registers; two CTAs hide each other's barriers)
+// or 1 (no register cap: no spills or rematerialised addresses in the k-loop, but 8 warps per SM).
+template <bool TA, bool TB, int MINB>
+__global__ void __launch_bounds__(DG_THREADS, MINB) sgemm_kernel(const GemmArgs g) {
+    // two shared-memory stages: tile t lives in stage t & 1, so ONE barrier per k-tile suffices (a thread can only
+    // overwrite stage s in iteration t + 1 after every thread passed the barrier of iteration t, i.e. finished reading
+    // stage s in iteration t - 1)
+    __shared__ __align__(16) float As[2][DG_BK][DG_PITCH];
+    __shared__ __align__(16) float Bs[2][DG_BK][DG_PITCH];
     const int tid = threadIdx.x;
     const int64_t m0 = (int64_t)blockIdx.x * DG_BM;
     const int64_t n0 = (int64_t)blockIdx.y * DG_BN;
@@ -44,13 +55,18 @@ __global__ void __launch_bounds__(DG_THREADS, 2) sgemm_kernel(const GemmArgs g) 
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-    if (kbeg < kend) gemm_load<TA, TB>(g, tid, m0, n0, kbeg, kend, ra, rb);
-    for (int64_t k0 = kbeg; k0 < kend; k0 += DG_BK) {
-        gemm_store<TA, TB>(tid, ra, rb, As, Bs);
+    GemmLoadState S;
+    gemm_prepare<TA, TB>(g, tid, m0, n0, kbeg, S);
+    if (kbeg < kend) gemm_load_tile<TA, TB>(S, kbeg, kend, ra, rb);
+    int stage = 0;
+    for (int64_t k0 = kbeg; k0 < kend; k0 += DG_BK, stage ^= 1) {
+        gemm_store<TA, TB>(tid, ra, rb, As[stage], Bs[stage]);
         __syncthreads();
-        if (k0 + DG_BK < kend) gemm_load<TA, TB>(g, tid, m0, n0, k0 + DG_BK, kend, ra, rb);   // in flight under the FMAs
-        gemm_compute(tid, As, Bs, acc);
-        __syncthreads();
+        if (k0 + DG_BK < kend) {   // next tile's loads in flight under the FMAs of this one
+            gemm_advance(S);
+            gemm_load_tile<TA, TB>(S, k0 + DG_BK, kend, ra, rb);
+        }
+        gemm_compute(tid, As[stage], Bs[stage], acc);
     }
     gemm_epilogue(g, tid, m0, n0, C, acc);
 }
@@ -76,10 +92,20 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ Z
     }
 }
 
+// tuning switch (measurement only): EMD_SGEMM_MINB=1|2 selects the register-allocation flavour; default below
+int sgemm_minb() {
+    static const int v = [] {
+        const char* e = getenv("EMD_SGEMM_MINB");
+        return (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : DG_DEFAULT_MINB;
+    }();
+    return v;
+}
+
 template <bool TA, bool TB>
 void launch_sgemm(const GemmArgs& g, int splits, cudaStream_t stream) {
     dim3 grid((unsigned)emd_cdiv(g.M, DG_BM), (unsigned)emd_cdiv(g.N, DG_BN), (unsigned)splits);
-    sgemm_kernel<TA, TB><<<grid, DG_THREADS, 0, stream>>>(g);
+    if (sgemm_minb() == 1) sgemm_kernel<TA, TB, 1><<<grid, DG_THREADS, 0, stream>>>(g);
+    else sgemm_kernel<TA, TB, 2><<<grid, DG_THREADS, 0, stream>>>(g);
 }
 
 }  // namespace
@@ -253,17 +279,21 @@ __global__ void __launch_bounds__(256) deform_apply_bwd_kernel(const float* __re
     }
 }
 
-// v_emb[i, c] = sum over the points of instance i (emission order of the instance-sorted index) of g0[n, c] + g1[n, c]
+// partial[i][c][e] = sum over the points of chunk c of instance i (emission order of the instance-sorted index) of
+// g0[n, e] + g1[n, e].  grid (chunks, I): enough CTAs to hide the order[] -> g[] dependent-load latency.
+constexpr int EMBG_CHUNK = 256;      // points per CTA
 __global__ void __launch_bounds__(256) deform_embed_grad_kernel(const float* __restrict__ g0, const float* __restrict__ g1, int E,
                                                                 const int64_t* __restrict__ order,
-                                                                const int64_t* __restrict__ seg_start, float* __restrict__ v_emb) {
+                                                                const int64_t* __restrict__ seg_start, float* __restrict__ partial) {
     __shared__ float s[256];
-    const int i = blockIdx.x;
+    const int i = blockIdx.y, chunk = blockIdx.x;
     const int rows = 256 / E;                       // E <= 256
     const int r = threadIdx.x / E, c = threadIdx.x - r * E;
+    const int64_t lo = seg_start[i] + (int64_t)chunk * EMBG_CHUNK;
+    const int64_t hi = min(seg_start[i + 1], lo + EMBG_CHUNK);
     float acc = 0.f;
     if (r < rows) {
-        for (int64_t p = seg_start[i] + r; p < seg_start[i + 1]; p += rows) {
+        for (int64_t p = lo + r; p < hi; p += rows) {
             const int64_t n = order[p];
             acc += g0[n * E + c] + (g1 ? g1[n * E + c] : 0.f);
         }
@@ -273,8 +303,19 @@ __global__ void __launch_bounds__(256) deform_embed_grad_kernel(const float* __r
     if (threadIdx.x < E) {
         float tot = 0.f;
         for (int k = 0; k < rows; ++k) tot += s[k * E + threadIdx.x];
-        v_emb[(int64_t)i * E + threadIdx.x] = tot;
+        partial[((int64_t)i * gridDim.x + chunk) * E + threadIdx.x] = tot;
     }
+}
+
+// v_emb[i][e] = sum over the chunks, fixed order
+__global__ void __launch_bounds__(256) deform_embed_grad_finish_kernel(const float* __restrict__ partial, int chunks, int E, int I,
+                                                                       float* __restrict__ v_emb) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= I * E) return;
+    const int i = t / E, e = t - i * E;
+    float acc = 0.f;
+    for (int c = 0; c < chunks; ++c) acc += partial[((int64_t)i * chunks + c) * E + e];
+    v_emb[t] = acc;
 }
 
 }  // namespace
@@ -301,16 +342,36 @@ extern "C" int emd_deform_input_fwd(const float* means, const int64_t* point_ids
     return EMD_OK;
 }
 
+extern "C" size_t emd_deform_embed_grad_workspace_bytes(int I, int E, int64_t max_points_per_instance) {
+    const int64_t chunks = emd_cdiv(max_points_per_instance > 0 ? max_points_per_instance : 1, EMBG_CHUNK);
+    return (size_t)(I > 0 ? I : 1) * (size_t)chunks * (size_t)(E > 0 ? E : 1) * sizeof(float);
+}
+
 // Gradient of the instance embedding: v_emb[I,E] = per-instance sum of g0[N,E] (+ g1[N,E] when not NULL), the embedding
 // columns of the layer-0 and skip-layer input gradients.  order / seg_start: points stably sorted by instance + the I+1
-// boundaries (the index emd_rigid_deform_fwd uses).
+// boundaries (the index emd_rigid_deform_fwd uses); max_points_per_instance: any upper bound on the largest segment.
+// Fixed-order two-level reduction (per 256-point chunk, then over the chunks).
 extern "C" int emd_deform_embed_grad(const float* g0, const float* g1, int E, const int64_t* order, const int64_t* seg_start,
-                                     int I, float* v_emb, cudaStream_t stream) {
-    EMD_CHECK_ARG(E >= 1 && E <= 256 && I >= 0, "emd_deform_embed_grad: E=%d I=%d", E, I);
+                                     int I, int64_t max_points_per_instance, void* workspace, size_t workspace_bytes,
+                                     float* v_emb, cudaStream_t stream) {
+    EMD_CHECK_ARG(E >= 1 && E <= 256 && I >= 0 && max_points_per_instance >= 0, "emd_deform_embed_grad: E=%d I=%d max=%lld", E, I,
+                  (long long)max_points_per_instance);
     if (I == 0) return EMD_OK;
     EMD_CHECK_ARG(g0 && order && seg_start && v_emb, "emd_deform_embed_grad: null argument");
-    EMD_LAUNCH(EK_DEFORM_IN, stream, (deform_embed_grad_kernel<<<(unsigned)I, 256, 0, stream>>>(g0, g1, E, order, seg_start, v_emb)));
+    const int64_t chunks = emd_cdiv(max_points_per_instance > 0 ? max_points_per_instance : 1, EMBG_CHUNK);
+    EMD_CHECK_ARG(chunks <= 0x7fffffff && I <= 65535, "emd_deform_embed_grad: grid too large (chunks=%lld, I=%d)", (long long)chunks, I);
+    if (!workspace || workspace_bytes < emd_deform_embed_grad_workspace_bytes(I, E, max_points_per_instance)) {
+        emd_set_error("emd_deform_embed_grad: workspace too small (%zu < %zu)", workspace_bytes,
+                      emd_deform_embed_grad_workspace_bytes(I, E, max_points_per_instance));
+        return EMD_ERR_WORKSPACE;
+    }
+    float* partial = static_cast<float*>(workspace);
+    EMD_LAUNCH(EK_DEFORM_IN, stream,
+               (deform_embed_grad_kernel<<<dim3((unsigned)chunks, (unsigned)I), 256, 0, stream>>>(g0, g1, E, order, seg_start, partial)));
     EMD_CHECK_LAUNCH("emd_deform_embed_grad");
+    EMD_LAUNCH(EK_DEFORM_IN, stream,
+               (deform_embed_grad_finish_kernel<<<(unsigned)emd_cdiv((int64_t)I * E, 256), 256, 0, stream>>>(partial, (int)chunks, E, I, v_emb)));
+    EMD_CHECK_LAUNCH("emd_deform_embed_grad(finish)");
     return EMD_OK;
 }
 

@@ -44,25 +44,70 @@ struct GemmArgs {
 
 // C[m,n] = sum_k A(m,k) B(k,n);   A(m,k) = TA ? A[k*lda + m] : A[m*lda + k];   B(k,n) = TB ? B[n*ldb + k] : B[k*ldb + n]
 // Each thread fetches 8 elements of the 128x16 A tile and 8 of the 16x128 B tile, consecutive threads along the
-// operand's contiguous dimension.
+// operand's contiguous dimension.  Element i of a thread sits a FIXED stride after element 0 (16 rows when the
+// operand is k-contiguous, 2 k-steps when it is row-contiguous), so a thread keeps one base offset per operand and the
+// tile loop only adds k0 * (k stride): no per-element index arithmetic, no branches around the guarded loads.
+struct GemmLoadState {
+    const float* pa;        // this thread's element 0 of the CURRENT k-tile (advanced by gemm_advance)
+    const float* pb;
+    int64_t stepA, stepB;   // offset between the thread's consecutive elements
+    int64_t advA, advB;     // offset between consecutive k-tiles
+    int kA, kB;             // tile-local k of element 0
+    unsigned maskA, maskB;  // bit i: the ROW (m resp. n) of element i is inside the matrix
+};
+
 template <bool TA, bool TB>
-EMD_HD void gemm_load(const GemmArgs& g, int tid, int64_t m0, int64_t n0, int64_t k0, int64_t kend, float (&ra)[8], float (&rb)[8]) {
+EMD_HD void gemm_prepare(const GemmArgs& g, int tid, int64_t m0, int64_t n0, int64_t kbeg, GemmLoadState& S) {
+    const int rowA = TA ? (tid & (DG_BM - 1)) : (tid >> 4);
+    const int rowB = TB ? (tid >> 4) : (tid & (DG_BN - 1));
+    S.kA = TA ? (tid >> 7) : (tid & (DG_BK - 1));
+    S.kB = TB ? (tid & (DG_BK - 1)) : (tid >> 7);
+    S.pa = g.A + (TA ? (kbeg + S.kA) * g.lda + (m0 + rowA) : (m0 + rowA) * g.lda + (kbeg + S.kA));
+    S.pb = g.B + (TB ? (n0 + rowB) * g.ldb + (kbeg + S.kB) : (kbeg + S.kB) * g.ldb + (n0 + rowB));
+    S.stepA = TA ? 2 * g.lda : 16 * g.lda;      // TA: element i is k + 2 i of the same m; else: row m + 16 i of the same k
+    S.stepB = TB ? 16 * g.ldb : 2 * g.ldb;
+    S.advA = TA ? DG_BK * g.lda : DG_BK;
+    S.advB = TB ? DG_BK : DG_BK * g.ldb;
+    S.maskA = 0;
+    S.maskB = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int e = tid + i * DG_THREADS;
-        {
-            const int m = TA ? (e & (DG_BM - 1)) : (e >> 4);
-            const int k = TA ? (e >> 7) : (e & (DG_BK - 1));
-            const int64_t gm = m0 + m, gk = k0 + k;
-            ra[i] = (gm < g.M && gk < kend) ? DG_LDG(TA ? g.A + gk * g.lda + gm : g.A + gm * g.lda + gk) : 0.f;
-        }
-        {
-            const int n = TB ? (e >> 4) : (e & (DG_BN - 1));
-            const int k = TB ? (e & (DG_BK - 1)) : (e >> 7);
-            const int64_t gn = n0 + n, gk = k0 + k;
-            rb[i] = (gn < g.N && gk < kend) ? DG_LDG(TB ? g.B + gn * g.ldb + gk : g.B + gk * g.ldb + gn) : 0.f;
-        }
+        if (m0 + rowA + (TA ? 0 : 16 * i) < g.M) S.maskA |= 1u << i;
+        if (n0 + rowB + (TB ? 16 * i : 0) < g.N) S.maskB |= 1u << i;
     }
+}
+
+// loads the thread's 8 + 8 elements of the k-tile that starts at k0 (S.pa / S.pb point at it).  FULLK: the whole
+// tile lies below kend, only the row masks guard the loads; otherwise every element's k is checked as well.
+template <bool TA, bool TB, bool FULLK>
+EMD_HD void gemm_load(const GemmLoadState& S, int64_t k0, int64_t kend, float (&ra)[8], float (&rb)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        bool oka = (S.maskA >> i) & 1u, okb = (S.maskB >> i) & 1u;
+        if (!FULLK) {
+            oka = oka && (k0 + S.kA + (TA ? 2 * i : 0) < kend);
+            okb = okb && (k0 + S.kB + (TB ? 0 : 2 * i) < kend);
+        }
+        const float* qa = S.pa + i * S.stepA;
+        const float* qb = S.pb + i * S.stepB;
+        float va = 0.f, vb = 0.f;
+        if (oka) va = DG_LDG(qa);
+        if (okb) vb = DG_LDG(qb);
+        ra[i] = va;
+        rb[i] = vb;
+    }
+}
+
+EMD_HD void gemm_advance(GemmLoadState& S) {
+    S.pa += S.advA;
+    S.pb += S.advB;
+}
+
+// one k-tile's loads, choosing the unguarded-k flavour when the tile is full (uniform across the CTA)
+template <bool TA, bool TB>
+EMD_HD void gemm_load_tile(const GemmLoadState& S, int64_t k0, int64_t kend, float (&ra)[8], float (&rb)[8]) {
+    if (k0 + DG_BK <= kend) gemm_load<TA, TB, true>(S, k0, kend, ra, rb);
+    else gemm_load<TA, TB, false>(S, k0, kend, ra, rb);
 }
 
 // shared tiles are k-major: As[k][m], Bs[k][n]
@@ -160,8 +205,8 @@ static inline DenseSplit dense_split(int64_t M, int K, int Nout) {
     if (want < 1) want = 1;
     s.k_per_split = dg_cdiv(kt, want) * DG_BK;
     s.splits = (int)dg_cdiv(rows, s.k_per_split);
-    int64_t chunks = dg_cdiv(rows, 512);
-    if (chunks > 2 * DG_NUM_SMS) chunks = 2 * DG_NUM_SMS;
+    int64_t chunks = dg_cdiv(rows, 128);
+    if (chunks > 4 * DG_NUM_SMS) chunks = 4 * DG_NUM_SMS;
     s.rows_per_chunk = dg_cdiv(rows, chunks);
     s.col_chunks = (int)dg_cdiv(rows, s.rows_per_chunk);
     return s;

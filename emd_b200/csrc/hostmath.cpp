@@ -258,12 +258,17 @@ static void host_sgemm(const GemmArgs& g, int splits) {
                 for (int t = 0; t < DG_THREADS; ++t)
                     for (int i = 0; i < 8; ++i)
                         for (int j = 0; j < 8; ++j) acc[t][i][j] = 0.f;
+                static GemmLoadState S[DG_THREADS];
+                for (int t = 0; t < DG_THREADS; ++t) gemm_prepare<TA, TB>(g, t, m0, n0, kbeg, S[t]);
                 if (kbeg < kend)
-                    for (int t = 0; t < DG_THREADS; ++t) gemm_load<TA, TB>(g, t, m0, n0, kbeg, kend, ra[t], rb[t]);
+                    for (int t = 0; t < DG_THREADS; ++t) gemm_load_tile<TA, TB>(S[t], kbeg, kend, ra[t], rb[t]);
                 for (int64_t k0 = kbeg; k0 < kend; k0 += DG_BK) {
                     for (int t = 0; t < DG_THREADS; ++t) gemm_store<TA, TB>(t, ra[t], rb[t], As, Bs);
                     if (k0 + DG_BK < kend)
-                        for (int t = 0; t < DG_THREADS; ++t) gemm_load<TA, TB>(g, t, m0, n0, k0 + DG_BK, kend, ra[t], rb[t]);
+                        for (int t = 0; t < DG_THREADS; ++t) {
+                            gemm_advance(S[t]);
+                            gemm_load_tile<TA, TB>(S[t], k0 + DG_BK, kend, ra[t], rb[t]);
+                        }
                     for (int t = 0; t < DG_THREADS; ++t) gemm_compute(t, As, Bs, acc[t]);
                 }
                 for (int t = 0; t < DG_THREADS; ++t) gemm_epilogue(g, t, m0, n0, C, acc[t]);

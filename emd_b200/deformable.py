@@ -156,11 +156,14 @@ class _DeformNet(torch.autograd.Function):
             grads[2 * i], grads[2 * i + 1] = dW, db
         v_emb = None
         if E > 0 and ctx.needs_input_grad[2]:
-            order, seg_start, _ = segment_index(ids, I)
+            order, seg_start, max_chunks = segment_index(ids, I)
+            max_pts = max_chunks * L.emd_rigid_chunk_size()      # upper bound on the largest instance (cached with the index)
             v_emb = torch.empty(I, E, dtype=torch.float32, device=dev)
             g1 = g_emb[1] if len(g_emb) > 1 else None
-            _C.check(L.emd_deform_embed_grad(_C.ptr(g_emb[0]), _C.ptr(g1), E, _C.ptr(order), _C.ptr(seg_start), I,
-                                             _C.ptr(v_emb), st), "emd_deform_embed_grad")
+            eb = L.emd_deform_embed_grad_workspace_bytes(I, E, max_pts)
+            ews = torch.empty(eb, dtype=torch.uint8, device=dev)
+            _C.check(L.emd_deform_embed_grad(_C.ptr(g_emb[0]), _C.ptr(g1), E, _C.ptr(order), _C.ptr(seg_start), I, max_pts,
+                                             _C.ptr(ews), eb, _C.ptr(v_emb), st), "emd_deform_embed_grad")
         return (v_means, v_quats, v_emb, None, None, None, None, None, None, None, *grads)
 
 

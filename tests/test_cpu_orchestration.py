@@ -104,13 +104,17 @@ class FakeLib:
             _arr(v_quats, (N, 4))[:] = (go - u * (u * go).sum(1, keepdims=True)) / nrm
         return 0
 
-    def emd_deform_embed_grad(self, g0, g1, E, order, seg_start, I, v_emb, stream):
+    def emd_deform_embed_grad_workspace_bytes(self, I, E, max_pts):
+        return 16
+
+    def emd_deform_embed_grad(self, g0, g1, E, order, seg_start, I, max_pts, ws, wsb, v_emb, stream):
         seg = _arr(seg_start, (I + 1,), np.int64)
         N = int(seg[-1])
         od = _arr(order, (N,), np.int64)
         g = _arr(g0, (N, E)) + (_arr(g1, (N, E)) if g1 else 0)
         out = _arr(v_emb, (I, E))
         for i in range(I):
+            assert seg[i + 1] - seg[i] <= max_pts
             out[i] = g[od[seg[i]:seg[i + 1]]].sum(0)
         return 0
 

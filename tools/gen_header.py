@@ -26,7 +26,7 @@ GROUPS = [
      ["emd_voxel_lbs_fwd", "emd_voxel_lbs_bwd", "emd_smpl_weight_grad"]),
     ("Next (SURVEY 8f-4): DeformableNodes deformation network (K1g)",
      ["emd_deform_input_fwd", "emd_dense_fwd", "emd_dense_bwd_workspace_bytes", "emd_dense_bwd", "emd_deform_apply_fwd",
-      "emd_deform_apply_bwd", "emd_deform_embed_grad"]),
+      "emd_deform_apply_bwd", "emd_deform_embed_grad_workspace_bytes", "emd_deform_embed_grad"]),
     ("K2   projection", ["emd_projection_fwd", "emd_projection_bwd", "emd_dg_preprocess_fwd", "emd_dg_preprocess_bwd"]),
     ("K3   tile intersection", ["emd_scan_workspace_bytes", "emd_cumsum_i32_i64", "emd_exclusive_scan_u32",
                                 "emd_isect_emit", "emd_dg_isect_emit"]),
@@ -147,8 +147,10 @@ DOC = {
     "emd_deform_apply_fwd": "deformable.py:57-68: means + d_xyz and get_quats + delta_quat (get_quats = quats / |quats|, "
                             "vanilla.py:142-146) from the heads' output d[N,dcols] (3, or 7 with the quaternion head).",
     "emd_deform_apply_bwd": "VJP of emd_deform_apply_fwd: v_d[N,dcols], v_means (NULL when stop_optimizing_canonical_xyz), v_quats.",
+    "emd_deform_embed_grad_workspace_bytes": "Workspace bytes of emd_deform_embed_grad (per-chunk partial sums).",
     "emd_deform_embed_grad": "VJP of the instances_embedding[point_ids] gather (deformable.py:40): per-instance fixed-order sum of "
-                             "the embedding-column gradients g0 (+ g1) over the instance-sorted index (order, seg_start).",
+                             "the embedding-column gradients g0 (+ g1) over the instance-sorted index (order, seg_start); "
+                             "max_points_per_instance is any upper bound on the largest instance (sizes the grid).",
     "emd_scan_workspace_bytes": "Workspace bytes of the scans for n elements.",
     "emd_cumsum_i32_i64": "Inclusive cumulative sum (torch.cumsum of tiles_per_gauss in gsplat's isect_tiles); total -> device scalar.",
     "emd_exclusive_scan_u32": "Exclusive scan (radix-sort tables); in-place allowed.",
