@@ -4,8 +4,10 @@ OmniRe's DeformableNodes -- ``Embedder`` / ``get_embedder`` (``OmniRe/models/mod
 ``get_gaussians`` (``OmniRe/models/nodes/deformable.py:35-68``).
 
 Pinned: ``tests/golden/omnire_modules.npz`` holds outputs and parameter gradients of the reference's own
-``ConditionalDeformNetwork`` (``tests/golden/make_golden.py --modules``); ``tests/test_cpu_golden.py`` checks this file
-against them.  Parameters are passed as the module's ``state_dict`` (``linear.{i}.weight``, ``gaussian_warp.weight`` ...).
+``ConditionalDeformNetwork`` (``tests/golden/make_golden.py --modules``), and ``tests/golden/deformable_nodes.npz`` the
+outputs and every gradient of the reference's own ``DeformableNodes.get_gaussians`` (``--deformable``: the class itself,
+third-party imports stubbed); ``tests/test_cpu_golden.py`` checks this file -- composed with ``oracle/emd_rigid.py`` as
+``deformable.py`` composes with ``RigidNodes`` -- against both.  Parameters are passed as the module's ``state_dict`` (``linear.{i}.weight``, ``gaussian_warp.weight`` ...).
 """
 from __future__ import annotations
 

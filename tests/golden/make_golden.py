@@ -180,7 +180,7 @@ def main():
     print("golden fixtures written to", HERE)
 
 
-if __name__ == "__main__" and not any(a in sys.argv for a in ("--s3g", "--hexplane", "--losses", "--modules")):
+if __name__ == "__main__" and not any(a in sys.argv for a in ("--s3g", "--hexplane", "--losses", "--modules", "--deformable")):
     main()
 
 
@@ -399,3 +399,106 @@ def make_modules_golden():
 
 if __name__ == "__main__" and "--modules" in sys.argv:
     make_modules_golden()
+
+
+def make_deformable_golden():
+    """The reference's own ``DeformableNodes.get_gaussians`` (OmniRe/models/nodes/deformable.py:49-113, with
+    ``get_deformation`` :35-47 and the ``ConditionalDeformNetwork`` of models/modules.py) run on the CPU ->
+    tests/golden/deformable_nodes.npz: outputs and gradients w.r.t. the network, the instance embedding and the Gaussian
+    parameters, for the shipped control flags (use_deformgs_for_nonrigid, use_deformgs_after = 3000,
+    stop_optimizing_canonical_xyz) and for stop_optimizing_canonical_xyz = False."""
+    _stub(["open3d", "omegaconf", "pytorch3d", "pytorch3d.transforms", "pytorch3d.ops", "gsplat", "gsplat.rendering",
+           "gsplat.cuda", "gsplat.cuda._wrapper", "nvdiffrast", "nvdiffrast.torch", "imageio", "matplotlib",
+           "matplotlib.pyplot", "trimesh", "kornia", "third_party", "third_party.smplx", "third_party.smplx.smplx",
+           "third_party.smplx.smplx.lbs", "third_party.smplx.smplx.utils", "smplx", "tinycudann", "simple_knn",
+           "simple_knn._C", "diff_gauss", "plyfile", "lpips", "wandb", "pytorch_msssim", "mmcv"])
+    _cpuify()
+    g = torch.Generator().manual_seed(20250611)
+    sh_utils = load_file("ref_sh_utils", f"{REF}/S3Gaussian/utils/sh_utils.py")
+    sys.path.insert(0, f"{REF}/OmniRe")
+    basics = importlib.import_module("models.gaussians.basics")
+    sh = lambda deg, d, c: sh_utils.eval_sh(deg, c.transpose(1, 2), d / d.norm(dim=-1, keepdim=True))  # noqa: E731
+    basics.spherical_harmonics = sh
+    rigid_mod = importlib.import_module("models.nodes.rigid")
+    rigid_mod.spherical_harmonics = sh
+    deform_mod = importlib.import_module("models.nodes.deformable")
+    deform_mod.spherical_harmonics = sh
+    from emd_b200 import scenes
+    I, F, E = 3, 12, 16
+    rs = scenes.rigid_nodes(I, 60, g, num_frames=F)
+    rs.instances_quats = rs.instances_quats + 0.05 * torch.randn(rs.instances_quats.shape, generator=g)
+    node = object.__new__(deform_mod.DeformableNodes)
+    torch.nn.Module.__init__(node)
+    P = torch.nn.Parameter
+    node._means, node._quats, node._scales = P(rs.means.clone()), P(rs.quats.clone()), P(rs.scales.clone())
+    node._opacities, node._features_dc, node._features_rest = P(rs.opacities.clone()), P(rs.features_dc.clone()), P(rs.features_rest.clone())
+    node._embeddings, node.weight = P(rs.embeddings.clone()), P(rs.weight.clone())
+    node.point_ids = rs.point_ids.clone()
+    node.instances_quats, node.instances_trans = P(rs.instances_quats.clone()), P(rs.instances_trans.clone())
+    node.instances_fv = rs.instances_fv.clone()
+    node.instances_size = torch.tensor([0.8, 0.7, 1.7]) + 0.2 * torch.rand(I, 3, generator=g)
+    node.instances_embedding = P(torch.rand(I, E, generator=g))
+    node.normalized_timestamps = torch.linspace(0, 1, F)
+    for nm, out in (("rot_c", 1), ("rot_f", 1), ("trans_c", 3), ("trans_f", 3)):
+        lin = torch.nn.Linear(36, out)
+        lin.weight.data.copy_(rs.track[nm + "_w"]); lin.bias.data.copy_(rs.track[nm + "_b"])
+        setattr(node, "track_" + nm, lin)
+    node.temporal_embedding_dim, node.gaussian_embedding_dim = 32, 4
+    node.max_embeddings, node.min_embeddings, node.c2f_temporal_iter = 150, 30, 20000
+    for flag in ("no_temporal_embedding_dim", "no_gaussian_embedding_dim", "no_coarse_deform", "no_fine_deform",
+                 "no_c2f_temporal_embedding", "no_apply_embed_shs", "no_apply_embed_track"):
+        setattr(node, flag, False)
+    node.ball_gaussians, node.gaussian_2d, node.in_test_set = False, False, False
+    node.device = torch.device("cpu")
+    torch.manual_seed(99)
+    node.deform_network = deform_mod.ConditionalDeformNetwork(input_ch=3, D=8, W=32, embed_dim=E, x_multires=10, t_multires=10,
+                                                              deform_quat=True, deform_scale=False)
+    # a freshly initialised network deforms by ~1e-2; scale the heads up so the deformation is visible in the outputs
+    with torch.no_grad():
+        node.deform_network.gaussian_warp.weight.mul_(4.0)
+        node.deform_network.gaussian_rotation.weight.mul_(4.0)
+    out = dict(means=rs.means, quats=rs.quats, scales=rs.scales, opacities=rs.opacities, features_dc=rs.features_dc,
+               features_rest=rs.features_rest, embeddings=rs.embeddings, point_ids=rs.point_ids, weight=rs.weight,
+               instances_quats=rs.instances_quats, instances_trans=rs.instances_trans, instances_fv=rs.instances_fv,
+               instances_size=node.instances_size, instances_embedding=node.instances_embedding.detach(),
+               normalized_timestamps=node.normalized_timestamps, **{"track_" + k: v for k, v in rs.track.items()})
+    out = {k: v.numpy() for k, v in out.items()}
+    for k, v in node.deform_network.state_dict().items():
+        out[f"net_sd.{k}"] = v.numpy().copy()
+    cam = types.SimpleNamespace(camtoworlds=torch.eye(4))
+    cam.camtoworlds[:3, 3] = torch.tensor([0.3, -0.2, 1.6])
+    out["cam_pos"] = cam.camtoworlds[:3, 3].numpy()
+    cases = [(5, 8000, True), (11, 3001, False), (2, 3000, True)]      # (frame, step, stop_optimizing_canonical_xyz)
+    out["cases"] = np.array([(f, s, int(t)) for f, s, t in cases])
+    grad_of = dict(means=node._means, quats=node._quats, scales=node._scales, opacities=node._opacities,
+                   features_dc=node._features_dc, features_rest=node._features_rest, embeddings=node._embeddings,
+                   weight=node.weight, instances_quats=node.instances_quats, instances_trans=node.instances_trans,
+                   instances_embedding=node.instances_embedding)
+    for ci, (frame, step, stop) in enumerate(cases):
+        node.cur_frame, node.step = frame, step
+        node.ctrl_cfg = types.SimpleNamespace(sh_degree_interval=1000, sh_degree=3, use_deformgs_for_nonrigid=True,
+                                              use_deformgs_after=3000, stop_optimizing_canonical_xyz=stop)
+        node.zero_grad(set_to_none=True)
+        gs = node.get_gaussians(cam)
+        loss = 0.0
+        for k in ("_means", "_opacities", "_rgbs", "_scales", "_quats"):
+            out[f"c{ci}_gs{k}"] = gs[k].detach().numpy()
+            cot = torch.randn(gs[k].shape, generator=g)
+            out[f"c{ci}_cot{k}"] = cot.numpy()
+            loss = loss + (gs[k] * cot).sum()
+        loss.backward()
+        for k, p in grad_of.items():
+            if p.grad is not None:
+                out[f"c{ci}_grad_{k}"] = p.grad.numpy().copy()
+        for k, p in node.deform_network.named_parameters():
+            if p.grad is not None:
+                out[f"c{ci}_netgrad.{k}"] = p.grad.numpy().copy()
+        lx = node._gs_cache["local_xyz_deformed"]
+        if lx is not None:
+            out[f"c{ci}_local_xyz_deformed"] = lx.detach().numpy()
+    np.savez_compressed(f"{HERE}/deformable_nodes.npz", **out)
+    print("wrote deformable_nodes.npz with", len(out), "arrays")
+
+
+if __name__ == "__main__" and "--deformable" in sys.argv:
+    make_deformable_golden()

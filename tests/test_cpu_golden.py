@@ -195,3 +195,57 @@ def test_conditional_deform_network_golden():
     for k, p in sd.items():
         ref = _t(z[f"net_grad.{k}"])
         assert (p.grad - ref).abs().max() <= 1e-5 * max(1.0, ref.abs().max().item()), k
+
+
+def test_deformable_nodes_golden():
+    """The oracle's DeformableNodes composition (oracle/deform_network.py:deformed_canonical -> oracle/emd_rigid.py:
+    get_gaussians) against the reference's own ``DeformableNodes.get_gaussians`` run on the CPU: outputs, the cached
+    deformed canonical points and every gradient (network, instance embedding, Gaussian parameters, EMD tables, poses),
+    for stop_optimizing_canonical_xyz on / off and for a step before use_deformgs_after (plain rigid route)."""
+    from oracle import deform_network as ON
+    from oracle import emd_rigid as ER
+    z = np.load(f"{G}/deformable_nodes.npz")
+    heads = ("rot_c_w", "rot_c_b", "rot_f_w", "rot_f_b", "trans_c_w", "trans_c_b", "trans_f_w", "trans_f_b")
+    names = ("means", "quats", "scales", "opacities", "features_dc", "features_rest", "embeddings", "weight",
+             "instances_quats", "instances_trans", "instances_embedding")
+    ts = z["normalized_timestamps"].tolist()
+    for ci, (frame, step, stop) in enumerate(z["cases"].tolist()):
+        c = {k: _t(z[k]).clone().requires_grad_(True) for k in names}
+        net = {k[len("net_sd."):]: _t(z[k]).clone().requires_grad_(True) for k in z.files if k.startswith("net_sd.")}
+        p = ER.RigidEMD(point_ids=_t(z["point_ids"])[:, 0], embeddings=c["embeddings"], weight=c["weight"],
+                        instances_quats=c["instances_quats"], instances_trans=c["instances_trans"],
+                        instances_fv=_t(z["instances_fv"]), **{k: _t(z["track_" + k]) for k in heads})
+        if step > 3000:
+            m, q = ON.deformed_canonical(net, c["means"], c["quats"], _t(z["point_ids"]), _t(z["instances_size"]),
+                                         c["instances_embedding"], ts[frame], D=8, stop_optimizing_canonical_xyz=bool(stop))
+            assert torch.allclose(m, _t(z[f"c{ci}_local_xyz_deformed"]), atol=1e-6)
+        else:
+            m, q = c["means"], c["quats"]
+            assert f"c{ci}_local_xyz_deformed" not in z.files
+        out = ER.get_gaussians(p, m, q, c["scales"], c["opacities"], c["features_dc"], c["features_rest"], int(frame),
+                               int(step), _t(z["cam_pos"]))
+        loss = 0.0
+        for k in ("_means", "_opacities", "_rgbs", "_scales", "_quats"):
+            ref = _t(z[f"c{ci}_gs{k}"])
+            assert out[k].shape == ref.shape, (ci, k)
+            assert (out[k] - ref).abs().max() <= 3e-6 * max(1.0, ref.abs().max().item()), (ci, k)
+            loss = loss + (out[k] * _t(z[f"c{ci}_cot{k}"])).sum()
+        loss.backward()
+        for k in names:
+            key = f"c{ci}_grad_{k}"
+            if key not in z.files:
+                assert c[k].grad is None or float(c[k].grad.abs().max()) == 0.0, (ci, k)
+                continue
+            ref = _t(z[key])
+            got = c[k].grad if c[k].grad is not None else torch.zeros_like(ref)
+            assert (got - ref).abs().max() <= 2e-5 * max(1.0, ref.abs().max().item()), (ci, k)
+        for k in net:
+            key = f"c{ci}_netgrad.{k}"
+            if key not in z.files:
+                assert net[k].grad is None, (ci, k)
+                continue
+            ref = _t(z[key])
+            assert (net[k].grad - ref).abs().max() <= 2e-5 * max(1.0, ref.abs().max().item()), (ci, k)
+        if step > 3000:
+            assert float(net["linear.0.weight"].grad.abs().max()) > 0 and float(c["instances_embedding"].grad.abs().max()) > 0
+            assert (c["means"].grad is None) == bool(stop)     # stop_optimizing_canonical_xyz detaches the canonical means
