@@ -349,3 +349,48 @@ def test_smpl_weight_grad_host_math(hostlib):
     f(_fp(W), _fp(A), _fp(x), _fp(q), _fp(cg), _fp(cq), N, out.ctypes.data_as(P))
     ref = W.grad.numpy()
     assert np.abs(out - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_projection_tile_edge_cases_bit_exact(hostlib):
+    """Adversarial placements: projected means EXACTLY on tile corners / edges (the optical axis lands on
+    pixel (480, 320) = tile corner (30, 20); offsets of whole tiles along each axis), radii that end exactly on a tile
+    edge, Gaussians at the image border and just outside it, at the near plane, and with a zero scale axis.  Radii,
+    means2d, depths, conics, tile rectangles and tiles-per-Gaussian must stay bit-identical to the oracle."""
+    W, H = 960, 640
+    viewmats, Ks, _ = scenes.cameras((0.0,), W, H)
+    fx, cx, cy = float(Ks[0, 0, 0]), float(Ks[0, 0, 2]), float(Ks[0, 1, 2])
+    assert cx == 480.0 and cy == 320.0
+    c2w = torch.linalg.inv(viewmats[0])
+    pts_cam, scl = [], []
+    for z in (0.05, -1.0, 0.1, 0.10000001, 1.0, 5.15, 20.0, 103.0):   # 5.15 = fx / 200, 103 = fx / 10: whole-pixel offsets below
+        for du in (0.0, 16.0, -16.0, 160.0, 479.0, 480.0, -480.0, -481.0, 496.0, 3000.0):
+            for dv in (0.0, 16.0, -320.0, 319.0, 321.0):
+                pts_cam.append([du * z / fx, dv * z / fx, z])
+                # sigma chosen so that 3 sigma in pixels is an integer number of tiles for some of them
+                scl.append([16.0 / 3.0 * z / fx, 32.0 / 3.0 * z / fx, 0.0 if du == 160.0 else 1e-3])
+    pc = torch.tensor(pts_cam, dtype=torch.float32)
+    means = (c2w[:3, :3] @ pc.T).T + c2w[:3, 3]
+    N = means.shape[0]
+    quats = torch.zeros(N, 4); quats[:, 0] = 1.0
+    quats[::3] = torch.tensor([0.9238795, 0.0, 0.0, 0.3826834])
+    scales = torch.tensor(scl, dtype=torch.float32)
+    radii, m2d, depths, conics, comps = G.projection(means, quats, scales, viewmats, Ks, W, H, 0.3, 0.1, 1e10, 0.0)
+    r2 = np.zeros((1, N), np.int32); m2 = np.zeros((1, N, 2), np.float32); d2 = np.zeros((1, N), np.float32)
+    c2 = np.zeros((1, N, 3), np.float32); cp = np.zeros((1, N), np.float32); tp = np.zeros((1, N), np.int32)
+    rc = np.zeros((1, N, 4), np.int32)
+    f = hostlib.emd_host_projection_fwd
+    f.argtypes = [P] * 5 + [ctypes.c_int64] * 2 + [ctypes.c_int] * 2 + [ctypes.c_float] * 4 + [ctypes.c_int] * 2 + [P] * 7
+    f(_fp(means), _fp(quats), _fp(scales), _fp(viewmats), _fp(Ks), N, 1, W, H, 0.3, 0.1, 1e10, 0.0, 60, 40,
+      *[a.ctypes.data_as(P) for a in (r2, m2, d2, c2, cp, tp, rc)])
+    vis = radii[0] > 0
+    assert 0.3 * N < int(vis.sum()) < N                      # both culled and visible placements are present
+    on_edge = vis & ((m2d[0, :, 0] % 16 == 0) | (m2d[0, :, 1] % 16 == 0))
+    assert int(on_edge.sum()) >= 20                          # means that really sit on tile edges after fp32 projection
+    assert np.array_equal(r2, radii.numpy())
+    assert np.array_equal(m2.view(np.int32), m2d.numpy().view(np.int32))
+    assert np.array_equal(d2.view(np.int32), depths.numpy().view(np.int32))
+    assert np.array_equal(c2.view(np.int32), conics.numpy().view(np.int32))
+    tpg, ids, flat, bits = G.isect_tiles(m2d, radii, depths, 16, 60, 40)
+    assert np.array_equal(tp, tpg.numpy())
+    x0, y0, x1, y1 = G.tile_rects(m2d, radii, 16, 60, 40)
+    assert np.array_equal(rc, torch.stack([x0, y0, x1, y1], -1).numpy().astype(np.int32))
