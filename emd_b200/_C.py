@@ -57,6 +57,8 @@ _SIGS = {
     "emd_dense_bwd_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "emd_dense_bwd": (c_int, [P, c_int64, P, P, c_int64, c_int64, c_int, c_int, P, c_int64, c_int, c_int, P, c_int64, P, P,
                               P, c_size_t, P]),
+    "emd_dense_tc_enabled": (c_int, []),
+    "emd_dense_set_tc": (None, [c_int]),
     "emd_deform_input_fwd": (c_int, [P, P, P, P, c_float, c_int, c_int, c_int, c_int64, P, c_int64, P, c_int64, P]),
     "emd_deform_embed_grad_workspace_bytes": (c_size_t, [c_int, c_int, c_int64]),
     "emd_deform_embed_grad": (c_int, [P, P, c_int, P, P, c_int, c_int64, P, c_size_t, P, P]),

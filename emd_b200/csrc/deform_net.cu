@@ -29,6 +29,11 @@
 #define DG_DEFAULT_MINB 2
 #endif
 
+// experimental tensor-core path (deform_net_tc.cu): 1 when it took the call (status in *rc), 0 -> SIMT path below.
+// Off unless emd_dense_set_tc(1) / EMD_DENSE_TC=1.
+int emd_dense_tc_try(int dgrad, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, const float* mask,
+                     int64_t ldmask, float* Y, int64_t ldy, int64_t M, int K, int N, int relu, cudaStream_t stream, int* rc);
+
 namespace {
 
 // C[m,n] = sum_k A(m,k) B(k,n) -- tile logic in dense_math.cuh (shared with the host emulation the CPU tests run)
@@ -119,6 +124,8 @@ extern "C" int emd_dense_fwd(const float* X, int64_t ldx, const float* W, const 
     if (M == 0) return EMD_OK;
     EMD_CHECK_ARG(X && W && Y, "emd_dense_fwd: null argument");
     EMD_CHECK_ARG(emd_cdiv(Nout, DG_BN) <= 65535, "emd_dense_fwd: Nout=%d too wide", Nout);
+    int rc_tc = EMD_OK;
+    if (emd_dense_tc_try(0, X, ldx, W, K, b, nullptr, 0, Y, ldy, M, K, Nout, relu_out, stream, &rc_tc)) return rc_tc;
     const GemmArgs g = dense_fwd_args(X, ldx, W, b, M, K, Nout, relu_out, Y, ldy);
     EMD_LAUNCH(EK_DENSE_FWD, stream, (launch_sgemm<false, true>(g, 1, stream)));
     EMD_CHECK_LAUNCH("emd_dense_fwd");
@@ -147,9 +154,14 @@ extern "C" int emd_dense_bwd(const float* X, int64_t ldx, const float* W, const 
                       "emd_dense_bwd: column window [%d, %d) of K=%d, lddx=%lld ldmask=%lld", col0, col0 + ncols, K,
                       (long long)lddx, (long long)ldmask);
         if (M > 0) {
-            const GemmArgs g = dense_dgrad_args(W, dZ, lddz, M, K, Nout, dX, lddx, col0, ncols, mask, ldmask);
-            EMD_LAUNCH(EK_DENSE_BWD, stream, (launch_sgemm<false, false>(g, 1, stream)));
-            EMD_CHECK_LAUNCH("emd_dense_bwd(dgrad)");
+            int rc_tc = EMD_OK;
+            if (emd_dense_tc_try(1, dZ, lddz, W + col0, K, nullptr, mask, ldmask, dX, lddx, M, Nout, ncols, 0, stream, &rc_tc)) {
+                if (rc_tc != EMD_OK) return rc_tc;
+            } else {
+                const GemmArgs g = dense_dgrad_args(W, dZ, lddz, M, K, Nout, dX, lddx, col0, ncols, mask, ldmask);
+                EMD_LAUNCH(EK_DENSE_BWD, stream, (launch_sgemm<false, false>(g, 1, stream)));
+                EMD_CHECK_LAUNCH("emd_dense_bwd(dgrad)");
+            }
         }
     }
     if (!dW && !db) return EMD_OK;

@@ -25,7 +25,8 @@ GROUPS = [
     ("Next (SURVEY 8f-4): voxel LBS weights of the SMPL nodes (K1f)",
      ["emd_voxel_lbs_fwd", "emd_voxel_lbs_bwd", "emd_smpl_weight_grad"]),
     ("Next (SURVEY 8f-4): DeformableNodes deformation network (K1g)",
-     ["emd_deform_input_fwd", "emd_dense_fwd", "emd_dense_bwd_workspace_bytes", "emd_dense_bwd", "emd_deform_apply_fwd",
+     ["emd_deform_input_fwd", "emd_dense_fwd", "emd_dense_bwd_workspace_bytes", "emd_dense_bwd", "emd_dense_tc_enabled",
+      "emd_dense_set_tc", "emd_deform_apply_fwd",
       "emd_deform_apply_bwd", "emd_deform_embed_grad_workspace_bytes", "emd_deform_embed_grad"]),
     ("K2   projection", ["emd_projection_fwd", "emd_projection_bwd", "emd_dg_preprocess_fwd", "emd_dg_preprocess_bwd"]),
     ("K3   tile intersection", ["emd_scan_workspace_bytes", "emd_cumsum_i32_i64", "emd_exclusive_scan_u32",
@@ -144,6 +145,10 @@ DOC = {
     "emd_dense_bwd": "VJP of emd_dense_fwd given dZ = dL/d(pre-activation): dX on the column window [col0, col0+ncols) of the "
                      "operand, multiplied by (mask > 0) where mask is the operand's producer's ReLU output (may be NULL); "
                      "dW[Nout,K], db[Nout] by fixed-order reductions.  dX, dW, db may each be NULL.",
+    "emd_dense_tc_enabled": "1 when the EXPERIMENTAL tcgen05 (3xTF32) path of emd_dense_fwd / emd_dense_bwd's data gradient is "
+                            "selected (default 0; EMD_DENSE_TC=1 or emd_dense_set_tc).  Written in round 1 after the GPU budget "
+                            "was spent: compiled, not yet run on hardware (csrc/deform_net_tc.cu).",
+    "emd_dense_set_tc": "Select (1) / deselect (0) the experimental tensor-core path; process-wide, for bring-up and measurement.",
     "emd_deform_apply_fwd": "deformable.py:57-68: means + d_xyz and get_quats + delta_quat (get_quats = quats / |quats|, "
                             "vanilla.py:142-146) from the heads' output d[N,dcols] (3, or 7 with the quaternion head).",
     "emd_deform_apply_bwd": "VJP of emd_deform_apply_fwd: v_d[N,dcols], v_means (NULL when stop_optimizing_canonical_xyz), v_quats.",
