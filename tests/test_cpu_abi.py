@@ -61,3 +61,14 @@ def test_no_cpu_fallback():
     with pytest.raises(_C.EmdError):
         emd_b200.rasterization(z, torch.zeros(4, 4), z, torch.zeros(4), z, torch.eye(4)[None], torch.eye(3)[None],
                                32, 32, packed=False)
+
+
+def test_experimental_tensor_core_dense_path_is_off_by_default(monkeypatch):
+    """csrc/deform_net_tc.cu has not run on hardware yet: nothing may select it implicitly."""
+    import subprocess
+    import sys
+    code = ("import os; os.environ.pop('EMD_DENSE_TC', None); from emd_b200 import _C; "
+            "print(_C.lib().emd_dense_tc_enabled())")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip().endswith("0")
