@@ -27,14 +27,16 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tc_stage_math.cuh"
 
 namespace {
 
-constexpr int DT_THREADS = 256;
-constexpr int DT_KC = 32;                                   // reduction columns per chunk (8 core-matrix columns)
-constexpr int DT_NMAX = 256;                                // output columns per tile (UMMA N <= 256)
+constexpr int DT_THREADS = DTS_THREADS;
+constexpr int DT_KC = DTS_KC;                               // reduction columns per chunk (8 core-matrix columns)
+constexpr int DT_NMAX = DTS_NMAX;                           // output columns per tile (UMMA N <= 256)
 constexpr int DT_A_BYTES = (DT_KC / 4) * TC_A_LBO;          // one of {hi, lo} of an A chunk
-constexpr int DT_B_LBO = DT_NMAX * 16 + 16;                 // bytes between K-adjacent core-matrix columns of B
+constexpr int DT_B_LBO = DTS_B_LBO;                         // bytes between K-adjacent core-matrix columns of B
+static_assert(TC_A_LBO == DTS_A_LBO && TC_SBO == DTS_SBO && TC_ROWS == DTS_ROWS, "tc_stage_math.cuh mirrors tc_common.cuh");
 constexpr int DT_B_BYTES = (DT_KC / 4) * DT_B_LBO;          // one of {hi, lo} of a B chunk
 constexpr int DT_STAGE_BYTES = 2 * DT_A_BYTES + 2 * DT_B_BYTES;
 constexpr int DT_SMEM_BYTES = 2 * DT_STAGE_BYTES;           // 197 632 B
@@ -88,14 +90,15 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(const DenseTcAr
     bool pend0 = false, pend1 = false;
 
     // thread -> (row, core-matrix column) of the 128 x 32 A chunk: 4 float4 per thread, rows cr + 32 i (as mlp_tc.cu)
-    const int cj = tid & 7, cr = tid >> 3;
     const int64_t n_tiles = (a.M + TC_ROWS - 1) / TC_ROWS;
     float4 pre[4];
     auto load_a = [&](int64_t row0, int c) {
-        const int jg = c * (DT_KC / 4) + cj;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int64_t row = row0 + cr + 32 * i;
+            int r, cj;
+            dts_a_elem(tid, i, r, cj);
+            const int jg = c * (DT_KC / 4) + cj;
+            const int64_t row = row0 + r;
             pre[i] = (row < a.M && jg < kq) ? __ldg(reinterpret_cast<const float4*>(a.A + row * a.lda) + jg) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
@@ -121,31 +124,33 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(const DenseTcAr
                 const float4 x = pre[i];
                 float4 hi, lo;
                 split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
-                *reinterpret_cast<float4*>(sAhi + cj * TC_A_LBO + (cr + 32 * i) * 16) = hi;
-                *reinterpret_cast<float4*>(sAlo + cj * TC_A_LBO + (cr + 32 * i) * 16) = lo;
+                int r, cj;
+                dts_a_elem(tid, i, r, cj);
+                *reinterpret_cast<float4*>(sAhi + dts_a_store_offset(r, cj)) = hi;
+                *reinterpret_cast<float4*>(sAlo + dts_a_store_offset(r, cj)) = lo;
             }
             // ---- B: this chunk of W (L2-resident) -> hi/lo split -> canonical layout: element (n, k) of the chunk at
             //      (k >> 2) * DT_B_LBO + n * 16 + (k & 3) * 4 ----
             if (!TB) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int e = tid + DT_THREADS * i;
-                    const int n = e >> 3, j = e & 7;
+                    int n, j;
+                    dts_b_elem_fwd(tid, i, n, j);
                     const int jg = c * (DT_KC / 4) + j;
                     if (n < npad) {
                         const float4 w = (n < a.N && jg < kq) ? __ldg(reinterpret_cast<const float4*>(a.W + (int64_t)n * a.ldw) + jg)
                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
                         float4 hi, lo;
                         split_tf32(w.x, hi.x, lo.x); split_tf32(w.y, hi.y, lo.y); split_tf32(w.z, hi.z, lo.z); split_tf32(w.w, hi.w, lo.w);
-                        *reinterpret_cast<float4*>(sBhi + j * DT_B_LBO + n * 16) = hi;
-                        *reinterpret_cast<float4*>(sBlo + j * DT_B_LBO + n * 16) = lo;
+                        *reinterpret_cast<float4*>(sBhi + dts_b_store_offset_fwd(n, j)) = hi;
+                        *reinterpret_cast<float4*>(sBlo + dts_b_store_offset_fwd(n, j)) = lo;
                     }
                 }
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int e = tid + DT_THREADS * i;
-                    const int k = e >> 6, n = (e & 63) * 4;       // W row k of the chunk, 4 consecutive output columns
+                    int k, n;                                       // W row k of the chunk, 4 consecutive output columns
+                    dts_b_elem_dgrad(tid, i, k, n);
                     const int kg = c * DT_KC + k;
                     if (n < npad) {
                         const float4 w = (kg < a.K && n < a.N) ? __ldg(reinterpret_cast<const float4*>(a.W + (int64_t)kg * a.ldw + n))
@@ -155,7 +160,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(const DenseTcAr
                         for (int q = 0; q < 4; ++q) {
                             float hi, lo;
                             split_tf32(wv[q], hi, lo);
-                            const int off = (k >> 2) * DT_B_LBO + (n + q) * 16 + (k & 3) * 4;
+                            const int off = dts_b_store_offset_dgrad(k, n + q);
                             *reinterpret_cast<float*>(sBhi + off) = hi;
                             *reinterpret_cast<float*>(sBlo + off) = lo;
                         }
@@ -175,10 +180,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(const DenseTcAr
                 const int s1 = min(s0 + DT_KC / 8, ksteps);
                 for (int s = s0; s < s1; ++s) {
                     const int sl = s - s0;   // k-step inside the stage
-                    const uint64_t dAh = umma_desc(aHi + 2 * sl * TC_A_LBO, TC_A_LBO, TC_SBO);
-                    const uint64_t dAl = umma_desc(aLo + 2 * sl * TC_A_LBO, TC_A_LBO, TC_SBO);
-                    const uint64_t dBh = umma_desc(bHi + 2 * sl * DT_B_LBO, DT_B_LBO, TC_SBO);
-                    const uint64_t dBl = umma_desc(bLo + 2 * sl * DT_B_LBO, DT_B_LBO, TC_SBO);
+                    const uint64_t dAh = umma_desc(aHi + dts_kstep_offset(sl, TC_A_LBO), TC_A_LBO, TC_SBO);
+                    const uint64_t dAl = umma_desc(aLo + dts_kstep_offset(sl, TC_A_LBO), TC_A_LBO, TC_SBO);
+                    const uint64_t dBh = umma_desc(bHi + dts_kstep_offset(sl, DT_B_LBO), DT_B_LBO, TC_SBO);
+                    const uint64_t dBl = umma_desc(bLo + dts_kstep_offset(sl, DT_B_LBO), DT_B_LBO, TC_SBO);
                     umma_tf32(tmem, dAl, dBh, idesc, s > 0 ? 1u : 0u);   // small terms first
                     umma_tf32(tmem, dAh, dBl, idesc, 1u);
                     umma_tf32(tmem, dAh, dBh, idesc, 1u);

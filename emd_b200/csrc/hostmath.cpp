@@ -322,6 +322,59 @@ extern "C" void emd_host_smpl_weight_grad(const float* Wn, const float* A, const
         smpl_point_weight_grad(Wn + n * SMPL_J, A, x + n * 3, q + n * 4, g + n * 3, vg + n * 4, v_W + n * SMPL_J);
 }
 
+// ---- tensor-core staging maps (tc_stage_math.cuh): replay every thread's shared-memory writes of one chunk, then read
+//      the operand back the way the UMMA descriptor walks it (canonical K-major layout) -------------------------------------
+#include <string.h>
+#include "tc_stage_math.cuh"
+
+// which = 0: A chunk [128 x 32] from src[128][32]; 1: B chunk forward from src[n][32] (n < npad); 2: B chunk dgrad from
+// src[32][npad].  out[rows][32] = the operand as k-step descriptors (start = kstep offset, LBO, SBO = 128) expose it;
+// returns the number of bytes written more than once (must be 0) and fills *untouched with the count of operand bytes
+// of the [rows x 32] region no thread wrote.
+extern "C" int emd_host_tc_stage_replay(int which, int npad, const float* src, float* out, int* untouched) {
+    const int lbo = which == 0 ? DTS_A_LBO : DTS_B_LBO;
+    const int rows = which == 0 ? DTS_ROWS : npad;
+    const int bytes = (DTS_KC / 4) * lbo;
+    std::vector<unsigned char> mem(bytes, 0), hit(bytes, 0);
+    int twice = 0;
+    auto put = [&](int off, const float* v, int n) {
+        for (int b = 0; b < 4 * n; ++b) { twice += hit[off + b]; hit[off + b] = 1; }
+        memcpy(mem.data() + off, v, 4 * n);
+    };
+    for (int tid = 0; tid < DTS_THREADS; ++tid) {
+        if (which == 0) {
+            for (int i = 0; i < 4; ++i) {
+                int r, cj;
+                dts_a_elem(tid, i, r, cj);
+                put(dts_a_store_offset(r, cj), src + r * DTS_KC + 4 * cj, 4);
+            }
+        } else if (which == 1) {
+            for (int i = 0; i < 8; ++i) {
+                int n, j;
+                dts_b_elem_fwd(tid, i, n, j);
+                if (n < npad) put(dts_b_store_offset_fwd(n, j), src + n * DTS_KC + 4 * j, 4);
+            }
+        } else {
+            for (int i = 0; i < 8; ++i) {
+                int k, n;
+                dts_b_elem_dgrad(tid, i, k, n);
+                if (n < npad)
+                    for (int q = 0; q < 4; ++q) put(dts_b_store_offset_dgrad(k, n + q), src + k * npad + n + q, 1);
+            }
+        }
+    }
+    int miss = 0;
+    for (int r = 0; r < rows; ++r)
+        for (int k = 0; k < DTS_KC; ++k) {
+            // k-step sl = k / 8 starts at dts_kstep_offset(sl); inside it the element is column k % 8
+            const int off = dts_kstep_offset(k / 8, lbo) + dts_canonical_offset(r, k % 8, lbo);
+            for (int b = 0; b < 4; ++b) miss += !hit[off + b];
+            memcpy(out + r * DTS_KC + k, mem.data() + off, 4);
+        }
+    *untouched = miss;
+    return twice;
+}
+
 // ---- Adam (adam_math.cuh) -----------------------------------------------------------------------------------
 #include "adam_math.cuh"
 

@@ -394,3 +394,23 @@ def test_projection_tile_edge_cases_bit_exact(hostlib):
     assert np.array_equal(tp, tpg.numpy())
     x0, y0, x1, y1 = G.tile_rects(m2d, radii, 16, 60, 40)
     assert np.array_equal(rc, torch.stack([x0, y0, x1, y1], -1).numpy().astype(np.int32))
+
+
+@pytest.mark.parametrize("which,npad", [(0, 128), (1, 256), (1, 16), (1, 112), (2, 256), (2, 16), (2, 48)])
+def test_tensor_core_staging_maps(hostlib, which, npad):
+    """tc_stage_math.cuh (the thread -> shared-memory maps of the experimental tcgen05 GEMM, csrc/deform_net_tc.cu): every
+    thread's writes of one chunk replayed on the host must tile the operand exactly once, and reading it back the way
+    the UMMA k-step descriptors walk the canonical K-major layout must give the source matrix (A chunk; W chunk in the
+    forward orientation [n][k]; W chunk in the data-gradient orientation [k][n])."""
+    rows = 128 if which == 0 else npad
+    g = torch.Generator().manual_seed(which * 1000 + npad)
+    src = torch.randn(rows, 32, generator=g) if which != 2 else torch.randn(32, npad, generator=g)
+    out = np.zeros((rows, 32), np.float32)
+    miss = ctypes.c_int(-1)
+    f = hostlib.emd_host_tc_stage_replay
+    f.argtypes = [ctypes.c_int, ctypes.c_int, P, P, ctypes.POINTER(ctypes.c_int)]
+    f.restype = ctypes.c_int
+    twice = f(which, npad, _fp(src), out.ctypes.data_as(P), ctypes.byref(miss))
+    assert twice == 0 and miss.value == 0
+    want = src.numpy() if which != 2 else src.numpy().T
+    assert np.array_equal(out, want)
