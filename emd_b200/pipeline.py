@@ -33,6 +33,9 @@ class StreetScene:
         self.bg = {k: P(v) for k, v in bg.items()}
         self.rigid = None
         self.smpl = None
+        # further node classes (``DeformableNodesEMD`` -- OmniRe's fourth Gaussian class, scene_graph.py:195-227 -- or more
+        # rigid / SMPL groups): anything with ``p``, ``track``, ``get_gaussians / get_geometry / get_colors``
+        self.extra_nodes: List = []
         if rigid is not None:
             rp = dict(_means=P(rigid.means), _quats=P(rigid.quats), _scales=P(rigid.scales),
                       _opacities=P(rigid.opacities), _features_dc=P(rigid.features_dc),
@@ -51,21 +54,24 @@ class StreetScene:
                                      dict(J_canonical=smpl.J_canonical.to(device), A0_inv=smpl.A0_inv.to(device),
                                           W=smpl.W.to(device)))
 
+    def add_node(self, node) -> None:
+        """Append a node class built by the caller on this scene's device (e.g. ``emd_b200.deformable.DeformableNodesEMD``)."""
+        self.extra_nodes.append(node)
+
+    def _nodes(self):
+        return [n for n in (self.rigid, self.smpl) if n is not None] + self.extra_nodes
+
     def parameters(self) -> List[Tensor]:
         ps = [v for v in self.bg.values() if v.requires_grad]
-        for node in (self.rigid, self.smpl):
-            if node is not None:
-                ps += [v for v in node.p.values() if isinstance(v, Tensor) and v.requires_grad]
-                ps += [v for v in node.track.values() if v.requires_grad]
+        for node in self._nodes():
+            ps += [v for v in node.p.values() if isinstance(v, Tensor) and v.requires_grad]
+            ps += [v for v in node.track.values() if v.requires_grad]
+            ps += [v for v in getattr(node, "network", {}).values() if v.requires_grad]   # DeformableNodes' deform_network
         return ps
 
     @property
     def num_gaussians(self) -> int:
-        n = self.bg["means"].shape[0]
-        for node in (self.rigid, self.smpl):
-            if node is not None:
-                n += node.p["_means"].shape[0]
-        return n
+        return self.bg["means"].shape[0] + sum(node.p["_means"].shape[0] for node in self._nodes())
 
     def collect_gaussians(self, cam_centers, frame: int, step: int):
         """``collect_gaussians`` (base.py:342-383): per-class activated Gaussians, concatenated.
@@ -76,9 +82,7 @@ class StreetScene:
         rgbs, opac, sc, qn = activate_gaussians(b["means"], b["features_dc"], b["features_rest"], b["opacities"],
                                                 b["scales"], b["quats"], cam_centers, n)
         parts = [dict(_means=b["means"], _opacities=opac[:, None], _rgbs=rgbs, _scales=sc, _quats=qn)]
-        for node in (self.rigid, self.smpl):
-            if node is None:
-                continue
+        for node in self._nodes():
             gs = node.get_gaussians(cam_centers, frame, step)
             if gs is not None:
                 parts.append(gs)
@@ -95,9 +99,7 @@ class StreetScene:
         parts = [dict(_means=b["means"], _opacities=opac[:, None], _scales=sc, _quats=qn)]
         n = min(step // 1000, 3)
         thunks = [lambda cams: sh_colors(b["means"], b["features_dc"], b["features_rest"], cams, n)]
-        for node in (self.rigid, self.smpl):
-            if node is None:
-                continue
+        for node in self._nodes():
             gs = node.get_geometry(frame, step)
             if gs is not None:
                 parts.append(gs)
