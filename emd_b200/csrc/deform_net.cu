@@ -34,6 +34,10 @@
 int emd_dense_tc_try(int dgrad, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, const float* mask,
                      int64_t ldmask, float* Y, int64_t ldy, int64_t M, int K, int N, int relu, cudaStream_t stream, int* rc);
 
+size_t emd_dense_tc_wgrad_partial_floats(int64_t M, int K, int Nout);
+int emd_dense_tc_try_wgrad(const float* X, int64_t ldx, const float* dZ, int64_t lddz, int64_t M, int K, int Nout, float* partial,
+                           int* splits_out, cudaStream_t stream, int* rc);
+
 namespace {
 
 // C[m,n] = sum_k A(m,k) B(k,n) -- tile logic in dense_math.cuh (shared with the host emulation the CPU tests run)
@@ -132,9 +136,16 @@ extern "C" int emd_dense_fwd(const float* X, int64_t ldx, const float* W, const 
     return EMD_OK;
 }
 
+static size_t dense_wgrad_partial_floats(int64_t M, int K, int Nout) {
+    const DenseSplit s = dense_split(M, K, Nout);
+    const size_t simt = (size_t)s.splits * (size_t)Nout * (size_t)K;
+    const size_t tc = emd_dense_tc_wgrad_partial_floats(M, K, Nout);     // 0 unless the experimental path is selected
+    return simt > tc ? simt : tc;
+}
+
 extern "C" size_t emd_dense_bwd_workspace_bytes(int64_t M, int K, int Nout) {
     const DenseSplit s = dense_split(M, K, Nout);
-    return ((size_t)s.splits * (size_t)Nout * (size_t)K + (size_t)s.col_chunks * (size_t)Nout) * sizeof(float);
+    return (dense_wgrad_partial_floats(M, K, Nout) + (size_t)s.col_chunks * (size_t)Nout) * sizeof(float);
 }
 
 // VJP of emd_dense_fwd given dZ[M, 0:Nout] (row stride lddz) = dL/d(pre-activation) (the caller's upstream kernel
@@ -171,17 +182,22 @@ extern "C" int emd_dense_bwd(const float* X, int64_t ldx, const float* W, const 
         return EMD_ERR_WORKSPACE;
     }
     float* wpart = static_cast<float*>(workspace);
-    float* bpart = wpart + (size_t)s.splits * Nout * K;
+    float* bpart = wpart + dense_wgrad_partial_floats(M, K, Nout);
     if (dW) {
         if (M == 0) {
             cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)Nout * K, stream);
         } else {
-            const GemmArgs g = dense_wgrad_args(X, ldx, dZ, lddz, M, K, Nout, s, wpart);
-            EMD_LAUNCH(EK_DENSE_BWD, stream, (launch_sgemm<true, false>(g, s.splits, stream)));
-            EMD_CHECK_LAUNCH("emd_dense_bwd(wgrad)");
+            int splits = s.splits, rc_tc = EMD_OK;
+            if (emd_dense_tc_try_wgrad(X, ldx, dZ, lddz, M, K, Nout, wpart, &splits, stream, &rc_tc)) {
+                if (rc_tc != EMD_OK) return rc_tc;
+            } else {
+                const GemmArgs g = dense_wgrad_args(X, ldx, dZ, lddz, M, K, Nout, s, wpart);
+                EMD_LAUNCH(EK_DENSE_BWD, stream, (launch_sgemm<true, false>(g, s.splits, stream)));
+                EMD_CHECK_LAUNCH("emd_dense_bwd(wgrad)");
+            }
             const int64_t n = (int64_t)Nout * K;
             EMD_LAUNCH(EK_DENSE_BWD, stream,
-                       (split_reduce_kernel<<<(unsigned)emd_cdiv(n, 256), 256, 0, stream>>>(wpart, n, s.splits, n, dW)));
+                       (split_reduce_kernel<<<(unsigned)emd_cdiv(n, 256), 256, 0, stream>>>(wpart, n, splits, n, dW)));
             EMD_CHECK_LAUNCH("emd_dense_bwd(wgrad reduce)");
         }
     }

@@ -9,6 +9,7 @@
 //
 //     Y[M, 0:N] = epilogue( A[M, 0:K] . B )          forward: A = X,  B(k, n) = W[n*ldw + k], epilogue = bias + ReLU
 //                                                    dgrad  : A = dZ, B(k, n) = W[k*ldw + n], epilogue = (mask > 0)
+//     dW[Nout, K] = dZ^T . X                         wgrad  : reduction over the rows, split across CTAs (wgrad_tc_kernel)
 //
 // Same numerics contract as csrc/mlp_tc.cu (3xTF32: every operand split into hi = TF32-exact part and lo = x - hi,
 // products accumulated as lo*hi + hi*lo + hi*hi in the fp32 TMEM accumulator -> fp32-class results) and the same
@@ -232,6 +233,172 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(const DenseTcAr
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(DT_TMEM_COLS) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// weight gradient: partial[z][n][k] = sum over the rows r of split z of dZ[r][n] X[r][k]
+//   UMMA M = 128 output features (block nb), UMMA N = up to 256 input features (block cb), reduction = rows, 32 per chunk.
+//   Both operands are row-contiguous in memory across the UMMA M / N index (dZ[r][n .. n+3], X[r][k .. k+3]), so both are
+//   staged with the transposing map (4 scalar stores per float4).  A CTA keeps its accumulator in TMEM over ALL chunks of
+//   its row range and runs the epilogue once; the per-split partials are summed in a fixed order by the caller
+//   (split_reduce_kernel of deform_net.cu): bit-reproducible, no atomics.
+// ---------------------------------------------------------------------------------------------------------------
+struct WgradTcArgs {
+    const float* dZ;       // [M, Nout] row stride lddz
+    int64_t lddz;
+    const float* X;        // [M, K] row stride ldx
+    int64_t ldx;
+    float* partial;        // [splits][Nout][K]
+    int64_t M;
+    int K, Nout;
+    int n_blocks;          // ceil(Nout / 128)
+    int64_t rows_per_split;
+};
+
+__global__ void __launch_bounds__(DT_THREADS, 1) wgrad_tc_kernel(const WgradTcArgs a) {
+    extern __shared__ __align__(128) unsigned char dt_smem[];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nb = blockIdx.x % a.n_blocks, cb = blockIdx.x / a.n_blocks;
+    const int n0 = nb * TC_ROWS;                              // first output feature of this tile
+    const int k0 = cb * DT_NMAX;                              // first input feature of this tile
+    const int ncols = min(DT_NMAX, a.K - k0);
+    const int npad = (ncols + 15) / 16 * 16;
+    const int64_t rbeg = (int64_t)blockIdx.y * a.rows_per_split;
+    const int64_t rend = min(a.M, rbeg + a.rows_per_split);
+    const int nchunks = (int)((rend - rbeg + DT_KC - 1) / DT_KC);
+
+    for (int e = tid; e < DT_SMEM_BYTES / 16; e += DT_THREADS) reinterpret_cast<float4*>(dt_smem)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]);
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(DT_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = umma_idesc_tf32(TC_ROWS, npad);
+    uint32_t phase0 = 0, phase1 = 0;
+    bool pend0 = false, pend1 = false;
+
+    for (int c = 0; c < nchunks; ++c) {
+        const int st = c & 1;
+        unsigned char* sAhi = dt_smem + st * DT_STAGE_BYTES;
+        unsigned char* sAlo = sAhi + DT_A_BYTES;
+        unsigned char* sBhi = sAlo + DT_A_BYTES;
+        unsigned char* sBlo = sBhi + DT_B_BYTES;
+        if (st == 0) {
+            if (pend0) { mbar_wait(bar0, phase0); phase0 ^= 1u; pend0 = false; }
+        } else {
+            if (pend1) { mbar_wait(bar1, phase1); phase1 ^= 1u; pend1 = false; }
+        }
+        const int64_t r0 = rbeg + (int64_t)c * DT_KC;
+        // ---- A = dZ^T chunk: element (m = output feature, k = row) ----
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int k, m;
+            dts_at_elem(tid, i, k, m);
+            const int64_t row = r0 + k;
+            const int n = n0 + m;
+            float wv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (row < rend && n < a.Nout) {
+                if (n + 3 < a.Nout) {
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(a.dZ + row * a.lddz + n));   // Nout % 4 == 0, lddz % 4 == 0
+                    wv[0] = w.x; wv[1] = w.y; wv[2] = w.z; wv[3] = w.w;
+                } else {
+                    for (int q = 0; q < 4; ++q)
+                        if (n + q < a.Nout) wv[q] = __ldg(a.dZ + row * a.lddz + n + q);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float hi, lo;
+                split_tf32(wv[q], hi, lo);
+                const int off = dts_at_store_offset(k, m + q);
+                *reinterpret_cast<float*>(sAhi + off) = hi;
+                *reinterpret_cast<float*>(sAlo + off) = lo;
+            }
+        }
+        // ---- B = X chunk: element (n = input feature, k = row) ----
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int k, n;
+            dts_b_elem_dgrad(tid, i, k, n);
+            if (n < npad) {
+                const int64_t row = r0 + k;
+                float wv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (row < rend && n < ncols) {
+                    if (n + 3 < ncols) {
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(a.X + row * a.ldx + k0 + n));   // ldx % 4 == 0
+                        wv[0] = w.x; wv[1] = w.y; wv[2] = w.z; wv[3] = w.w;
+                    } else {
+                        for (int q = 0; q < 4; ++q)
+                            if (n + q < ncols) wv[q] = __ldg(a.X + row * a.ldx + k0 + n + q);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float hi, lo;
+                    split_tf32(wv[q], hi, lo);
+                    const int off = dts_b_store_offset_dgrad(k, n + q);
+                    *reinterpret_cast<float*>(sBhi + off) = hi;
+                    *reinterpret_cast<float*>(sBlo + off) = lo;
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t aHi = smem_u32(sAhi), aLo = smem_u32(sAlo), bHi = smem_u32(sBhi), bLo = smem_u32(sBlo);
+#pragma unroll
+            for (int sl = 0; sl < DT_KC / 8; ++sl) {     // rows beyond rend were staged as zeros: all 4 k-steps are safe
+                const uint64_t dAh = umma_desc(aHi + dts_kstep_offset(sl, TC_A_LBO), TC_A_LBO, TC_SBO);
+                const uint64_t dAl = umma_desc(aLo + dts_kstep_offset(sl, TC_A_LBO), TC_A_LBO, TC_SBO);
+                const uint64_t dBh = umma_desc(bHi + dts_kstep_offset(sl, DT_B_LBO), DT_B_LBO, TC_SBO);
+                const uint64_t dBl = umma_desc(bLo + dts_kstep_offset(sl, DT_B_LBO), DT_B_LBO, TC_SBO);
+                umma_tf32(tmem, dAl, dBh, idesc, (c > 0 || sl > 0) ? 1u : 0u);
+                umma_tf32(tmem, dAh, dBl, idesc, 1u);
+                umma_tf32(tmem, dAh, dBh, idesc, 1u);
+            }
+            umma_commit(st == 0 ? bar0 : bar1);
+        }
+        if (st == 0) pend0 = true; else pend1 = true;
+    }
+    if (pend0) { mbar_wait(bar0, phase0); phase0 ^= 1u; pend0 = false; }
+    if (pend1) { mbar_wait(bar1, phase1); phase1 ^= 1u; pend1 = false; }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- epilogue: lane = output feature, columns = input features -> partial[z][n0 + lane ..][k0 + c] ----
+    const int n = n0 + (warp & 3) * 32 + lane;
+    float* out = a.partial + ((int64_t)blockIdx.y * a.Nout + n) * a.K + k0;
+    const int cbeg = (warp >> 2) * 128;
+    const int cend = min(npad, cbeg + 128);
+    for (int c0 = cbeg; c0 < cend; c0 += 16) {
+        float v[16];
+        if (nchunks > 0) {
+            tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = 0.f;      // empty row range: TMEM was never written
+        }
+        if (n < a.Nout) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                if (c0 + c < ncols) out[c0 + c] = v[c];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(DT_TMEM_COLS) : "memory");
+}
+
 int g_dense_tc = -1;   // -1: read EMD_DENSE_TC on first use
 
 }  // namespace
@@ -283,6 +450,40 @@ int emd_dense_tc_try(int dgrad, const float* A, int64_t lda, const float* W, int
         *rc = EMD_ERR_CUDA;
         return 1;
     }
+    *rc = EMD_OK;
+    return 1;
+}
+
+// Floats of the per-split partial buffer the tensor-core weight gradient needs (0 when the path is off / the shape does
+// not qualify); emd_dense_bwd_workspace_bytes takes the larger of this and the SIMT requirement.
+size_t emd_dense_tc_wgrad_partial_floats(int64_t M, int K, int Nout) {
+    if (!emd_dense_tc_enabled() || M <= 0 || Nout % 4 != 0 || K < 4) return 0;
+    const DtsWgradSplit s = dts_wgrad_split(M, K, Nout, EMD_NUM_SMS);
+    return (size_t)s.splits * (size_t)Nout * (size_t)K;
+}
+
+// Weight gradient on the tensor cores into `partial` ([splits][Nout][K]); *splits_out tells the caller how many partials
+// to sum.  Returns 1 when launched (status in *rc), 0 when the caller must take the SIMT path.
+int emd_dense_tc_try_wgrad(const float* X, int64_t ldx, const float* dZ, int64_t lddz, int64_t M, int K, int Nout, float* partial,
+                           int* splits_out, cudaStream_t stream, int* rc) {
+    if (!emd_dense_tc_enabled() || M <= 0) return 0;
+    if (Nout % 4 != 0 || K < 4 || lddz % 4 != 0 || ldx % 4 != 0 || !dt_al16(dZ) || !dt_al16(X)) return 0;
+    const DtsWgradSplit s = dts_wgrad_split(M, K, Nout, EMD_NUM_SMS);
+    WgradTcArgs a;
+    a.dZ = dZ; a.lddz = lddz; a.X = X; a.ldx = ldx; a.partial = partial; a.M = M; a.K = K; a.Nout = Nout;
+    a.n_blocks = s.n_blocks; a.rows_per_split = s.rows_per_split;
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES);
+    if (e == cudaSuccess) {
+        const dim3 grid((unsigned)(s.n_blocks * s.col_blocks), (unsigned)s.splits);
+        EMD_LAUNCH(EK_DENSE_BWD, stream, (wgrad_tc_kernel<<<grid, DT_THREADS, DT_SMEM_BYTES, stream>>>(a)));
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        emd_set_error("emd_dense(tc wgrad): %s", cudaGetErrorString(e));
+        *rc = EMD_ERR_CUDA;
+        return 1;
+    }
+    *splits_out = s.splits;
     *rc = EMD_OK;
     return 1;
 }

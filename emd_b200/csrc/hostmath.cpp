@@ -328,12 +328,12 @@ extern "C" void emd_host_smpl_weight_grad(const float* Wn, const float* A, const
 #include "tc_stage_math.cuh"
 
 // which = 0: A chunk [128 x 32] from src[128][32]; 1: B chunk forward from src[n][32] (n < npad); 2: B chunk dgrad from
-// src[32][npad].  out[rows][32] = the operand as k-step descriptors (start = kstep offset, LBO, SBO = 128) expose it;
+// src[32][npad]; 3: A chunk of the weight gradient from src[32][128] (operand rows contiguous in memory).  out[rows][32] = the operand as k-step descriptors (start = kstep offset, LBO, SBO = 128) expose it;
 // returns the number of bytes written more than once (must be 0) and fills *untouched with the count of operand bytes
 // of the [rows x 32] region no thread wrote.
 extern "C" int emd_host_tc_stage_replay(int which, int npad, const float* src, float* out, int* untouched) {
-    const int lbo = which == 0 ? DTS_A_LBO : DTS_B_LBO;
-    const int rows = which == 0 ? DTS_ROWS : npad;
+    const int lbo = (which == 0 || which == 3) ? DTS_A_LBO : DTS_B_LBO;
+    const int rows = (which == 0 || which == 3) ? DTS_ROWS : npad;
     const int bytes = (DTS_KC / 4) * lbo;
     std::vector<unsigned char> mem(bytes, 0), hit(bytes, 0);
     int twice = 0;
@@ -353,6 +353,12 @@ extern "C" int emd_host_tc_stage_replay(int which, int npad, const float* src, f
                 int n, j;
                 dts_b_elem_fwd(tid, i, n, j);
                 if (n < npad) put(dts_b_store_offset_fwd(n, j), src + n * DTS_KC + 4 * j, 4);
+            }
+        } else if (which == 3) {
+            for (int i = 0; i < 4; ++i) {
+                int k, m;
+                dts_at_elem(tid, i, k, m);
+                for (int q = 0; q < 4; ++q) put(dts_at_store_offset(k, m + q), src + k * DTS_ROWS + m + q, 1);
             }
         } else {
             for (int i = 0; i < 8; ++i) {

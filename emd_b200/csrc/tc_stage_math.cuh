@@ -50,5 +50,33 @@ EMD_HD void dts_b_elem_dgrad(int tid, int i, int& k, int& n) {
 }
 EMD_HD int dts_b_store_offset_dgrad(int k, int n) { return (k >> 2) * DTS_B_LBO + n * 16 + (k & 3) * 4; }
 
+// A chunk of the weight-gradient GEMM (A(m, k) = dZ[k][m], m contiguous in memory): thread tid, i < 4 -> reduction row k
+// of the chunk, 4 consecutive operand rows starting at m; four scalar stores
+EMD_HD void dts_at_elem(int tid, int i, int& k, int& m) {
+    const int e = tid + DTS_THREADS * i;
+    k = e >> 5;
+    m = (e & 31) * 4;
+}
+EMD_HD int dts_at_store_offset(int k, int m) { return (k >> 2) * DTS_A_LBO + m * 16 + (k & 3) * 4; }
+
+// how the weight gradient's reduction over the M rows is split across CTAs (shared by the workspace query and the launch)
+struct DtsWgradSplit {
+    int n_blocks, col_blocks, splits;
+    int64_t rows_per_split;      // multiple of DTS_KC
+};
+static inline DtsWgradSplit dts_wgrad_split(int64_t M, int K, int Nout, int num_sms) {
+    DtsWgradSplit s;
+    s.n_blocks = (Nout + DTS_ROWS - 1) / DTS_ROWS;
+    s.col_blocks = (K + DTS_NMAX - 1) / DTS_NMAX;
+    const int64_t rows = M > 0 ? M : 1;
+    const int64_t chunks = (rows + DTS_KC - 1) / DTS_KC;
+    int64_t want = num_sms / (s.n_blocks * s.col_blocks);
+    if (want < 1) want = 1;
+    if (want > chunks) want = chunks;
+    s.rows_per_split = ((chunks + want - 1) / want) * DTS_KC;
+    s.splits = (int)((rows + s.rows_per_split - 1) / s.rows_per_split);
+    return s;
+}
+
 // start offset (inside a stage's operand) of the two core-matrix columns MMA k-step `sl` of the chunk reads
 EMD_HD int dts_kstep_offset(int sl, int lbo) { return 2 * sl * lbo; }

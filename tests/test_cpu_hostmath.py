@@ -396,15 +396,15 @@ def test_projection_tile_edge_cases_bit_exact(hostlib):
     assert np.array_equal(rc, torch.stack([x0, y0, x1, y1], -1).numpy().astype(np.int32))
 
 
-@pytest.mark.parametrize("which,npad", [(0, 128), (1, 256), (1, 16), (1, 112), (2, 256), (2, 16), (2, 48)])
+@pytest.mark.parametrize("which,npad", [(0, 128), (1, 256), (1, 16), (1, 112), (2, 256), (2, 16), (2, 48), (3, 128)])
 def test_tensor_core_staging_maps(hostlib, which, npad):
     """tc_stage_math.cuh (the thread -> shared-memory maps of the experimental tcgen05 GEMM, csrc/deform_net_tc.cu): every
     thread's writes of one chunk replayed on the host must tile the operand exactly once, and reading it back the way
     the UMMA k-step descriptors walk the canonical K-major layout must give the source matrix (A chunk; W chunk in the
-    forward orientation [n][k]; W chunk in the data-gradient orientation [k][n])."""
-    rows = 128 if which == 0 else npad
+    forward orientation [n][k]; W chunk in the data-gradient orientation [k][n]; dZ chunk of the weight gradient [k][m])."""
+    rows = 128 if which in (0, 3) else npad
     g = torch.Generator().manual_seed(which * 1000 + npad)
-    src = torch.randn(rows, 32, generator=g) if which != 2 else torch.randn(32, npad, generator=g)
+    src = torch.randn(rows, 32, generator=g) if which in (0, 1) else torch.randn(32, rows, generator=g)
     out = np.zeros((rows, 32), np.float32)
     miss = ctypes.c_int(-1)
     f = hostlib.emd_host_tc_stage_replay
@@ -412,5 +412,5 @@ def test_tensor_core_staging_maps(hostlib, which, npad):
     f.restype = ctypes.c_int
     twice = f(which, npad, _fp(src), out.ctypes.data_as(P), ctypes.byref(miss))
     assert twice == 0 and miss.value == 0
-    want = src.numpy() if which != 2 else src.numpy().T
+    want = src.numpy() if which in (0, 1) else src.numpy().T
     assert np.array_equal(out, want)

@@ -73,5 +73,22 @@ for K, Nout, ldx, ldy, relu in [(100, 256, 100, 256, 1), (256, 256, 256, 256, 1)
     ok = e_tc <= 5e-5 * max(1.0, float(ref.abs().max()))
     bad += not ok
     report.append({"op": "dgrad", "M": M, "K": Nout, "N": ncols, "err_simt": e_simt, "err_tc": e_tc, "ms_simt": round(ms[0], 4), "ms_tc": round(ms[1], 4), "ok": ok})
+    # weight / bias gradient (split over the rows, fixed-order reduction of the partials)
+    outs, ms = [], []
+    for tc in (0, 1):
+        L.emd_dense_set_tc(tc)
+        wsb = L.emd_dense_bwd_workspace_bytes(M, K, Nout)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        dW, db = torch.empty(Nout, K, device=dev), torch.empty(Nout, device=dev)
+        call = lambda: _C.check(L.emd_dense_bwd(_C.ptr(X), ldx, _C.ptr(W), _C.ptr(dZ), Nout, M, K, Nout, None, 0, 0, 0, None, 0,  # noqa: E731
+                                                _C.ptr(dW), _C.ptr(db), _C.ptr(ws), wsb, st), "bwd")
+        ms.append(timed(call))
+        outs.append(dW.clone())
+    L.emd_dense_set_tc(0)
+    ref = dZ.double().T @ X[:, :K].double()
+    e_simt, e_tc = float((outs[0].double() - ref).abs().max()), float((outs[1].double() - ref).abs().max())
+    ok = e_tc <= 5e-5 * max(1.0, float(ref.abs().max()))
+    bad += not ok
+    report.append({"op": "wgrad", "M": M, "K": K, "N": Nout, "err_simt": e_simt, "err_tc": e_tc, "ms_simt": round(ms[0], 4), "ms_tc": round(ms[1], 4), "ok": ok})
 print(json.dumps(report, indent=1))
 sys.exit(1 if bad else 0)
