@@ -27,6 +27,9 @@ _SIGS = {
     "emd_kernel_name": (ctypes.c_char_p, [c_int]),
     "emd_profile_enable": (None, [c_int]),
     "emd_profile_collect": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),
+    "emd_raster_set_counters": (None, [P]),
+    "emd_fp32_probe": (c_int, [c_int, c_int, P, P]),
+    "emd_fp32_probe_lane_instructions": (c_int64, [c_int, c_int]),
     "emd_projection_fwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int, c_int, c_float, c_float, c_float, c_float,
                                    c_int, c_int, P, P, P, P, P, P, P]),
     "emd_projection_bwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int, c_int, c_float, c_float, c_float, c_float,

@@ -410,6 +410,10 @@ __device__ __forceinline__ float butterfly12(float (&v)[12], int lane) {
     return c + __shfl_xor_sync(0xffffffffu, c, 1);
 }
 
+// COUNT: measurement build of the same kernel (bench.py / tools only): counters[0] += (warp, candidate) evaluations,
+// [1] += evaluations in which at least one lane blended, [2] += blended (pixel, Gaussian) pairs, [3] += staged
+// (tile, Gaussian) pairs.  The product path launches COUNT = false.
+template <bool COUNT>
 __global__ void __launch_bounds__(RB) raster_bwd_kernel(
     const float4* __restrict__ recs, const int32_t* __restrict__ tile_offsets, const int32_t* __restrict__ flatten_ids,
     const int32_t* __restrict__ tile_order, const int32_t* __restrict__ radii, const int64_t* __restrict__ cum_tiles,
@@ -418,7 +422,8 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
     const int32_t* __restrict__ ckpt_base, const float* __restrict__ ckpt,
     const float* __restrict__ out_colors, const float* __restrict__ out_alphas, const int32_t* __restrict__ last_ids,
     const float* __restrict__ v_out_colors, const float* __restrict__ v_out_alphas, float* __restrict__ partials,
-    uint8_t* __restrict__ touched) {
+    uint8_t* __restrict__ touched, unsigned long long* __restrict__ counters) {
+    unsigned cnt_eval = 0, cnt_hit = 0, cnt_pairs = 0, cnt_staged = 0;
     __shared__ float4 s_r0[RB];
     __shared__ float4 s_r1[RB];
     __shared__ float2 s_r2[RB];
@@ -536,6 +541,7 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
             s_slot[tr] = (uint32_t)(base + (int64_t)(tile_y - y0) * (x1 - x0) + (tile_x - x0));
         }
         s_mask[tr] = mask;
+        if (COUNT) cnt_staged += tr < batch_size;
         __syncthreads();
         for (int sub = 0; sub < batch_size; sub += BSUB) {
             const int sub_n = min(BSUB, batch_size - sub);
@@ -561,7 +567,9 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
                     const float vis = exp_neg(sigma);
                     const float alpha = fminf(cfg.alpha_max, r0.z * vis);
                     if (sigma < 0.f || alpha < ALPHA_MIN) valid = false;
+                    if (COUNT) { cnt_eval += lane == 0; cnt_pairs += valid; }
                     if (!__any_sync(0xffffffffu, valid)) continue;
+                    if (COUNT) cnt_hit += lane == 0;
                     float v[12];
 #pragma unroll
                     for (int k = 0; k < 12; ++k) v[k] = 0.f;
@@ -624,6 +632,21 @@ __global__ void __launch_bounds__(RB) raster_bwd_kernel(
                 }
                 __syncthreads();
             }
+        }
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            cnt_eval += __shfl_xor_sync(0xffffffffu, cnt_eval, o);
+            cnt_hit += __shfl_xor_sync(0xffffffffu, cnt_hit, o);
+            cnt_pairs += __shfl_xor_sync(0xffffffffu, cnt_pairs, o);
+            cnt_staged += __shfl_xor_sync(0xffffffffu, cnt_staged, o);
+        }
+        if (lane == 0) {
+            atomicAdd(counters + 0, (unsigned long long)cnt_eval);
+            atomicAdd(counters + 1, (unsigned long long)cnt_hit);
+            atomicAdd(counters + 2, (unsigned long long)cnt_pairs);
+            atomicAdd(counters + 3, (unsigned long long)cnt_staged);
         }
     }
 }
@@ -757,6 +780,11 @@ extern "C" int emd_raster_pack(const float* means2d, const float* conics, const 
     return EMD_OK;
 }
 
+// Measurement aid: while a non-NULL device pointer to 8 uint64 counters is set, emd_rasterize_bwd launches the counting
+// build of its kernel (see raster_bwd_kernel<COUNT>).  Process-global; not for concurrent use.
+static unsigned long long* g_raster_counters = nullptr;
+extern "C" void emd_raster_set_counters(void* counters_u64x8) { g_raster_counters = reinterpret_cast<unsigned long long*>(counters_u64x8); }
+
 extern "C" int emd_raster_segment_size() { return SEG; }
 extern "C" int emd_raster_checkpoint_floats() { return CKPT_FLOATS; }
 extern "C" int emd_raster_segout_floats() { return SEGOUT_FLOATS; }
@@ -849,11 +877,16 @@ extern "C" int emd_rasterize_bwd(const float* recs, const int32_t* tile_offsets,
         cudaMemsetAsync(touched, 0, (size_t)P, stream);
         // upper bound on the number of (tile, segment) CTAs; surplus CTAs exit at once
         dim3 grid((unsigned)(P / SEG + C * tile_w * tile_h)), block(RB, 1, 1);
-        EMD_LAUNCH(EK_RASTER_BWD, stream, raster_bwd_kernel<<<grid, block, 0, stream>>>(
-            reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, tile_order, radii, cum_tiles, P, (int)C, width,
-            height, tile_w, tile_h, channels, ed_mode, cfg, backgrounds, seg_prefix, ckpt_base, ckpt, out_colors, out_alphas,
-            last_ids, v_out_colors,
-            v_out_alphas, partials, touched));
+        if (g_raster_counters)
+            EMD_LAUNCH(EK_RASTER_BWD, stream, raster_bwd_kernel<true><<<grid, block, 0, stream>>>(
+                reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, tile_order, radii, cum_tiles, P, (int)C, width,
+                height, tile_w, tile_h, channels, ed_mode, cfg, backgrounds, seg_prefix, ckpt_base, ckpt, out_colors, out_alphas,
+                last_ids, v_out_colors, v_out_alphas, partials, touched, g_raster_counters));
+        else
+            EMD_LAUNCH(EK_RASTER_BWD, stream, raster_bwd_kernel<false><<<grid, block, 0, stream>>>(
+                reinterpret_cast<const float4*>(recs), tile_offsets, flatten_ids, tile_order, radii, cum_tiles, P, (int)C, width,
+                height, tile_w, tile_h, channels, ed_mode, cfg, backgrounds, seg_prefix, ckpt_base, ckpt, out_colors, out_alphas,
+                last_ids, v_out_colors, v_out_alphas, partials, touched, nullptr));
     }
     EMD_LAUNCH(EK_RASTER_GATHER, stream, raster_gather_kernel<<<(unsigned)emd_cdiv(CN, 256), 256, 0, stream>>>(partials, touched, cum_tiles, CN, d_color,
                                                                            with_depth, v_means2d, v_means2d_abs,

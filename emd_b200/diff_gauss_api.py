@@ -113,7 +113,9 @@ class _ScreenGradTap(torch.autograd.Function):
 
 
 def rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        extra_attrs, s: GaussianRasterizationSettings):
+                        extra_attrs, s: GaussianRasterizationSettings, info: Optional[dict] = None):
+    """``info`` (optional dict) receives the integer artefacts of the call -- ``tiles_touched``, ``point_list_keys``,
+    ``point_list``, ``ranges`` (first sorted index per tile), ``last_ids`` -- which upstream keeps in its binning state."""
     if cov3Ds_precomp is not None and (not isinstance(cov3Ds_precomp, Tensor) or cov3Ds_precomp.numel() > 0):
         raise NotImplementedError("emd_b200.diff_gauss: cov3Ds_precomp is not supported; pass scales and rotations")
     if extra_attrs is not None and (not isinstance(extra_attrs, Tensor) or extra_attrs.numel() > 0):
@@ -144,6 +146,9 @@ def rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales
     out, alpha, last_ids = R.rasterize_to_pixels(
         means2d[None], conics[None], colors[None], opacities.reshape(1, N), depths[None], bg, radii[None], cum,
         offsets, vals, W, H, with_depth=True, ed_mode=False, absgrad=False, flavour=1)
+    if info is not None:
+        info.update(tiles_touched=tiles, point_list_keys=keys, point_list=vals, ranges=offsets, last_ids=last_ids,
+                    means2d=means2d.detach(), depths=depths.detach(), conics=conics.detach())
     color = out[0, ..., :3].permute(2, 0, 1)
     depth = out[0, ..., 3:4].permute(2, 0, 1)
     normal = torch.zeros(3, H, W, dtype=torch.float32, device=dev)
@@ -164,5 +169,6 @@ class GaussianRasterizer(nn.Module):
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
                 cov3Ds_precomp=None, extra_attrs=None):
+        self.last_info = {}   # binning state of the most recent call (tests / diagnostics)
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                                   extra_attrs, self.raster_settings)
+                                   extra_attrs, self.raster_settings, self.last_info)

@@ -137,7 +137,7 @@ def sh_colors(shs: Tensor, means3D: Tensor, campos: Tensor, degree: int) -> Tens
 
 
 def rasterize(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, s: Settings,
-              return_unstable: bool = False):
+              return_unstable: bool = False, tile_rows=None):
     """GaussianRasterizer.forward -> (color[3,H,W], depth[1,H,W], normal[3,H,W] zeros, alpha[1,H,W], radii[N], info).
 
     ``means2D`` takes part in the graph only as the holder of the screen-space gradient
@@ -171,7 +171,7 @@ def rasterize(means3D, means2D, shs, colors_precomp, opacities, scales, rotation
     bg = torch.cat([s.bg.to(torch.float32), torch.zeros(1)])[None]
     res = G.rasterize_to_pixels(m2d[None], conics[None], feat[None], opacities.reshape(1, N), W, H, 16, offs, flat,
                                 backgrounds=bg, return_unstable=return_unstable, max_alpha=0.99,
-                                t_stop_inclusive=False, pixel_center=0.0)
+                                t_stop_inclusive=False, pixel_center=0.0, tile_rows=tile_rows)
     out, alpha, last = res[:3]
     color = out[0, ..., :3].permute(2, 0, 1)
     depth = out[0, ..., 3:4].permute(2, 0, 1)

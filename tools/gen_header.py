@@ -9,7 +9,8 @@ ROOT = Path(__file__).resolve().parent.parent
 
 GROUPS = [
     ("Library plumbing", ["emd_abi_version", "emd_device_check", "emd_last_error_string", "emd_launch_count",
-                          "emd_kernel_id_count", "emd_kernel_name", "emd_profile_enable", "emd_profile_collect"]),
+                          "emd_kernel_id_count", "emd_kernel_name", "emd_profile_enable", "emd_profile_collect",
+                          "emd_fp32_probe", "emd_fp32_probe_lane_instructions"]),
     ("K1a  EMD motion-embedding deformation, rigid nodes", ["emd_rigid_chunk_size", "emd_rigid_param_count",
                                                           "emd_rigid_deform_fwd", "emd_rigid_deform_bwd"]),
     ("K1c  EMD motion-embedding deformation, SMPL nodes", ["emd_smpl_param_count", "emd_smpl_max_chunks",
@@ -35,7 +36,7 @@ GROUPS = [
     ("K5   tile ranges", ["emd_isect_offsets", "emd_tile_order", "emd_raster_segment_size", "emd_raster_checkpoint_floats",
                         "emd_raster_segout_floats", "emd_raster_segment_slots"]),
     ("K6/K7 rasterization", ["emd_raster_pack", "emd_rasterize_fwd", "emd_rasterize_bwd_workspace_bytes",
-                             "emd_rasterize_bwd"]),
+                             "emd_rasterize_bwd", "emd_raster_set_counters"]),
 ]
 
 DOC = {
@@ -47,6 +48,14 @@ DOC = {
     "emd_kernel_name": "Name of kernel id `id`.",
     "emd_profile_enable": "When on, every kernel launch is bracketed by CUDA events on its own stream.",
     "emd_profile_collect": "Synchronise recorded events; ADD durations (ms) / launch counts into the [emd_kernel_id_count()] arrays.",
+    "emd_raster_set_counters": "Measurement aid: while a non-NULL DEVICE pointer to 8 zero-initialised uint64 is set, emd_rasterize_bwd "
+                               "runs the counting build of its kernel: [0] (warp, candidate Gaussian) evaluations, [1] those in which "
+                               "a lane blended, [2] blended (pixel, Gaussian) pairs, [3] staged (tile, Gaussian) pairs.  NULL restores "
+                               "the product kernel.  Process-global.",
+    "emd_fp32_probe": "Measurement aid (no reference counterpart): register-only throughput probe of one instruction class "
+                      "(kind 0 FFMA, 1 FFMA2, 2 FADD, 3 FADD2, 4 SHFL.BFLY, 5 MUFU.EX2) on 148 x 8 CTAs; the caller times it with CUDA "
+                      "events -> the measured FP32-pipe ceiling bench.py reports beside the nominal one.",
+    "emd_fp32_probe_lane_instructions": "Lane-level instructions one emd_fp32_probe(kind, iters) launch executes.",
     "emd_rigid_chunk_size": "Points per (instance, chunk) block of the rigid kernels (sizes the scratch buffers).",
     "emd_rigid_param_count": "Floats in the flat track_* gradient: 2*(d+g+1) + 2*(3*(d+g)+3).",
     "emd_rigid_deform_fwd": "Replaces RigidNodes.transform_means + transform_quats incl. the per-instance Python loops "

@@ -27,13 +27,7 @@ def timeit(fn, warm=3, it=10):
     return ts[len(ts) // 2]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=1_300_000)
-    ap.add_argument("--cams", type=int, default=3)
-    ap.add_argument("--w", type=int, default=960)
-    ap.add_argument("--h", type=int, default=640)
-    a = ap.parse_args()
+def run(a):
     dev = torch.device("cuda")
     g = torch.Generator().manual_seed(0)
     bg = scenes.background(a.n, g)
@@ -94,9 +88,47 @@ def main():
         (c * vc).sum().backward()
     res["full_fwd_bwd_ms"] = timeit(full, it=5)
     res["mpix_per_s"] = C * W * H / res["full_fwd_bwd_ms"] / 1e3
-    # pixel-pair statistics: how far pixels walk
-    last = _[0] if False else None
-    print(json.dumps(res, indent=1))
+    # per-stage roofline: algorithmic bytes / CUDA-event time / measured HBM copy bandwidth
+    try:
+        hbm = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
+        src = "measured"
+    except Exception:  # noqa: BLE001
+        hbm, src = 6650.0, "fallback"
+    N = a.n
+    keybits = 32 + bits + cam_bits
+    passes = (keybits + 7) // 8
+    alg = {"activate_fwd_ms": (192 + 12 + 4 + 12 + 16 + 12 * C + 4 + 12 + 16) * N,
+           "proj_fwd_ms": (40 + 32 * C) * N, "proj_bwd_ms": (40 + 28 * C + 40) * N,
+           "emit_ms": 12 * P + 24 * C * N, "sort_ms": (8 + 24 * passes) * P, "offsets_ms": 8 * P}
+    res["hbm_peak_gbs"] = hbm
+    res["hbm_peak_source"] = src
+    res["sort_passes"] = passes
+    res["frac_of_hbm"] = {k.replace("_ms", ""): round(v / (res[k] * 1e-3) / 1e9 / hbm, 4) for k, v in alg.items() if res.get(k)}
+    res["sort_frac_of_hbm_single_pass_floor"] = round(24 * P / (res["sort_ms"] * 1e-3) / 1e9 / hbm, 4)
+    res["raster_fwd_gpairs_per_s"] = None
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=1_300_000)
+    ap.add_argument("--cams", type=int, default=3)
+    ap.add_argument("--w", type=int, default=960)
+    ap.add_argument("--h", type=int, default=640)
+    ap.add_argument("--sweep", action="store_true",
+                    help="BASELINE.json configs[4]: N in {1e5,3e5,1e6,3e6,1e7} x {640x960, 1280x1920}, one camera")
+    a = ap.parse_args()
+    if not a.sweep:
+        print(json.dumps(run(a), indent=1))
+        return
+    out = []
+    for (w, h) in ((960, 640), (1920, 1280)):
+        for n in (100_000, 300_000, 1_000_000, 3_000_000, 10_000_000):
+            a.n, a.w, a.h, a.cams = n, w, h, 1
+            r = run(a)
+            out.append(r)
+            print(json.dumps(r), flush=True)
+            torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":
