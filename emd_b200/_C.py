@@ -37,6 +37,7 @@ _SIGS = {
     "emd_scan_workspace_bytes": (c_size_t, [c_int64]),
     "emd_cumsum_i32_i64": (c_int, [P, P, c_int64, P, P, c_size_t, P]),
     "emd_exclusive_scan_u32": (c_int, [P, P, c_int64, P, c_size_t, P]),
+    "emd_exclusive_scan_u8_u32": (c_int, [P, P, c_int64, P, P, c_size_t, P]),
     "emd_isect_emit": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, P, P, P]),
     "emd_isect_offsets": (c_int, [P, c_int64, c_int64, c_int, c_int, c_int, P, P]),
     "emd_radix_sort_workspace_bytes": (c_size_t, [c_int64]),
@@ -73,11 +74,13 @@ _SIGS = {
     "emd_image_loss_partials_floats": (c_int64, [c_int, c_int, c_int]),
     "emd_image_loss_fwd": (c_int, [P] * 8 + [c_int, c_int, c_int, P, ctypes.POINTER(c_float)] + [P] * 4 + [P]),
     "emd_image_loss_bwd": (c_int, [P] * 8 + [c_int, c_int, c_int, P, ctypes.POINTER(c_float)] + [P] * 7 + [P]),
-    "emd_tile_order": (c_int, [P, c_int64, c_int64, P, P, P, P]),
+    "emd_tile_order": (c_int, [P, c_int64, c_int64, P, P, P, P, P]),
+    "emd_raster_max_ctas": (c_int64, [c_int64, c_int64]),
     "emd_raster_segment_size": (c_int, []),
     "emd_raster_checkpoint_floats": (c_int, []),
     "emd_raster_segout_floats": (c_int, []),
     "emd_raster_segment_slots": (c_int64, [c_int64]),
+    "emd_raster_sort_records": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P]),
     "emd_rasterize_fwd": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P,
                                   P, P, P, P]),
     "emd_dg_preprocess_fwd": (c_int, [P] * 4 + [ctypes.POINTER(c_float)] * 3 + [c_float, c_float, c_int, c_int, c_float,
@@ -102,7 +105,7 @@ _SIGS = {
     "emd_smpl_deform_fwd": (c_int, [P] * 12 + [c_int] * 5 + [c_float, c_int, c_int] + [P] * 5 + [P]),
     "emd_smpl_deform_bwd": (c_int, [P] * 11 + [c_int] * 5 + [c_float, c_int, c_int] + [P] * 14 + [P]),
     "emd_smpl_weight_grad": (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P]),
-    "emd_rasterize_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
+    "emd_rasterize_bwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_int, P, P, P, P, P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
 }
 

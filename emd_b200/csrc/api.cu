@@ -15,7 +15,7 @@ void emd_set_error(const char* fmt, ...) {
 
 extern "C" const char* emd_last_error_string() { return g_err; }
 
-extern "C" int emd_abi_version() { return 2; }
+extern "C" int emd_abi_version() { return 3; }
 
 // 0 when the current device can run the sm_100a kernels in this library.
 extern "C" int emd_device_check() {

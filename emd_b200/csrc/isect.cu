@@ -193,6 +193,14 @@ extern "C" int emd_exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t
     return scan_impl<uint32_t, uint32_t, false>(in, out, n, (uint32_t*)nullptr, workspace, ws_bytes, stream);
 }
 
+// exclusive scan uint8 -> uint32 with the grand total written to *total_out (a DEVICE pointer; out + n is a valid
+// choice, which makes `out` an (n+1)-long offsets array)
+extern "C" int emd_exclusive_scan_u8_u32(const uint8_t* in, uint32_t* out, int64_t n, uint32_t* total_out, void* workspace,
+                                         size_t ws_bytes, cudaStream_t stream) {
+    EMD_CHECK_ARG(n >= 0, "exclusive_scan: negative n");
+    return scan_impl<uint8_t, uint32_t, false>(in, out, n, total_out, workspace, ws_bytes, stream);
+}
+
 extern "C" int emd_isect_emit(const float* means2d, const int32_t* radii, const float* depths,
                               const int64_t* cum_tiles, int64_t N, int64_t C, int tile_w, int tile_h,
                               int tile_n_bits, int64_t* isect_ids, int32_t* flatten_ids, cudaStream_t stream) {

@@ -145,7 +145,7 @@ def rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales
     bg = torch.cat([s.bg.float().reshape(3), torch.zeros(1, device=dev)])[None]
     out, alpha, last_ids = R.rasterize_to_pixels(
         means2d[None], conics[None], colors[None], opacities.reshape(1, N), depths[None], bg, radii[None], cum,
-        offsets, vals, W, H, with_depth=True, ed_mode=False, absgrad=False, flavour=1)
+        offsets, vals, keys, W, H, with_depth=True, ed_mode=False, absgrad=False, flavour=1)
     if info is not None:
         info.update(tiles_touched=tiles, point_list_keys=keys, point_list=vals, ranges=offsets, last_ids=last_ids,
                     means2d=means2d.detach(), depths=depths.detach(), conics=conics.detach())

@@ -123,7 +123,7 @@ def rasterization(
             else torch.zeros(C, 1, device=bg.device, dtype=bg.dtype)
 
     render_colors, render_alphas, last_ids = R.rasterize_to_pixels(
-        means2d, conics, ras_colors, opac, depths, bg, radii, cum_tiles, isect_offsets, flatten_ids, width, height,
+        means2d, conics, ras_colors, opac, depths, bg, radii, cum_tiles, isect_offsets, flatten_ids, isect_ids, width, height,
         with_depth=with_depth, ed_mode=ed_mode, absgrad=absgrad)
 
     meta = {

@@ -198,7 +198,7 @@ class _Rasterize(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, conics, colors, opacities, depths, backgrounds, radii, cum_tiles, isect_offsets,
-                flatten_ids, width, height, with_depth, ed_mode, absgrad, flavour=0):
+                flatten_ids, isect_ids, width, height, with_depth, ed_mode, absgrad, flavour=0):
         L = _C.lib()
         C, N = radii.shape
         dev = radii.device
@@ -210,14 +210,38 @@ class _Rasterize(torch.autograd.Function):
         opac_per_cam = 1 if opacities.dim() == 2 else 0
         CH = d_color + (1 if with_depth else 0)
         depths_c = _f32c(depths) if with_depth else None
-        tw, th, _ = tile_grid(width, height)
+        tw, th, tile_bits = tile_grid(width, height)
         P = flatten_ids.numel()
+        assert isect_ids.numel() == P, "isect_ids / flatten_ids: the sorted keys and values of the same intersections"
         recs = torch.empty(C * N * 3, 4, dtype=torch.float32, device=dev)
         dummy = means2d  # never dereferenced when d_color == 0
         _C.check(L.emd_raster_pack(_C.ptr(means2d), _C.ptr(conics), _C.ptr(opacities), opac_per_cam,
                                    _C.ptr(colors if colors is not None else dummy), colors_per_cam, d_color,
                                    _C.ptr(depths_c), 1 if with_depth else 0, _C.ptr(radii, torch.int32), N, C,
                                    _C.ptr(recs), _C.stream()), "emd_raster_pack")
+        # the depth-sorted, per-tile-contiguous record stream both compositing kernels read with bulk copies
+        srecs = torch.empty(max(P, 1) * 3, 4, dtype=torch.float32, device=dev)
+        want_bwd = any(ctx.needs_input_grad[:6])
+        cand = torch.empty(max(P, 1), dtype=torch.uint8, device=dev) if want_bwd else None
+        _C.check(L.emd_raster_sort_records(_C.ptr(recs), _C.ptr(isect_ids, torch.int64), _C.ptr(flatten_ids, torch.int32),
+                                           _C.ptr(radii, torch.int32), _C.ptr(cum_tiles, torch.int64), P, tw, th, tile_bits,
+                                           int(flavour), _C.ptr(srecs), _C.ptr(cand), _C.stream()), "emd_raster_sort_records")
+        del recs
+        entry_base, n_entries_host, n_entries_ev = None, None, None
+        if want_bwd:
+            # gradient entries of the backward: one per (pair, 8x4 pixel block its alpha box reaches); entry_base[slot] =
+            # first entry of the pair, entry_base[P] = their number -- read back asynchronously (the backward, which
+            # sizes its workspace with it, runs long after the copy has landed: no stall)
+            entry_base = torch.empty(P + 1, dtype=torch.int32, device=dev)
+            ws_bytes = L.emd_scan_workspace_bytes(P)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _C.check(L.emd_exclusive_scan_u8_u32(_C.ptr(cand), _C.ptr(entry_base), P, entry_base.data_ptr() + 4 * P,
+                                                 _C.ptr(ws), ws_bytes, _C.stream()), "emd_exclusive_scan_u8_u32")
+            n_entries_host = torch.empty(1, dtype=torch.int32).pin_memory()
+            n_entries_host.copy_(entry_base[P:], non_blocking=True)
+            n_entries_ev = torch.cuda.Event()
+            n_entries_ev.record()
+            del ws, cand
         out_colors = torch.empty(C, height, width, CH, dtype=torch.float32, device=dev)
         out_alphas = torch.empty(C, height, width, 1, dtype=torch.float32, device=dev)
         last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
@@ -225,20 +249,25 @@ class _Rasterize(torch.autograd.Function):
         n_ct = C * th * tw
         sched = torch.empty(3, n_ct, dtype=torch.int32, device=dev)  # tile order | segment prefix | checkpoint base
         tile_order, seg_prefix, ckpt_base = sched[0], sched[1], sched[2]
+        cta_map = torch.empty(int(L.emd_raster_max_ctas(P, n_ct)), 2, dtype=torch.int32, device=dev)   # CTA -> (tile, segment)
         _C.check(L.emd_tile_order(_C.ptr(isect_offsets, torch.int32), P, n_ct, _C.ptr(tile_order), _C.ptr(seg_prefix),
-                                  _C.ptr(ckpt_base), _C.stream()), "emd_tile_order")
+                                  _C.ptr(ckpt_base), _C.ptr(cta_map), _C.stream()), "emd_tile_order")
         # checkpoints (kept for the backward) + per-segment scratch of the segment-parallel forward
         slots = int(L.emd_raster_segment_slots(P))
         ckpt = torch.empty(slots * L.emd_raster_checkpoint_floats(), dtype=torch.float32, device=dev)
         seg_out = torch.empty(slots * L.emd_raster_segout_floats(), dtype=torch.float32, device=dev)
-        _C.check(L.emd_rasterize_fwd(_C.ptr(recs), _C.ptr(isect_offsets, torch.int32), _C.ptr(flatten_ids, torch.int32),
-                                     _C.ptr(tile_order), _C.ptr(seg_prefix), _C.ptr(ckpt_base), P, C, width, height, tw, th,
+        _C.check(L.emd_rasterize_fwd(_C.ptr(srecs), _C.ptr(isect_offsets, torch.int32),
+                                     _C.ptr(tile_order), _C.ptr(seg_prefix), _C.ptr(ckpt_base), _C.ptr(cta_map), P, C, width,
+                                     height, tw, th,
                                      CH, 1 if ed_mode else 0, int(flavour), _C.ptr(bg), _C.ptr(ckpt), _C.ptr(seg_out),
                                      _C.ptr(out_colors), _C.ptr(out_alphas), _C.ptr(last_ids), _C.stream()),
                  "emd_rasterize_fwd")
         del seg_out
-        ctx.save_for_backward(recs, isect_offsets, flatten_ids, radii, cum_tiles, bg if bg is not None else torch.empty(0, device=dev),
-                              out_colors, out_alphas, last_ids, sched, ckpt)
+        ctx.save_for_backward(srecs, isect_offsets, radii, cum_tiles, entry_base if entry_base is not None else torch.empty(0, device=dev),
+                              bg if bg is not None else torch.empty(0, device=dev),
+                              out_colors, out_alphas, last_ids, sched, ckpt, cta_map)
+        ctx.n_isects = P
+        ctx.n_entries = (n_entries_host, n_entries_ev)
         ctx.cfg = (width, height, CH, d_color, bool(with_depth), bool(ed_mode), bool(absgrad), colors_per_cam,
                    opac_per_cam, bg is not None, int(flavour))
         ctx.means2d_ref = means2d if absgrad else None
@@ -248,13 +277,13 @@ class _Rasterize(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_colors_out, v_alphas_out, _v_last):
         L = _C.lib()
-        recs, isect_offsets, flatten_ids, radii, cum_tiles, bg, out_colors, out_alphas, last_ids, sched, ckpt = ctx.saved_tensors
+        srecs, isect_offsets, radii, cum_tiles, entry_base, bg, out_colors, out_alphas, last_ids, sched, ckpt, cta_map = ctx.saved_tensors
         tile_order, seg_prefix, ckpt_base = sched[0], sched[1], sched[2]
         width, height, CH, d_color, with_depth, ed_mode, absgrad, colors_per_cam, opac_per_cam, has_bg, flavour = ctx.cfg
         C, N = radii.shape
         dev = radii.device
         tw, th, _ = tile_grid(width, height)
-        P = flatten_ids.numel()
+        P = ctx.n_isects
         v_colors_out = _f32c(v_colors_out) if v_colors_out is not None else torch.zeros_like(out_colors)
         v_alphas_out = _f32c(v_alphas_out) if v_alphas_out is not None else torch.zeros_like(out_alphas)
         v_means2d = torch.empty(C, N, 2, dtype=torch.float32, device=dev)
@@ -263,10 +292,13 @@ class _Rasterize(torch.autograd.Function):
         v_colors = torch.empty(C, N, max(d_color, 1), dtype=torch.float32, device=dev)
         v_depths = torch.empty(C, N, dtype=torch.float32, device=dev) if with_depth else None
         v_opac = torch.empty(C, N, dtype=torch.float32, device=dev)
-        ws_bytes = L.emd_rasterize_bwd_workspace_bytes(P)
+        n_entries_host, n_entries_ev = ctx.n_entries
+        n_entries_ev.synchronize()
+        n_entries = int(n_entries_host.item())
+        ws_bytes = L.emd_rasterize_bwd_workspace_bytes(n_entries)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _C.check(L.emd_rasterize_bwd(
-            _C.ptr(recs), _C.ptr(isect_offsets), _C.ptr(flatten_ids), _C.ptr(tile_order), _C.ptr(radii), _C.ptr(cum_tiles), P, N, C,
+            _C.ptr(srecs), _C.ptr(isect_offsets), _C.ptr(cta_map), _C.ptr(cum_tiles), _C.ptr(entry_base), n_entries, P, N, C,
             width, height, tw, th, CH, 1 if ed_mode else 0, flavour, _C.ptr(bg) if has_bg else None, _C.ptr(seg_prefix),
             _C.ptr(ckpt_base), _C.ptr(ckpt), _C.ptr(out_colors),
             _C.ptr(out_alphas), _C.ptr(last_ids), _C.ptr(v_colors_out), _C.ptr(v_alphas_out), d_color,
@@ -285,12 +317,13 @@ class _Rasterize(torch.autograd.Function):
         if has_bg and ctx.needs_input_grad[5]:
             T_final = 1.0 - out_alphas  # [C,H,W,1]
             g_bg = (v_colors_out * T_final).sum(dim=(1, 2))
-        return (v_means2d, v_conics, g_colors, g_opac, v_depths, g_bg) + (None,) * 10
+        return (v_means2d, v_conics, g_colors, g_opac, v_depths, g_bg) + (None,) * 11
 
 
 def rasterize_to_pixels(means2d, conics, colors, opacities, depths, backgrounds, radii, cum_tiles, isect_offsets,
-                        flatten_ids, width, height, with_depth=False, ed_mode=False, absgrad=False, flavour=0):
-    """flavour 0 = gsplat compositing rule, 1 = diff_gauss / Inria rule (see RasterCfg in rasterize.cu)."""
+                        flatten_ids, isect_ids, width, height, with_depth=False, ed_mode=False, absgrad=False, flavour=0):
+    """``isect_ids`` / ``flatten_ids``: the sorted keys and values (the tile of a pair is read from its key).
+    flavour 0 = gsplat compositing rule, 1 = diff_gauss / Inria rule (see RasterCfg in rasterize.cu)."""
     return _Rasterize.apply(means2d, conics, colors, opacities, depths, backgrounds, radii, cum_tiles, isect_offsets,
-                            flatten_ids, int(width), int(height), bool(with_depth), bool(ed_mode), bool(absgrad),
-                            int(flavour))
+                            flatten_ids, isect_ids, int(width), int(height), bool(with_depth), bool(ed_mode),
+                            bool(absgrad), int(flavour))

@@ -29,7 +29,7 @@ def _stage_forward(means2d, conics, colors, opac, depths, radii, W, H, flavour):
     m2, cn, cl, op, dp, rd = (t.to(dev) for t in (means2d[None], conics[None], colors[None], opac[None], depths[None], radii[None]))
     _, ids, flat, cum = R.isect_tiles(m2, rd.contiguous(), dp, tpg.to(dev).contiguous(), W, H)
     offs = R.isect_offset_encode(ids, 1, W, H)
-    out, alpha, last = R.rasterize_to_pixels(m2, cn, cl, op, None, None, rd.contiguous(), cum, offs, flat, W, H,
+    out, alpha, last = R.rasterize_to_pixels(m2, cn, cl, op, None, None, rd.contiguous(), cum, offs, flat, ids, W, H,
                                              with_depth=False, ed_mode=False, absgrad=False, flavour=flavour)
     kw = dict(max_alpha=0.99, t_stop_inclusive=False, pixel_center=0.0) if flavour == 1 else {}
     rout, ralpha, rlast, unstable = G.rasterize_to_pixels(means2d[None], conics[None], colors[None], opac[None], W, H, 16,

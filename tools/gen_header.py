@@ -30,12 +30,12 @@ GROUPS = [
       "emd_dense_set_tc", "emd_deform_apply_fwd",
       "emd_deform_apply_bwd", "emd_deform_embed_grad_workspace_bytes", "emd_deform_embed_grad"]),
     ("K2   projection", ["emd_projection_fwd", "emd_projection_bwd", "emd_dg_preprocess_fwd", "emd_dg_preprocess_bwd"]),
-    ("K3   tile intersection", ["emd_scan_workspace_bytes", "emd_cumsum_i32_i64", "emd_exclusive_scan_u32",
-                                "emd_isect_emit", "emd_dg_isect_emit"]),
+    ("K3   tile intersection", ["emd_scan_workspace_bytes", "emd_cumsum_i32_i64", "emd_exclusive_scan_u32", "emd_exclusive_scan_u8_u32",
+                                "emd_exclusive_scan_u8_u32", "emd_isect_emit", "emd_dg_isect_emit"]),
     ("K4   radix sort", ["emd_radix_sort_workspace_bytes", "emd_radix_sort_pairs"]),
     ("K5   tile ranges", ["emd_isect_offsets", "emd_tile_order", "emd_raster_segment_size", "emd_raster_checkpoint_floats",
-                        "emd_raster_segout_floats", "emd_raster_segment_slots"]),
-    ("K6/K7 rasterization", ["emd_raster_pack", "emd_rasterize_fwd", "emd_rasterize_bwd_workspace_bytes",
+                        "emd_raster_segout_floats", "emd_raster_segment_slots", "emd_raster_max_ctas"]),
+    ("K6/K7 rasterization", ["emd_raster_pack", "emd_raster_sort_records", "emd_rasterize_fwd", "emd_rasterize_bwd_workspace_bytes",
                              "emd_rasterize_bwd", "emd_raster_set_counters"]),
 ]
 
@@ -168,6 +168,8 @@ DOC = {
     "emd_scan_workspace_bytes": "Workspace bytes of the scans for n elements.",
     "emd_cumsum_i32_i64": "Inclusive cumulative sum (torch.cumsum of tiles_per_gauss in gsplat's isect_tiles); total -> device scalar.",
     "emd_exclusive_scan_u32": "Exclusive scan (radix-sort tables); in-place allowed.",
+    "emd_exclusive_scan_u8_u32": "Exclusive scan uint8 -> uint32 with the total written to *total_out (device; out + n makes `out` "
+                                 "an (n+1)-long offsets array): per-pair gradient-entry counts -> entry_base of the raster backward.",
     "emd_isect_emit": "gsplat isect_tiles second pass: key = cam << (32+tile_n_bits) | tile << 32 | float_bits(depth), value = cam*N+gid.",
     "emd_radix_sort_workspace_bytes": "Workspace bytes of emd_radix_sort_pairs for n pairs.",
     "emd_radix_sort_pairs": "cub::DeviceRadixSort::SortPairs as gsplat/diff_gauss call it: stable, ascending, bits [begin,end). "
@@ -175,20 +177,30 @@ DOC = {
     "emd_isect_offsets": "gsplat isect_offset_encode / diff_gauss identifyTileRanges: first sorted index of every (camera, tile).",
     "emd_tile_order": "Tile ids ordered longest-list-first (scheduling only; results do not depend on it) plus the segment "
                       "bookkeeping of the segment-parallel forward / backward: seg_prefix (inclusive #segments along that order) "
-                      "and ckpt_base (first checkpoint slot per multi-segment tile).",
+                      "ckpt_base (first checkpoint slot per multi-segment tile) and cta_map ([emd_raster_max_ctas] x (tile id, "
+                      "segment | segments << 16): the (tile, segment) each compositing CTA works on).",
+    "emd_raster_max_ctas": "Upper bound on the compositing CTAs (tile segments) for P intersections: length of cta_map.",
     "emd_raster_segment_size": "Gaussians per segment of a tile's sorted list (the backward runs one CTA per segment).",
     "emd_raster_checkpoint_floats": "Floats per forward checkpoint (T and 4 accumulators of a tile's 256 pixels).",
     "emd_raster_segout_floats": "Floats per segment-output record of the segment-parallel forward (scratch).",
     "emd_raster_segment_slots": "Upper bound on the checkpoint / segment-output slots needed for P intersections.",
-    "emd_raster_pack": "Packs per-(camera,Gaussian) mean2d/conic/opacity/colour(+depth) into three float4 records for the compositor.",
+    "emd_raster_pack": "Packs per-(camera,Gaussian) mean2d/conic/opacity/colour(+depth) + the half extents of its alpha >= 1/255 box "
+                       "into three float4 records.",
+    "emd_raster_sort_records": "Writes the depth-sorted, per-tile-contiguous record stream the compositing kernels stage with bulk "
+                               "asynchronous copies (cp.async.bulk + mbarrier): one 48-byte record per sorted (tile, Gaussian) "
+                               "intersection -- mean, opacity, conic pre-scaled for exp2, four channels, the mask of the tile's 8x4 "
+                               "pixel blocks its alpha >= 1/255 box reaches, and its gradient slot (emission-order index).  "
+                               "isect_ids / flatten_ids are the SORTED keys / values; flavour 0 gsplat, 1 diff_gauss tile rectangles.",
     "emd_rasterize_fwd": "gsplat rasterize_to_pixels forward (RGB / +depth / expected depth, alpha, last_ids) "
                          "(reference call OmniRe/models/trainers/base.py:393-408).  Tiles longer than one segment are "
                          "composited one CTA per segment (transmittance pass, compositing pass, combine); ckpt "
                          "[emd_raster_segment_slots(P) x emd_raster_checkpoint_floats()] is kept for the backward, seg_out "
-                         "[slots x emd_raster_segout_floats()] is scratch.",
+                         "[slots x emd_raster_segout_floats()] is scratch.  srecs = emd_raster_sort_records' stream.",
     "emd_rasterize_bwd_workspace_bytes": "Workspace bytes of emd_rasterize_bwd for P intersections.",
     "emd_rasterize_bwd": "gsplat rasterize_to_pixels backward: v_means2d (+abs), v_conics, v_colors, v_depths, v_opacities; "
-                         "deterministic (no float atomics).",
+                         "back to front from the forward's checkpoints over the same record stream; per warp a pixel-major pass "
+                         "(alpha, T, two scalars per pair) and a Gaussian-major pass (each lane sums one Gaussian's 12 components "
+                         "over the block's pixels); deterministic (no float atomics, no shuffle reductions per pair).",
 }
 
 

@@ -32,7 +32,8 @@ def count(scene, c2w, Ks, W, H, frame=7, step=20000):
     walked = int(torch.clamp(last - offs[:, ty, tx].to(torch.int64) + 1, min=0).sum().item())
     return {"n_isects": info["isect_ids"].numel(), "staged_tile_gaussian_pairs": c[3], "warp_candidate_evaluations": c[0],
             "evaluations_with_a_blend": c[1], "blended_pixel_gaussian_pairs": c[2], "walked_pixel_list_entries": walked,
-            "lanes_blending_per_evaluation": round(c[2] / max(c[0], 1), 2)}
+            "lanes_blending_per_evaluation": round(c[2] / max(c[0], 1), 2),
+            "phase2_groups": c[4], "phase2_group_members": c[5], "members_per_group_of_16": round(c[5] / max(c[4], 1), 2)}
 
 
 if __name__ == "__main__":

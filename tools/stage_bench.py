@@ -66,10 +66,10 @@ def run(a):
     res["offsets_ms"] = timeit(lambda: R.isect_offset_encode(ids_s, C, W, H))
     offs = R.isect_offset_encode(ids_s, C, W, H)
     def rfwd():
-        return R.rasterize_to_pixels(means2d, conics, rgbs, opac, depths, None, radii, cum, offs, flat_s, W, H, with_depth=True, ed_mode=True, absgrad=True)
+        return R.rasterize_to_pixels(means2d, conics, rgbs, opac, depths, None, radii, cum, offs, flat_s, ids_s, W, H, with_depth=True, ed_mode=True, absgrad=True)
     res["raster_fwd_ms(pack+fwd)"] = timeit(rfwd)
     m2 = means2d.detach().requires_grad_(True); cn = conics.detach().requires_grad_(True); cl = rgbs.detach().requires_grad_(True); op = opac.detach().requires_grad_(True); dp = depths.detach().requires_grad_(True)
-    out_c, out_a, _ = R.rasterize_to_pixels(m2, cn, cl, op, dp, None, radii, cum, offs, flat_s, W, H, with_depth=True, ed_mode=True, absgrad=True)
+    out_c, out_a, _ = R.rasterize_to_pixels(m2, cn, cl, op, dp, None, radii, cum, offs, flat_s, ids_s, W, H, with_depth=True, ed_mode=True, absgrad=True)
     vc = torch.randn_like(out_c); va = torch.randn_like(out_a)
     def rbwd():
         torch.autograd.grad([out_c, out_a], [m2, cn, cl, op, dp], [vc, va], retain_graph=True)
