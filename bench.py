@@ -31,6 +31,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# per-step buffer sizes follow the intersection count, which changes with the frame: expandable segments let the caching
+# allocator grow its blocks in place instead of calling cudaMalloc (a device-wide sync) whenever a step needs a little more
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+
 import torch  # noqa: E402
 
 W_IMG, H_IMG = 960, 640

@@ -23,19 +23,34 @@ def shard_views(num_timesteps: int, rank: int, world: int) -> List[int]:
     return list(range(rank, num_timesteps, world))
 
 
+def _flag_device(params) -> torch.device:
+    for p in params:
+        return p.device
+    return torch.device("cpu")
+
+
 def allreduce_grads(params: Iterable[Tensor], average: bool = False, bucket_bytes: int = 64 << 20) -> int:
     """Sum (or average) ``.grad`` of every parameter across ranks.
 
     Small tensors (track heads, pose rows, temporal tables) are packed into flat buckets so the launch
     count stays low; large per-Gaussian tensors go out as they are.  All operations are issued
     asynchronously and waited for once.  Returns the number of bytes reduced (per rank)."""
+    params = list(params)   # may be a generator (``model.parameters()``): it is walked more than once
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return 0
     world = dist.get_world_size()
+    # every rank must issue the same sequence of collectives: a parameter without a gradient on THIS rank (a node class
+    # none of this rank's views saw) takes part with zeros -- unless no rank has one, in which case it stays None
+    used = torch.tensor([0.0 if p.grad is None else 1.0 for p in params], device=_flag_device(params))
+    if used.numel():
+        dist.all_reduce(used, op=dist.ReduceOp.MAX)
+    used = used.tolist()
     big, small = [], []
-    for p in params:
-        if p.grad is None:
+    for p, u in zip(params, used):
+        if not u:
             continue
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
         (big if p.grad.numel() * p.grad.element_size() >= (1 << 20) else small).append(p.grad)
     works, total = [], 0
     for g in big:
@@ -92,7 +107,10 @@ class GradReducer:
     (projection, EMD deformation) runs under it.
     ``finish()`` -- called once after ``backward()`` -- reduces everything else in one more grouped launch
     (a parameter that got no gradient on this rank, e.g. SMPL nodes of a frame without visible pedestrians,
-    contributes zeros so every rank issues the same sequence) and waits for all of it.
+    contributes zeros so every rank issues the same sequence; one that got none on ANY rank gets its ``.grad`` reset
+    to None afterwards, so the optimizer skips it as the reference's does) and waits for all of it.
+    Contract: exactly ONE ``backward()`` per ``finish()`` (the hooks reduce a gradient the moment it is first
+    written; a second accumulation into it would race the all-reduce in flight) -- asserted.
 
     The early sequence is the order in which autograd completes the groups, which is the same on every rank as
     long as the early parameters are used by every rank's step; that is the contract of ``early``."""
@@ -124,8 +142,11 @@ class GradReducer:
         return n
 
     def _hook(self, p: Tensor) -> None:
-        if p.grad is None or id(p) in self._seen:
+        if p.grad is None:
             return
+        if id(p) in self._seen:
+            raise RuntimeError("GradReducer: a second backward() accumulated into an early-group gradient before finish(); "
+                               "run one backward() per finish() (or construct the reducer without `early`)")
         self._seen.add(id(p))
         gi = self._group_of[id(p)]
         self._pending[gi] -= 1
@@ -138,6 +159,11 @@ class GradReducer:
         if not self.active:
             return 0
         world = dist.get_world_size()
+
+        # which parameters got a gradient on ANY rank (one tiny MAX all-reduce, issued first on every rank)
+        mine = [p for p in self.params if p.requires_grad]
+        used = torch.tensor([0.0 if p.grad is None else 1.0 for p in mine], device=_flag_device(mine))
+        used_work = dist.all_reduce(used, op=dist.ReduceOp.MAX, async_op=True) if used.numel() else None
 
         def grad_of(p):
             if p.grad is None:
@@ -163,6 +189,11 @@ class GradReducer:
             w.wait()
         if flat is not None:
             torch._foreach_copy_(small, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in small]), small)])
+        if used_work is not None:
+            used_work.wait()
+            for p, u in zip(mine, used.tolist()):
+                if not u:
+                    p.grad = None       # unused on every rank: stays without a gradient, like in the reference
         if self.average:
             for p in self.params:
                 if p.grad is not None:

@@ -101,14 +101,18 @@ def rasterization(
         def _eval_colors():
             deferred["colors"] = colors_fn()
     tpg, isect_ids, flatten_ids, cum_tiles = R.isect_tiles(means2d.detach(), radii, depths.detach(), tpg, width, height,
-                                                           between=_eval_colors if callable(colors) else None)
+                                                           between=_eval_colors if callable(colors) else None,
+                                                           grad_enabled=torch.is_grad_enabled())
     if callable(colors):
         colors = deferred["colors"]
     isect_offsets = R.isect_offset_encode(isect_ids, C, width, height)
     if sh_degree is not None:
         # colors are SH coefficients [(C,)N,K,3]; directions from the camera centres
+        # DEVIATION from gsplat, stated: the view directions are taken from DETACHED means (the SH kernel has no direction
+        # gradient).  The reference never takes this branch -- it passes precomputed colours built from detached
+        # directions (vanilla.py:386-388, rigid.py:582-584) -- so its gradients are unaffected.
         camtoworlds = torch.linalg.inv(viewmats)
-        dirs = means[None, :, :] - camtoworlds[:, None, :3, 3]  # [C,N,3]
+        dirs = means.detach()[None, :, :] - camtoworlds[:, None, :3, 3]  # [C,N,3]
         coeffs = colors if colors.dim() == 4 else colors[None].expand(C, -1, -1, -1)
         cols = spherical_harmonics(sh_degree, dirs.reshape(-1, 3), coeffs.reshape(C * N, -1, 3)).reshape(C, N, 3)
         colors = torch.clamp_min(cols + 0.5, 0.0)

@@ -112,11 +112,13 @@ def fully_fused_projection(means, quats, scales, viewmats, Ks, width, height, ep
 
 
 @torch.no_grad()
-def cumsum_tiles(tiles_per_gauss: Tensor, between=None) -> Tuple[Tensor, int]:
+def cumsum_tiles(tiles_per_gauss: Tensor, between=None, grad_enabled: bool = True) -> Tuple[Tensor, int]:
     """Inclusive int64 cumulative sum + the total (one pinned-memory readback: the
     only host sync of the pipeline, as in gsplat).  ``between`` (optional callable) runs after the
     readback has been issued and before the host waits for it: work it launches keeps the GPU busy
-    while the count travels, so the stages that need the count start without a bubble."""
+    while the count travels, so the stages that need the count start without a bubble.  It runs under
+    ``torch.set_grad_enabled(grad_enabled)`` -- the CALLER's grad mode, captured before this no-grad helper was entered
+    (an eval render under ``torch.no_grad()`` must not build a graph for the deferred colours)."""
     L = _C.lib()
     flat = tiles_per_gauss.reshape(-1)
     n = flat.numel()
@@ -134,7 +136,7 @@ def cumsum_tiles(tiles_per_gauss: Tensor, between=None) -> Tuple[Tensor, int]:
     else:
         ev = torch.cuda.Event()
         ev.record()
-        with torch.enable_grad():
+        with torch.set_grad_enabled(grad_enabled):
             between()
         ev.synchronize()
     return cum, int(host.item())
@@ -162,13 +164,13 @@ def radix_sort_pairs(keys: Tensor, vals: Tensor, begin_bit: int, end_bit: int) -
 
 @torch.no_grad()
 def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, width: int, height: int,
-                sort: bool = True, between=None):
+                sort: bool = True, between=None, grad_enabled: bool = True):
     """-> tiles_per_gauss, isect_ids[P] i64 (sorted), flatten_ids[P] i32 (sorted), cum_tiles[C*N] i64.
     ``between``: see ``cumsum_tiles``."""
     L = _C.lib()
     C, N = radii.shape
     tw, th, bits = tile_grid(width, height)
-    cum, P = cumsum_tiles(tiles_per_gauss, between)
+    cum, P = cumsum_tiles(tiles_per_gauss, between, grad_enabled)
     dev = radii.device
     isect_ids = torch.empty(P, dtype=torch.int64, device=dev)
     flatten_ids = torch.empty(P, dtype=torch.int32, device=dev)

@@ -30,6 +30,15 @@ def _worker(rank, world, port, ret):
             dist.all_reduce(ref)
             assert torch.equal(p.grad, ref), "bucketed all-reduce differs from per-tensor all-reduce"
         assert nbytes == sum(l.numel() * 4 for l in local if l is not None)
+        # average=True through a GENERATOR of parameters (walked twice inside), and a gradient missing on one rank only
+        ps2 = [torch.zeros(4, requires_grad=True), torch.zeros(3, requires_grad=True), torch.zeros(2, requires_grad=True)]
+        ps2[0].grad = torch.full((4,), float(rank + 1))
+        if rank == 0:
+            ps2[1].grad = torch.full((3,), 4.0)
+        D.allreduce_grads((q for q in ps2), average=True)
+        assert torch.equal(ps2[0].grad, torch.full((4,), 1.5)), "average=True was skipped for a generator input"
+        assert torch.equal(ps2[1].grad, torch.full((3,), 2.0)), "a gradient present on one rank only must still be reduced"
+        assert ps2[2].grad is None, "a parameter unused on every rank keeps grad None"
         a, b, c = torch.full((4,), float(rank + 1)), torch.full((4,), 2.0), torch.tensor([1.0 + rank, 5.0 - rank])
         D.allreduce_densify_stats(a, b, c)
         assert torch.equal(a, torch.full((4,), 3.0)) and torch.equal(b, torch.full((4,), 4.0))
@@ -41,7 +50,8 @@ def _worker(rank, world, port, ret):
         mid = torch.randn(300000, 1, generator=gr).requires_grad_(True)      # >= 1 MB, reduced at finish
         tiny = torch.randn(6, 6, generator=gr).requires_grad_(True)          # flat bucket
         skip = torch.randn(9, generator=gr).requires_grad_(True)             # no grad on rank 1
-        ps = [big, mid, tiny, skip]
+        never = torch.randn(4, generator=gr).requires_grad_(True)            # no grad on any rank
+        ps = [big, mid, tiny, skip, never]
         red = D.GradReducer(ps, early=[[big], [mid, tiny]])
         for it in range(2):
             for q in ps:
@@ -54,6 +64,7 @@ def _worker(rank, world, port, ret):
                 assert red.early_bytes == (big.numel() + mid.numel() + tiny.numel()) * 4, "early groups were not reduced from their hooks"
             n = red.finish()
             assert n == sum(q.numel() * 4 for q in ps)
+            assert never.grad is None, "a parameter no rank used must come out of finish() without a gradient"
             assert torch.equal(big.grad, torch.full_like(big, 3.0))
             assert torch.allclose(mid.grad, 2 * mid.detach() * 5.0)
             assert torch.equal(tiny.grad, torch.full_like(tiny, 2.0 * (it + 1)))
