@@ -45,10 +45,6 @@ STEP_KEYS = ("pixels", "sky_masks", "lidar") if LOSS_MODE != "cotangents" else (
 METRIC = "fwd+bwd megapixels/s per train step"
 UNIT = "Mpix/s"
 
-# algorithmic work per unit
-FLOP_PER_PAIR_FWD = 42.0    # 21 FP32-pipe instructions, FMA counted as 2
-FLOP_PER_PAIR_BWD = 120.0   # 60 FP32-pipe instructions per blended pair
-FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal: MEASURED_PEAKS.json has no fp32 figure
 
 
 def workload_cfg(args):
@@ -144,6 +140,49 @@ def build_inputs(args, rank, world):
             host["lidar"].append(lidar.pin_memory())
         host["rgb_sky"] = torch.rand(C, H_IMG, W_IMG, 3, generator=g)             # sky model output (model side, resident)
     return (bg, rigid, smpl), host
+
+
+def fp32_probe(dev):
+    """Measured FP32-pipe ceilings of this GPU (library probe kernels: FFMA, packed FFMA2, shuffle), best of 5."""
+    from emd_b200 import _C
+    L = _C.lib()
+    out = torch.zeros(148 * 8 * 256, device=dev)
+    res = {}
+    for kind, name, flop in ((0, "ffma", 2), (1, "ffma2", 4), (4, "shfl_bfly", 0)):
+        best = None
+        for rep in range(6):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _C.check(L.emd_fp32_probe(kind, 400, _C.ptr(out), _C.stream()), "emd_fp32_probe")
+            b.record()
+            torch.cuda.synchronize()
+            if rep:
+                best = a.elapsed_time(b) if best is None else min(best, a.elapsed_time(b))
+        n = int(L.emd_fp32_probe_lane_instructions(kind, 400))
+        res[name] = {"lane_inst_per_clk_per_sm_at_1965MHz": round(n / (best * 1e-3) / 148 / 1.965e9, 2)}
+        if flop:
+            res[name]["tflops"] = round(n * flop / (best * 1e-3) / 1e12, 2)
+    return res
+
+
+def raster_counters(scene, dev_in, cam_centers, dev):
+    """One more step with the counting build of the raster backward: executed (warp, Gaussian) evaluations, those that
+    blended, blended (pixel, Gaussian) pairs, staged (tile, Gaussian) pairs, transposed-accumulation groups."""
+    from emd_b200 import _C
+    L = _C.lib()
+    ctr = torch.zeros(8, dtype=torch.int64, device=dev)
+    renders, alphas, info = scene.render_raw(dev_in["c2w"], dev_in["Ks"], W_IMG, H_IMG, 7, STEP0, viewmats=dev_in["viewmats"],
+                                             cam_centers=cam_centers)
+    L.emd_raster_set_counters(_C.ptr(ctr))
+    try:
+        (renders.mean() + alphas.mean()).backward()
+        torch.cuda.synchronize()
+    finally:
+        L.emd_raster_set_counters(None)
+    c = ctr.tolist()
+    return {"frame": 7, "n_isects": int(info["isect_ids"].numel()), "staged_tile_gaussian_pairs": c[3],
+            "warp_gaussian_evaluations": c[0], "evaluations_with_a_blend": c[1], "blended_pixel_gaussian_pairs": c[2],
+            "accumulation_groups": c[4], "members_per_group_of_16": round(c[5] / max(c[4], 1), 2)}
 
 
 def run_ours(args):
@@ -304,61 +343,101 @@ def run_ours(args):
     e2e_value = world * pix / (ms_e2e / args.steps * 1e-3) / 1e6
     h2d = sum(host[k].numel() * 4 for k in ("c2w", "Ks", "viewmats")) + sum(host[k][0].numel() * 4 for k in STEP_KEYS)
 
-    # dominant kernel: raster backward.  Algorithmic work = blended-or-tested pixel-Gaussian pairs.
-    info = stats["info"]
-    with torch.no_grad():
-        offs = info["isect_offsets"]  # [C,th,tw]
-        last = info["last_ids"].to(torch.int64)  # [C,H,W]
-        th, tw = offs.shape[1:]
-        ty = (torch.arange(H_IMG, device=dev) // 16)[:, None].expand(H_IMG, W_IMG)
-        tx = (torch.arange(W_IMG, device=dev) // 16)[None, :].expand(H_IMG, W_IMG)
-        start = offs[:, ty, tx].to(torch.int64)
-        pairs_bwd = int(torch.clamp(last - start + 1, min=0).sum().item())
+    # ---- roofline of the dominant kernel (raster backward): EXECUTED work, not a nominal pair count -------------------
+    # (a) live: the kernel's average CUDA-event duration over the profiled steps; the FP32-pipe ceiling measured by the
+    #     library's own FFMA probe on this GPU, now; the kernel's executed-work counters from one more step run with its
+    #     counting build (candidate evaluations, blended pairs).
+    # (b) from the committed `ncu --set full` capture of this same command (profiles/ncu_roofline.json names it):
+    #     executed warp instructions, FMA-pipe warp instructions, thread-level FADD / FMUL / FFMA, shared-memory
+    #     wavefronts, DRAM bytes per launch.  Instruction counts do not depend on the profiler's clocks; durations do,
+    #     so every rate below divides the capture's COUNTS by the LIVE event time.
     k_steps = args.steps
     rb_ms = kern.get("raster_bwd", (0.0, 1))[0] / max(1, kern.get("raster_bwd", (0.0, 1))[1])
     rf_ms = kern.get("raster_fwd", (0.0, 1))[0] / max(1, kern.get("raster_fwd", (0.0, 1))[1])
-    achieved = pairs_bwd * FLOP_PER_PAIR_BWD / (rb_ms * 1e-3) / 1e12 if rb_ms > 0 else 0.0
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:  # noqa: BLE001
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    probe = fp32_probe(dev)
+    counters = raster_counters(scene, dev_in, cam_centers, dev)
+    ncu = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_roofline.json")) as fh:
+            ncu = json.load(fh)
+    except (OSError, ValueError):
+        pass
+    cap = ncu.get("raster_bwd", {})
+    clk_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)   # SM clock sampled during the timed region
+    t_rb = rb_ms * 1e-3
+    lanes = 148 * 128
+
+    def rate(x, denom):
+        return round(x / denom, 4) if (x and t_rb > 0) else None
+
+    fma_inst = cap.get("pipe_fma_warp_inst")
+    thread_inst = (sum(cap.get(k) or 0 for k in ("thread_inst_fadd", "thread_inst_fmul", "thread_inst_ffma"))
+                   if cap.get("thread_inst_ffma") else None)
+    achieved = fma_inst * 32 * 2 / t_rb / 1e12 if (fma_inst and t_rb > 0) else 0.0
+    peak_meas = probe["ffma"]["tflops"]
+    roofline = {
+        "kernel": "raster_bwd", "bound": "fp32", "unit": "TFLOP/s",
+        "achieved": round(achieved, 3), "peak": peak_meas, "frac": round(achieved / peak_meas, 4) if peak_meas else None,
+        "definition": "FMA-pipe issue rate: warp instructions executed on the FMA pipe (FADD/FMUL/FFMA/IMAD, capture) x 32 "
+                      "lanes x 2 flop / live event-timed launch duration, against the FFMA rate this GPU sustained in the "
+                      "library's probe kernel during this run (emd_fp32_probe).  frac_of_nominal divides by 148 SM x 128 "
+                      "lanes x the SM clock sampled during the run instead -- the definition of ncu's "
+                      "sm__inst_executed_pipe_fma pct, quoted beside it from the capture",
+        "peak_source": "measured: emd_fp32_probe kind 0 (FFMA), best of 5 launches in this process; nominal 148 x 128 x 2 x "
+                       "1.965 GHz = 74.45 (MEASURED_PEAKS.json holds HBM and bf16 figures only)",
+        "frac_of_nominal": rate(fma_inst * 32 if fma_inst else None, t_rb * lanes * clk_hz),
+        "ncu_pipe_fma_pct_in_capture": cap.get("pipe_fma_pct"),
+        "executed_fp32_tflops": round(cap["fp32_flop"] / t_rb / 1e12, 3) if cap.get("fp32_flop") and t_rb > 0 else None,
+        "executed_fp32_frac_of_measured_peak": rate(cap.get("fp32_flop"), t_rb * peak_meas * 1e12),
+        "thread_fp32_inst_frac_of_nominal": rate(thread_inst, t_rb * lanes * clk_hz),
+        "issue_slot_util": rate(cap.get("warp_inst"), t_rb * 148 * 4 * clk_hz),
+        "smem_wavefront_util": rate(cap.get("smem_wavefronts"), t_rb * 148 * clk_hz),
+        "warp_instructions_per_launch": cap.get("warp_inst"), "registers": cap.get("registers"),
+        "traffic": cap.get("dram_bytes_per_launch"), "traffic_source": cap.get("source"),
+        "avg_launch_ms": round(rb_ms, 4), "avg_launch_ms_under_ncu": round(1e3 * cap["time_s"], 4) if cap.get("time_s") else None,
+        "executed_work_per_launch": counters,
+        "fp32_probe": probe,
+        "raster_fwd": {"avg_launch_ms": round(rf_ms, 4)},
+        "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
+    }
+    # ---- HBM-bound stages: algorithmic bytes per step / summed event time of the stage's launches
     P_is = stats["n_isects"]
     N = scene.num_gaussians
-    stage_bytes = {  # algorithmic bytes per launch
+    hits = counters.get("evaluations_with_a_blend", 0)
+    stage_bytes = {
         "projection_fwd": 40.0 * N + 32.0 * C * N, "projection_bwd": 40.0 * N + C * N * (4 + 24) + 40.0 * N,
-        "sort_hist": 8.0 * P_is, "sort_scatter": 24.0 * P_is, "isect_emit": 12.0 * P_is + 24.0 * C * N,
-        "activate_fwd": None, "raster_gather": 49.0 * P_is + 36.0 * C * N,
+        "isect_emit": 12.0 * P_is + 24.0 * C * N,
+        # activations + SH (all classes, deg 3): read sh 192 + mean 12 + opacity 4 + scale 12 + quat 16, write 12 C + 32
+        "activate_fwd": (236.0 + 12.0 * C + 32.0) * N,
+        # backward: the same inputs + cotangents (12 C + 32) read, gradients (192 + 4 + 12 + 16) written
+        "activate_bwd": (236.0 + 12.0 * C + 32.0 + 224.0) * N,
+        # pack (40 read + 48 written per camera-Gaussian) + sorted record stream (key 8 + id 4 + record 48 + radius 4 +
+        # offset 8 read, record 48 + count 1 written per intersection)
+        "raster_pack": 88.0 * C * N + 121.0 * P_is,
+        # entries of the blended (pair, warp) evaluations 64 B + flags, 16 B of offsets read and 36 B written per camera-Gaussian
+        "raster_gather": 65.0 * hits + 52.0 * C * N,
+        "image_loss_fwd": 96.0 * C * H_IMG * W_IMG, "image_loss_bwd": 132.0 * C * H_IMG * W_IMG,
     }
     per_kernel = {}
     step_kernel_ms = sum(v[0] for v in kern.values()) / k_steps
     for name, (ms_total, cnt) in sorted(kern.items(), key=lambda kv: -kv[1][0]):
         ent = {"ms_per_step": round(ms_total / k_steps, 4), "launches_per_step": cnt / k_steps,
                "share": round(ms_total / k_steps / step_kernel_ms, 4)}
-        b = stage_bytes.get(name)
-        if b:
-            gbs = b / (ms_total / cnt * 1e-3) / 1e9
-            ent.update({"bound": "hbm", "achieved_gbs": round(gbs, 1), "frac_of_measured_hbm": round(gbs / hbm_peak, 4)})
+        bts = stage_bytes.get(name)
+        if name in ("sort_hist", "sort_scatter"):     # per launch: keys read once (histograms) / one read + one write per pass
+            bts = (8.0 if name == "sort_hist" else 24.0) * P_is * cnt / k_steps
+        if bts:
+            gbs = bts / (ms_total / k_steps * 1e-3) / 1e9
+            ent.update({"bound": "hbm", "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm_peak, 4)})
         per_kernel[name] = ent
-    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same command
-    # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/ncu_traffic.json names the capture it came from)
-    traffic, traffic_src = None, None
-    try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as fh:
-            ent = json.load(fh)["raster_bwd"]
-        traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
-    except (OSError, KeyError, ValueError):
-        pass
-    roofline = {
-        "kernel": "raster_bwd", "bound": "fp32", "achieved": round(achieved, 3), "peak": round(FP32_PEAK_TFLOPS, 2),
-        "unit": "TFLOP/s", "frac": round(achieved / FP32_PEAK_TFLOPS, 4), "traffic": traffic, "traffic_source": traffic_src,
-        "peak_source": "nominal 148 SM x 128 FMA lanes x 1.965 GHz (MEASURED_PEAKS.json holds HBM and bf16 only)",
-        "algorithmic": f"{pairs_bwd} pixel-Gaussian pairs x {FLOP_PER_PAIR_BWD:.0f} flop per launch (3 cameras)",
-        "avg_launch_ms": round(rb_ms, 4), "pairs_per_launch": pairs_bwd,
-        "raster_fwd": {"avg_launch_ms": round(rf_ms, 4)},
-        "hbm_peak_gbs_measured": hbm_peak, "per_kernel": per_kernel,
-    }
+    roofline["per_kernel"] = per_kernel
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",

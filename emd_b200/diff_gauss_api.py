@@ -113,9 +113,11 @@ class _ScreenGradTap(torch.autograd.Function):
 
 
 def rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        extra_attrs, s: GaussianRasterizationSettings, info: Optional[dict] = None):
+                        extra_attrs, s: GaussianRasterizationSettings, info: Optional[dict] = None,
+                        cache: Optional[dict] = None):
     """``info`` (optional dict) receives the integer artefacts of the call -- ``tiles_touched``, ``point_list_keys``,
-    ``point_list``, ``ranges`` (first sorted index per tile), ``last_ids`` -- which upstream keeps in its binning state."""
+    ``point_list``, ``ranges`` (first sorted index per tile), ``last_ids`` -- which upstream keeps in its binning state.
+    ``cache`` (optional dict, owned by a ``GaussianRasterizer``) carries the geometry of the previous call."""
     if cov3Ds_precomp is not None and (not isinstance(cov3Ds_precomp, Tensor) or cov3Ds_precomp.numel() > 0):
         raise NotImplementedError("emd_b200.diff_gauss: cov3Ds_precomp is not supported; pass scales and rotations")
     if extra_attrs is not None and (not isinstance(extra_attrs, Tensor) or extra_attrs.numel() > 0):
@@ -125,23 +127,36 @@ def rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales
     L = _C.lib()
     W, H = int(s.image_width), int(s.image_height)
     N, dev = means3D.shape[0], means3D.device
-    cam = (_host16(s.viewmatrix), _host16(s.projmatrix), _host16(s.campos), float(s.tanfovx), float(s.tanfovy), W, H,
-           float(s.scale_modifier), int(s.sh_degree))
-    radii, means2d, depths, conics, tiles, rgb = _DgPreprocess.apply(means3D, scales, rotations, shs, cam)
-    if means2D is not None and means2D.requires_grad:
-        means2d = _ScreenGradTap.apply(means2d, means2D, W, H)
-    colors = colors_precomp if colors_precomp is not None else rgb
     tw, th, bits = R.tile_grid(W, H)
-    with torch.no_grad():
-        cum, P = R.cumsum_tiles(tiles)
-        keys = torch.empty(P, dtype=torch.int64, device=dev)
-        vals = torch.empty(P, dtype=torch.int32, device=dev)
-        if P > 0:
-            _C.check(L.emd_dg_isect_emit(_C.ptr(means2d.detach().contiguous()), _C.ptr(radii), _C.ptr(depths.detach()),
-                                         _C.ptr(cum), N, tw, th, _C.ptr(keys), _C.ptr(vals), _C.stream()),
-                     "emd_dg_isect_emit")
-            keys, vals = R.radix_sort_pairs(keys, vals, 0, 32 + bits)
-        offsets = R.isect_offset_encode(keys, 1, W, H)
+    # Geometry (projection, tile binning, depth sort, tile ranges) depends on means / scales / rotations and the camera
+    # only.  S3Gaussian rasterizes the SAME geometry three times per training step with different colours
+    # (gaussian_renderer/__init__.py:145, 172, 187); a rasterizer instance therefore keeps the geometry of its last call
+    # and reuses it while the same (unmodified) tensors come back -- the passes then share ONE projection node in the
+    # autograd graph, which sums their screen-space gradients before a single projection backward.
+    key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in (means3D, scales, rotations)) + \
+        (id(means2D), torch.is_grad_enabled())
+    geom = cache.get("geom") if (cache is not None and cache.get("key") == key and colors_precomp is not None) else None
+    if geom is None:
+        cam = (_host16(s.viewmatrix), _host16(s.projmatrix), _host16(s.campos), float(s.tanfovx), float(s.tanfovy), W, H,
+               float(s.scale_modifier), int(s.sh_degree))
+        radii, means2d, depths, conics, tiles, rgb = _DgPreprocess.apply(means3D, scales, rotations, shs, cam)
+        if means2D is not None and means2D.requires_grad:
+            means2d = _ScreenGradTap.apply(means2d, means2D, W, H)
+        with torch.no_grad():
+            cum, P = R.cumsum_tiles(tiles)
+            keys = torch.empty(P, dtype=torch.int64, device=dev)
+            vals = torch.empty(P, dtype=torch.int32, device=dev)
+            if P > 0:
+                _C.check(L.emd_dg_isect_emit(_C.ptr(means2d.detach().contiguous()), _C.ptr(radii), _C.ptr(depths.detach()),
+                                             _C.ptr(cum), N, tw, th, _C.ptr(keys), _C.ptr(vals), _C.stream()),
+                         "emd_dg_isect_emit")
+                keys, vals = R.radix_sort_pairs(keys, vals, 0, 32 + bits)
+            offsets = R.isect_offset_encode(keys, 1, W, H)
+        geom = (radii, means2d, depths, conics, tiles, rgb, cum, keys, vals, offsets)
+        if cache is not None:
+            cache["key"], cache["geom"] = key, geom
+    radii, means2d, depths, conics, tiles, rgb, cum, keys, vals, offsets = geom
+    colors = colors_precomp if colors_precomp is not None else rgb
     bg = torch.cat([s.bg.float().reshape(3), torch.zeros(1, device=dev)])[None]
     out, alpha, last_ids = R.rasterize_to_pixels(
         means2d[None], conics[None], colors[None], opacities.reshape(1, N), depths[None], bg, radii[None], cum,
@@ -160,6 +175,7 @@ class GaussianRasterizer(nn.Module):
     def __init__(self, raster_settings: GaussianRasterizationSettings):
         super().__init__()
         self.raster_settings = raster_settings
+        self._geom_cache = {}
 
     def markVisible(self, positions: Tensor) -> Tensor:
         """Frustum test of the Inria rasterizer (view-space z > 0.2)."""
@@ -171,4 +187,4 @@ class GaussianRasterizer(nn.Module):
                 cov3Ds_precomp=None, extra_attrs=None):
         self.last_info = {}   # binning state of the most recent call (tests / diagnostics)
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                                   extra_attrs, self.raster_settings, self.last_info)
+                                   extra_attrs, self.raster_settings, self.last_info, self._geom_cache)

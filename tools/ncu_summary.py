@@ -141,7 +141,7 @@ def main(argv):
     for rec in kernel_records(path):
         by.setdefault(rec["kernel"], []).append(rec)
     for name, recs in by.items():
-        key = name.replace("_kernel", "").split("<")[0]
+        key = name.replace("void ", "").split("<")[0].replace("_kernel", "").strip()
         avg = {k: (sum(r[k] for r in recs) / len(recs) if all(isinstance(r.get(k), (int, float)) for r in recs) else None)
                for k in recs[0] if k != "kernel"}
         avg.update({"launches_profiled": len(recs), "source": source,
