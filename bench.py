@@ -211,7 +211,21 @@ def run_ours(args):
               "rest+dc": [[scene.bg["features_rest"]], [scene.bg["features_dc"]]]}
     early = groups[os.environ.get("EMD_BENCH_EARLY", "rest")]
     ar_mode = os.environ.get("EMD_BENCH_ALLREDUCE", "hooks")   # experiments only: "finish" = no overlap, "none" = skip
-    reducer = D.GradReducer(params, early=early if ar_mode == "hooks" else None)
+    # the early groups' all-reduce is left in flight at the end of the step and completed where the NEXT step first needs
+    # those parameters (its SH colour evaluation, after projection / binning / sort have been issued): EMD_BENCH_DEFER=0
+    # restores the wait at the end of the step
+    defer = world > 1 and ar_mode == "hooks" and os.environ.get("EMD_BENCH_DEFER", "1") == "1"
+    reducer = D.GradReducer(params, early=early if ar_mode == "hooks" else None, defer_early=defer)
+    early_ids = {id(q) for grp in early for q in grp} if defer else set()
+    early_params = [q for grp in early for q in grp] if defer else []
+    late = {"opt": None}     # optimizer of the early parameters, run after their deferred exchange (with_optimizer leg)
+
+    def before_colors():
+        reducer.wait_deferred()
+        if late["opt"] is not None and all(q.grad is not None for q in early_params):
+            late["opt"].step(grad_scale=1.0 / world)
+        for q in early_params:
+            q.grad = None
     C = len(YAWS)
     cam_centers = host["c2w"][:, :3, 3].tolist()
     n_frames = 150
@@ -254,13 +268,15 @@ def run_ours(args):
             c2w, Ks, vm = dev_in["c2w"], dev_in["Ks"], dev_in["viewmats"]
             sup = [dev_in[k][s] for k in STEP_KEYS]
         for p in params:
-            p.grad = None
+            if id(p) not in early_ids:     # a deferred gradient is reset where its exchange completes (before_colors)
+                p.grad = None
         if rgb_sky is not None:
             rgb_sky.grad = None
         if LOSS_MODE == "cotangents":
             rgb, depth, alpha, info = scene.render(c2w, Ks, W_IMG, H_IMG, frame, STEP0, viewmats=vm, cam_centers=cam_centers)
         else:
-            renders, alphas, info = scene.render_raw(c2w, Ks, W_IMG, H_IMG, frame, STEP0, viewmats=vm, cam_centers=cam_centers)
+            renders, alphas, info = scene.render_raw(c2w, Ks, W_IMG, H_IMG, frame, STEP0, viewmats=vm, cam_centers=cam_centers,
+                                                     before_colors=before_colors if defer else None)
         if e2e:
             torch.cuda.current_stream().wait_event(copied)
             if not last:   # next step's supervision: issued after the forward (so the upload never sits in front of the
@@ -295,6 +311,8 @@ def run_ours(args):
         a.record()
         for i in range(k_steps):
             fn(first_index + i, e2e, last=(i == k_steps - 1))
+        if defer:
+            before_colors()      # the last step's deferred exchange (and update) completes inside the timed region
         b.record()
         barrier()
         t1 = time.perf_counter()
@@ -326,7 +344,9 @@ def run_ours(args):
     kern = prof.result()
 
     # the same step followed by the optimizer: fused Adam over every parameter, 1/world folded in
-    opt = OPT.FusedAdam([{"params": params}], lr=1e-7, eps=1e-15)
+    opt = OPT.FusedAdam([{"params": [q for q in params if id(q) not in early_ids]}], lr=1e-7, eps=1e-15)
+    if defer:
+        late["opt"] = OPT.FusedAdam([{"params": early_params}], lr=1e-7, eps=1e-15)
 
     def step_opt(i, e2e, last=False):
         loss = step(i, e2e, last)
@@ -337,6 +357,7 @@ def run_ours(args):
         step_opt(i, False)
     ms_opt, launches_opt, _, _ = timed(args.steps, False, args.warmup + 3 * args.steps, fn=step_opt)
 
+    reducer.close()      # the measurement passes below run single-rank work: no gradient hooks
     pix = C * H_IMG * W_IMG
     ms_step = ms_dev / args.steps
     value = world * pix / (ms_step * 1e-3) / 1e6
@@ -452,7 +473,8 @@ def run_ours(args):
                            "note": "same step + fused Adam (emd_adam_step) over all parameters; reported beside the fwd+bwd metric"},
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
         "n_isects_per_step": P_is, "allreduce_bytes_per_step": stats.get("allreduce_bytes", 0),
-        "allreduce_bytes_issued_during_backward": stats.get("allreduce_early_bytes", 0), "fwd_ms_per_frame": None, "clocks": clocks, "roofline": roofline,
+        "allreduce_bytes_issued_during_backward": stats.get("allreduce_early_bytes", 0),
+        "allreduce_deferred_into_next_step": bool(defer), "fwd_ms_per_frame": None, "clocks": clocks, "roofline": roofline,
     }
     if rank == 0:
         # forward-only render time (the second headline metric: ms per frame = per camera image)
@@ -532,6 +554,175 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ----------------------------------------------------------------------------------------------
+def s3g_scene(n: int, seed: int = 6666):
+    """BASELINE.json configs[2]: scene-016-shaped S3Gaussian model -- `n` Gaussians on the synthetic street (the background
+    generator of the OmniRe workload), raw GaussianModel parameters, the EMD deformation network (Xavier-initialised
+    weights of the reference module, tests/golden/emd_s3g.npz) and a HexPlane field [64,64,64,25] x [1,2,4,8]."""
+    import numpy as np
+    from emd_b200 import scenes
+    g = torch.Generator().manual_seed(seed)      # S3Gaussian/train.py:464
+    b = scenes.background(n, g)
+    p = dict(_xyz=b["means"], _scaling=b["scales"], _rotation=b["quats"], _opacity=b["opacities"],
+             _features_dc=b["features_dc"][:, None, :].contiguous(), _features_rest=b["features_rest"].contiguous(),
+             _embedding=0.1 * torch.randn(n, 4, generator=g))
+    z = np.load(os.path.join(ROOT, "tests", "golden", "emd_s3g.npz"))
+    pre = "w.deformation_net."
+    w = {k[len(pre):]: torch.from_numpy(z[k]).clone() for k in z.files
+         if k.startswith(pre) and not any(x in k for x in ("scales_deform", "rotations_deform"))}
+    return p, w, g
+
+
+def run_s3g(args):
+    """`--workload s3g`: one S3Gaussian + EMD training step per view (train.py:207-366): HexPlane gather -> deformation MLP
+    -> activations -> three diff_gauss passes (RGB + depth + alpha, coarse / fine feature maps) -> sky blend -> image
+    losses + deformation regularisers -> backward.  Single GPU (the reference trains one view per step)."""
+    from emd_b200 import _C, s3g_render as SR
+    from emd_b200.emd_s3g import S3GDeformation
+    from emd_b200.hexplane import HexPlaneField
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    _C.check(_C.lib().emd_device_check(), "emd_device_check")
+    n = args.s3g_gaussians
+    p, w, g = s3g_scene(n)
+    field = HexPlaneField(100.0, {"grid_dimensions": 2, "input_coordinate_dim": 4, "output_coordinate_dim": 32,
+                                  "resolution": [64, 64, 64, 25]}, [1, 2, 4, 8]).to(dev)
+    wg = {k: v.to(dev).requires_grad_(True) for k, v in w.items()}
+    pg = {k: v.to(dev).requires_grad_(True) for k, v in p.items()}
+    sky_param = torch.rand(3, H_IMG, W_IMG, generator=g).to(dev).requires_grad_(True)    # sky model output (model side)
+    pc = SR.S3GGaussians(pg, S3GDeformation(wg, hexplane=field), sky_model=lambda cam, acc=None, is_train=False: sky_param)
+    params = pc.parameters() + [sky_param]
+    opts = SR.S3GOptions()
+    n_frames, n_sets = 150, 4
+    yy = torch.linspace(0, 1, H_IMG)[None, :, None].expand(1, H_IMG, W_IMG)
+    host = {"gt_image": [], "gt_depth": [], "sky_mask": [], "gt_feat": []}
+    for _ in range(n_sets):
+        host["gt_image"].append(torch.rand(3, H_IMG, W_IMG, generator=g).pin_memory())
+        d = 2.0 + 70.0 * torch.rand(1, H_IMG, W_IMG, generator=g)
+        d[torch.rand(1, H_IMG, W_IMG, generator=g) < 0.9] = 0.0
+        host["gt_depth"].append(d.pin_memory())
+        host["sky_mask"].append(((yy + 0.1 * torch.randn(1, H_IMG, W_IMG, generator=g)) < 0.3).pin_memory())
+        host["gt_feat"].append(torch.rand(3, H_IMG, W_IMG, generator=g).pin_memory())
+    dev_in = {k: [t.to(dev) for t in v] for k, v in host.items()}
+    cams_host = [SR.make_camera(YAWS[i % 3], W_IMG, H_IMG, time=((7 + 13 * i) % n_frames) / (n_frames - 1), cam_no=i % 3)
+                 for i in range(32)]
+    bg = torch.zeros(3, device=dev)
+    loss_host = torch.zeros(1).pin_memory()
+    stats = {}
+
+    def step(i, e2e, last=False):
+        cam = cams_host[i % len(cams_host)]
+        sset = i % n_sets
+        if e2e:   # this view's camera + supervision from pinned host memory, inside the timed region
+            sup = {k: host[k][sset].to(dev, non_blocking=True) for k in host}
+        else:
+            sup = {k: dev_in[k][sset] for k in host}
+        for q in params:
+            q.grad = None
+        pkg = SR.render(opts, cam, pc, bg, stage="fine", return_dx=True, render_feat=True, iter=STEP0 + i, is_train=True)
+        losses = SR.training_losses(opts, pkg, sup["gt_image"], sup["gt_depth"], sup["sky_mask"], sup["gt_feat"], stage="fine")
+        loss = sum(losses.values())
+        loss.backward()
+        if e2e:
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        stats["n_isects"] = int(pkg["radii"].numel())
+        return loss
+
+    def timed(k_steps, e2e, first):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0, t0 = _C.launch_count(), time.perf_counter()
+        a.record()
+        for i in range(k_steps):
+            step(first + i, e2e)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b), _C.launch_count() - l0, t0, time.perf_counter()
+
+    for i in range(args.warmup):
+        step(i, False)
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    time.sleep(0.3)
+    ms_dev, launches, t0, t1 = timed(args.steps, False, args.warmup)
+    clocks = sampler.stop(t0, t1)
+    for i in range(2):
+        step(i, True)
+    ms_e2e, _, _, _ = timed(args.steps, True, args.warmup + args.steps)
+    with _C.profile() as prof:
+        torch.cuda.synchronize()
+        for i in range(args.steps):
+            step(args.warmup + 2 * args.steps + i, False)
+        torch.cuda.synchronize()
+    kern = prof.result()
+    pix = H_IMG * W_IMG
+    k_steps = args.steps
+    per_kernel = {name: {"ms_per_step": round(ms / k_steps, 4), "launches_per_step": cnt / k_steps}
+                  for name, (ms, cnt) in sorted(kern.items(), key=lambda kv: -kv[1][0])}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    mlp_ms = (kern.get("mlp_fwd", (0, 1))[0] + kern.get("mlp_bwd", (0, 1))[0]) / k_steps
+    mlp_flop = 121.6e3 * 3 * n           # SURVEY 8d: 121.6 kFLOP / Gaussian forward, x3 forward + backward
+    tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    achieved = mlp_flop / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+    h2d = sum(host[k][0].numel() * host[k][0].element_size() for k in host) + 2 * 64 + 12
+    line = {
+        "metric": METRIC, "value": round(pix / (ms_dev / k_steps * 1e-3) / 1e6, 2), "unit": UNIT, "n_gpus": 1, "steps": k_steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_dev / k_steps, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "S3Gaussian+EMD diff_gauss training step, one 640x960 view per step (BASELINE.json configs[2])",
+                   "gaussians": n, "height": H_IMG, "width": W_IMG, "sh_degree": 3, "hexplane": "[64,64,64,25] x [1,2,4,8], 32 features",
+                   "rasterizer_passes": 3, "stage": "fine", "iteration": STEP0, "seed": 6666,
+                   "loss": "L1 + D-SSIM + depth L2 + sky + dx/do/dshs L1 + feature-map L2 (train.py:226-363)",
+                   "l2_policy": "working set >> L2 (1.2 GB of parameters and activations per step); view and supervision change every step"},
+        "e2e": {"value": round(pix / (ms_e2e / k_steps * 1e-3) / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / k_steps, 4)},
+        "gpu_launches": int(launches), "gpu_launches_per_step": launches / k_steps, "clocks": clocks,
+        "roofline": {"kernel": "mlp_fwd + mlp_bwd (EMD deformation network, tcgen05 3xTF32)", "bound": "tensor",
+                     "achieved": round(achieved, 2), "peak": tc_peak, "unit": "TFLOP/s", "frac": round(achieved / tc_peak, 4),
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16 cuBLAS; the kernels run 3 TF32 passes "
+                                    "per product, so 1/6 of that figure is their ceiling)",
+                     "algorithmic": f"121.6 kFLOP x 3 (fwd + bwd) x {n} Gaussians per step", "ms_per_step": round(mlp_ms, 4),
+                     "traffic": None, "per_kernel": per_kernel},
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_s3g(args)
+    print(json.dumps(line))
+
+
+def cpu_baseline_s3g(args):
+    """The oracle's composed S3Gaussian step on a bounded sample: 100 k Gaussians of the same scene, full deformation
+    (HexPlane + MLP) and 3 rasterizer passes on tile rows 16..23 of 40; value = band pixels / time."""
+    from emd_b200 import s3g_render as SR
+    from oracle import diff_gauss_ref as DG, hexplane as OH, s3g_ref as OS
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = 100_000
+    p, w, g = s3g_scene(n)
+    p = {k: v.requires_grad_(True) for k, v in p.items()}
+    w = {k: v.requires_grad_(True) for k, v in w.items()}
+    grids = OH.hash_planes([16, 16, 16, 10], [1, 2, 4, 8], salt=1)
+    aabb = torch.tensor([[100.0] * 3, [-100.0] * 3])
+    cam = SR.make_camera(0.0, W_IMG, H_IMG, time=0.37, cam_no=0)
+    s = DG.Settings(H_IMG, W_IMG, math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5), torch.zeros(3), 1.0,
+                    cam.world_view_transform, cam.full_proj_transform, 3, cam.camera_center)
+    rows = (16, 24)
+    band_pix = (rows[1] - rows[0]) * 16 * W_IMG
+    t0 = time.perf_counter()
+    pkg = OS.render(w, grids, aabb, p, s, 0.37, 0, STEP0, None, tile_rows=rows)
+    gt = torch.rand(3, H_IMG, W_IMG, generator=g)
+    losses = OS.training_losses(pkg, gt, 40.0 * torch.rand(1, H_IMG, W_IMG, generator=g), None, gt)
+    sum(losses.values()).backward()
+    sec = time.perf_counter() - t0
+    return {"value": round(band_pix / sec / 1e6, 4), "unit": UNIT, "cores": cores, "kind": "port", "seconds_per_sample": round(sec, 2),
+            "sample": f"{n} Gaussians of the same scene generator, HexPlane [16,16,16,10] x [1,2,4,8]: deformation of all Gaussians + "
+                      f"three rasterizer passes and losses on tile rows {rows[0]}..{rows[1] - 1} of 40 ({band_pix} pixels), fwd + bwd; "
+                      f"pure-PyTorch CPU oracle"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -544,10 +735,15 @@ def main():
     ap.add_argument("--smpl-instances", type=int, default=8)
     ap.add_argument("--cpu-tile-rows", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="omnire", choices=["omnire", "s3g"],
+                    help="omnire: BASELINE.json configs[1] (the headline line); s3g: configs[2], the S3Gaussian+EMD step")
+    ap.add_argument("--s3g-gaussians", type=int, default=1_000_000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "s3g":
+        run_s3g(args)
     else:
         run_ours(args)
 

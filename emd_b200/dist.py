@@ -116,10 +116,20 @@ class GradReducer:
     long as the early parameters are used by every rank's step; that is the contract of ``early``."""
 
     def __init__(self, params: Sequence[Tensor], early: Optional[Sequence[Sequence[Tensor]]] = None,
-                 average: bool = False, pack_below: int = 4 << 20):
+                 average: bool = False, pack_below: int = 4 << 20, drop_unused: bool = False, defer_early: bool = False):
+        """``drop_unused``: exchange one flag per parameter so that a parameter no rank used keeps ``grad None`` (costs a
+        host read of the flags per step; off, such a parameter gets a zero gradient).
+        ``defer_early``: ``finish()`` returns without waiting for the EARLY groups' all-reduces; ``wait_deferred()``
+        completes them.  The early groups are the SH coefficients, which the next step only reads after its projection
+        and tile binning, so their exchange (and their optimizer update, which the caller runs after
+        ``wait_deferred()``) hides behind the next step's front end."""
         self.params = list(params)
         self.average = average
         self.pack_below = pack_below
+        self.drop_unused = drop_unused
+        self.defer_early = defer_early
+        self._deferred: List = []
+        self._early_works: List = []
         self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.groups: List[List[Tensor]] = [list(g) for g in (early or []) if len(g)]
         self._group_of = {id(p): gi for gi, g in enumerate(self.groups) for p in g}
@@ -135,15 +145,33 @@ class GradReducer:
                 for p in g:
                     self._handles.append(p.register_post_accumulate_grad_hook(self._hook))
 
-    def _launch(self, tensors: List[Tensor]) -> int:
-        self._works.append(_allreduce_group_async(tensors))
+    def _launch(self, tensors: List[Tensor], early: bool = False) -> int:
+        (self._early_works if early else self._works).append(_allreduce_group_async(tensors))
         n = sum(t.numel() * t.element_size() for t in tensors)
         self.bytes += n
         return n
 
+    def wait_deferred(self) -> None:
+        """Complete the early groups' all-reduces left in flight by ``finish()`` (``defer_early``).  Call before anything
+        reads or resets those gradients: the optimizer update of the early parameters, the next step's ``grad = None``."""
+        if not self._deferred:
+            return
+        for w in self._deferred:
+            w.wait()
+        self._deferred = []
+        if self.average:
+            world = dist.get_world_size()
+            for g in self.groups:
+                for p in g:
+                    if p.grad is not None:
+                        p.grad.div_(world)
+
     def _hook(self, p: Tensor) -> None:
         if p.grad is None:
             return
+        if self._deferred:
+            raise RuntimeError("GradReducer: the previous step's deferred all-reduces are still in flight; call "
+                               "wait_deferred() before the backward pass reaches the early parameters")
         if id(p) in self._seen:
             raise RuntimeError("GradReducer: a second backward() accumulated into an early-group gradient before finish(); "
                                "run one backward() per finish() (or construct the reducer without `early`)")
@@ -152,7 +180,7 @@ class GradReducer:
         self._pending[gi] -= 1
         if self._pending[gi] == 0 and not self._group_launched[gi]:
             self._group_launched[gi] = True
-            self.early_bytes += self._launch([q.grad for q in self.groups[gi]])
+            self.early_bytes += self._launch([q.grad for q in self.groups[gi]], early=True)
 
     def finish(self) -> int:
         """Reduce what the hooks did not, wait for everything; returns the bytes reduced this step (per rank)."""
@@ -161,9 +189,11 @@ class GradReducer:
         world = dist.get_world_size()
 
         # which parameters got a gradient on ANY rank (one tiny MAX all-reduce, issued first on every rank)
-        mine = [p for p in self.params if p.requires_grad]
-        used = torch.tensor([0.0 if p.grad is None else 1.0 for p in mine], device=_flag_device(mine))
-        used_work = dist.all_reduce(used, op=dist.ReduceOp.MAX, async_op=True) if used.numel() else None
+        mine = [p for p in self.params if p.requires_grad] if self.drop_unused else []
+        used_work = None
+        if mine:
+            used = torch.tensor([0.0 if p.grad is None else 1.0 for p in mine], device=_flag_device(mine))
+            used_work = dist.all_reduce(used, op=dist.ReduceOp.MAX, async_op=True)
 
         def grad_of(p):
             if p.grad is None:
@@ -173,7 +203,7 @@ class GradReducer:
         for gi, g in enumerate(self.groups):   # an early group whose hooks did not all fire (unused this step)
             if not self._group_launched[gi]:
                 self._group_launched[gi] = True
-                self._launch([grad_of(q) for q in g])
+                self._launch([grad_of(q) for q in g], early=True)
         # everything else: ONE grouped launch; tensors below `pack_below` bytes travel inside one flat buffer (a
         # collective per 100-byte tensor costs a full cross-GPU latency each: 31 tensors ~ 0.5 ms at 8 GPUs)
         rest = [grad_of(p) for p in self.params if p.requires_grad and id(p) not in self._group_of]
@@ -187,6 +217,12 @@ class GradReducer:
             self._launch(big)
         for w in self._works:
             w.wait()
+        if self.defer_early:
+            self._deferred, self._early_works = self._early_works, []
+        else:
+            for w in self._early_works:
+                w.wait()
+            self._early_works = []
         if flat is not None:
             torch._foreach_copy_(small, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in small]), small)])
         if used_work is not None:
@@ -196,7 +232,7 @@ class GradReducer:
                     p.grad = None       # unused on every rank: stays without a gradient, like in the reference
         if self.average:
             for p in self.params:
-                if p.grad is not None:
+                if p.grad is not None and not (self.defer_early and id(p) in self._group_of):
                     p.grad.div_(world)
         total = self.bytes
         self._works, self._seen, self.bytes, self.early_bytes = [], set(), 0, 0

@@ -129,17 +129,27 @@ class StreetScene:
 
     def render_raw(self, camtoworlds: Tensor, Ks: Tensor, width: int, height: int, frame: int, step: int,
                    viewmats: Optional[Tensor] = None, cam_centers=None, near_plane: float = 0.1, far_plane: float = 1e10,
-                   absgrad: bool = True, colors_after_projection: bool = True):
+                   absgrad: bool = True, colors_after_projection: bool = True, before_colors=None):
         """The rasterizer's own outputs ``(renders[C,H,W,4], alphas[C,H,W,1], info)`` (base.py:393-408), which
-        ``emd_b200.losses.omnire_image_losses`` consumes directly (the clamp / split of base.py:412-418 is fused there)."""
+        ``emd_b200.losses.omnire_image_losses`` consumes directly (the clamp / split of base.py:412-418 is fused there).
+        ``before_colors`` (optional callable) runs right before the SH colours are evaluated -- with
+        ``colors_after_projection`` that is after the projection and tile binning have been issued: the point where a
+        data-parallel caller completes the previous step's deferred SH-gradient all-reduce and optimizer update
+        (``dist.GradReducer(defer_early=True)``), hidden behind this step's front end."""
         if cam_centers is None:
             cam_centers = camtoworlds[:, :3, 3].detach().cpu().tolist()
         if viewmats is None:
             viewmats = torch.linalg.inv(camtoworlds)
         if colors_after_projection:
             gs, thunks = self.collect_geometry(frame, step)
-            colors = lambda: self.collect_colors(thunks, cam_centers)  # noqa: E731
+
+            def colors():
+                if before_colors is not None:
+                    before_colors()
+                return self.collect_colors(thunks, cam_centers)
         else:
+            if before_colors is not None:
+                before_colors()
             gs = self.collect_gaussians(cam_centers, frame, step)
             colors = gs["_rgbs"]
         renders, alphas, info = rasterization(

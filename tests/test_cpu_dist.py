@@ -52,7 +52,7 @@ def _worker(rank, world, port, ret):
         skip = torch.randn(9, generator=gr).requires_grad_(True)             # no grad on rank 1
         never = torch.randn(4, generator=gr).requires_grad_(True)            # no grad on any rank
         ps = [big, mid, tiny, skip, never]
-        red = D.GradReducer(ps, early=[[big], [mid, tiny]])
+        red = D.GradReducer(ps, early=[[big], [mid, tiny]], drop_unused=True)
         for it in range(2):
             for q in ps:
                 q.grad = None
@@ -70,6 +70,18 @@ def _worker(rank, world, port, ret):
             assert torch.equal(tiny.grad, torch.full_like(tiny, 2.0 * (it + 1)))
             assert torch.equal(skip.grad, torch.full_like(skip, 3.0))
         red.close()
+        # deferred early groups: finish() leaves their all-reduce in flight, wait_deferred() completes it (and averages)
+        red2 = D.GradReducer(ps, early=[[big]], average=True, defer_early=True)
+        for it in range(2):
+            red2.wait_deferred()           # start of a step: nothing may still be in flight when grads are reset
+            for q in ps:
+                q.grad = None
+            ((big * (rank + 1.0)).sum() + (mid.sum() * 2.0) + tiny.sum() + skip.sum() + never.sum()).backward()
+            red2.finish()
+            assert torch.equal(mid.grad, torch.full_like(mid, 2.0)), "non-deferred gradients are complete after finish()"
+            red2.wait_deferred()
+            assert torch.equal(big.grad, torch.full_like(big, 1.5)), "deferred gradient after wait_deferred(): mean of 1 and 2"
+        red2.close()
         views = D.shard_views(11, rank, world)
         gathered = [None] * world
         dist.all_gather_object(gathered, views)
