@@ -49,7 +49,10 @@ UNIT = "Mpix/s"
 
 def workload_cfg(args):
     return {
-        "workload": "OmniRe+EMD synthetic Waymo-shaped street scene, one training step (BASELINE.json configs[1])",
+        "workload": "OmniRe+EMD synthetic Waymo-shaped street scene, one training step (BASELINE.json configs[1])"
+                    if (len(YAWS) == 3 and args.n_bg == 1_300_000) else
+                    f"OmniRe+EMD synthetic street scene, {len(YAWS)} cameras x one timestep per rank (BASELINE.json configs[3] shape "
+                    f"when run with 5 cameras, ~6 M Gaussians on 8 GPUs)",
         "gaussians": args.n_bg + args.rigid_instances * args.pts_per_rigid + args.smpl_instances * 6890,
         "background": args.n_bg, "rigid": f"{args.rigid_instances}x{args.pts_per_rigid}",
         "smpl": f"{args.smpl_instances}x6890", "cameras": len(YAWS), "height": H_IMG, "width": W_IMG,
@@ -188,7 +191,7 @@ def raster_counters(scene, dev_in, cam_centers, dev):
 def run_ours(args):
     import torch.distributed as dist
 
-    from emd_b200 import _C, dist as D, losses as LS, optim as OPT, pipeline as P
+    from emd_b200 import _C, dist as D, losses as LS, optim as OPT, pipeline as P, raster_ops as R_ops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -200,6 +203,18 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     _C.check(_C.lib().emd_device_check(), "emd_device_check")
     if world > 1:
+        # one rank per GPU on ONE host: give every rank its own slice of the host cores, so the 8 launch threads do not
+        # migrate over each other (EMD_BENCH_AFFINITY=0 leaves the scheduler alone)
+        if os.environ.get("EMD_BENCH_AFFINITY", "1") == "1" and hasattr(os, "sched_setaffinity"):
+            try:
+                cores = sorted(os.sched_getaffinity(0))
+                per = max(1, len(cores) // int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+                mine = cores[local * per:(local + 1) * per]
+                if mine:
+                    os.sched_setaffinity(0, mine)
+                    torch.set_num_threads(max(1, min(4, len(mine))))
+            except OSError:
+                pass
         dist.init_process_group("nccl", device_id=dev)
 
     (bg, rigid, smpl), host = build_inputs(args, rank, world)
@@ -211,10 +226,10 @@ def run_ours(args):
               "rest+dc": [[scene.bg["features_rest"]], [scene.bg["features_dc"]]]}
     early = groups[os.environ.get("EMD_BENCH_EARLY", "rest")]
     ar_mode = os.environ.get("EMD_BENCH_ALLREDUCE", "hooks")   # experiments only: "finish" = no overlap, "none" = skip
-    # the early groups' all-reduce is left in flight at the end of the step and completed where the NEXT step first needs
-    # those parameters (its SH colour evaluation, after projection / binning / sort have been issued): EMD_BENCH_DEFER=0
-    # restores the wait at the end of the step
-    defer = world > 1 and ar_mode == "hooks" and os.environ.get("EMD_BENCH_DEFER", "1") == "1"
+    # EMD_BENCH_DEFER=1 (experiment; measured SLOWER at 8 GPUs, profiles/r02k_*): the early groups' all-reduce is left in
+    # flight at the end of the step and completed where the NEXT step first needs those parameters (its SH colour
+    # evaluation, after projection / binning / sort have been issued)
+    defer = world > 1 and ar_mode == "hooks" and os.environ.get("EMD_BENCH_DEFER", "0") == "1"
     reducer = D.GradReducer(params, early=early if ar_mode == "hooks" else None, defer_early=defer)
     early_ids = {id(q) for grp in early for q in grp} if defer else set()
     early_params = [q for grp in early for q in grp] if defer else []
@@ -307,6 +322,7 @@ def run_ours(args):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _C.launch_count()
+        stats["host_wait0"] = R_ops.HOST_WAIT_S[0]
         t0 = time.perf_counter()
         a.record()
         for i in range(k_steps):
@@ -314,6 +330,7 @@ def run_ours(args):
         if defer:
             before_colors()      # the last step's deferred exchange (and update) completes inside the timed region
         b.record()
+        stats["host_wait_ms_per_step"] = 1e3 * (R_ops.HOST_WAIT_S[0] - stats["host_wait0"]) / k_steps
         barrier()
         t1 = time.perf_counter()
         ms = a.elapsed_time(b)
@@ -325,11 +342,24 @@ def run_ours(args):
 
     for i in range(args.warmup):
         step(i, False)
+    # the W warm-up steps above are the contract's; the caching allocator may still be growing its pools (the per-step
+    # buffer sizes follow the frame's intersection count): keep stepping, untimed, until a step reserves no new memory
+    extra_warm = 0
+    while extra_warm < 24:
+        before = torch.cuda.memory_reserved(dev)
+        step(args.warmup + extra_warm, False)
+        extra_warm += 1
+        grew = torch.tensor([float(torch.cuda.memory_reserved(dev) > before)], device=dev)
+        if world > 1:
+            dist.all_reduce(grew, op=dist.ReduceOp.MAX)
+        if extra_warm >= 3 and not bool(grew.item()):
+            break
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    ms_dev, launches, t0, t1 = timed(args.steps, False, args.warmup)
+    ms_dev, launches, t0, t1 = timed(args.steps, False, args.warmup + extra_warm)
+    host_wait = stats["host_wait_ms_per_step"]
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     for i in range(3):   # warm the pinned-copy path (allocator pools of the copy stream, NCCL buffers)
         step(i, True, last=True)
@@ -472,6 +502,8 @@ def run_ours(args):
                            "ms_per_step": round(ms_opt / args.steps, 4), "gpu_launches_per_step": launches_opt / args.steps,
                            "note": "same step + fused Adam (emd_adam_step) over all parameters; reported beside the fwd+bwd metric"},
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+        "extra_untimed_warmup_steps": extra_warm,
+        "host_wait_ms_per_step": round(host_wait, 4),   # rank 0's host blocked on the GPU: ~0 means launch-bound
         "n_isects_per_step": P_is, "allreduce_bytes_per_step": stats.get("allreduce_bytes", 0),
         "allreduce_bytes_issued_during_backward": stats.get("allreduce_early_bytes", 0),
         "allreduce_deferred_into_next_step": bool(defer), "fwd_ms_per_frame": None, "clocks": clocks, "roofline": roofline,
@@ -738,7 +770,11 @@ def main():
     ap.add_argument("--workload", default="omnire", choices=["omnire", "s3g"],
                     help="omnire: BASELINE.json configs[1] (the headline line); s3g: configs[2], the S3Gaussian+EMD step")
     ap.add_argument("--s3g-gaussians", type=int, default=1_000_000)
+    ap.add_argument("--cameras", type=int, default=3, choices=[1, 2, 3, 4, 5],
+                    help="cameras per timestep (5 with --n-bg 5800000 on 8 GPUs = BASELINE.json configs[3])")
     args = ap.parse_args()
+    global YAWS
+    YAWS = (0.0, 45.0, -45.0, 90.0, -90.0)[:args.cameras]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

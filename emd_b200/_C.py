@@ -71,6 +71,7 @@ _SIGS = {
     "emd_adam_max_tensors": (c_int, []),
     "emd_adam_step": (c_int, [ctypes.POINTER(P)] * 4 + [ctypes.POINTER(c_int64)] + [ctypes.POINTER(ctypes.c_double)] * 5
                       + [ctypes.POINTER(c_int64), c_int, ctypes.c_double, P]),
+    "emd_densify_stats": (c_int, [P, P, c_int64, c_int64, c_float, c_float, c_float, c_int, P, P, P, P]),
     "emd_image_loss_partials_floats": (c_int64, [c_int, c_int, c_int]),
     "emd_image_loss_fwd": (c_int, [P] * 8 + [c_int, c_int, c_int, P, ctypes.POINTER(c_float)] + [P] * 4 + [P]),
     "emd_image_loss_bwd": (c_int, [P] * 8 + [c_int, c_int, c_int, P, ctypes.POINTER(c_float)] + [P] * 7 + [P]),
@@ -156,16 +157,23 @@ def ptr(t: Optional[torch.Tensor], dtype=None, name: str = "tensor") -> Optional
     """Device pointer of a contiguous CUDA tensor (None passes through as NULL)."""
     if t is None:
         return None
+    if t.is_cuda and t.is_contiguous() and (dtype is None or t.dtype == dtype):   # the hot path: one branch
+        return t.data_ptr()
     if not t.is_cuda:
         raise EmdError(f"emd_b200: {name} must be a CUDA tensor (got {t.device}); there is no CPU path")
     if not t.is_contiguous():
         raise EmdError(f"emd_b200: {name} must be contiguous")
-    if dtype is not None and t.dtype != dtype:
-        raise EmdError(f"emd_b200: {name} must be {dtype} (got {t.dtype})")
-    return t.data_ptr()
+    raise EmdError(f"emd_b200: {name} must be {dtype} (got {t.dtype})")
+
+
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
 def stream() -> int:
+    """``cudaStream_t`` of torch's current stream on the current device (the raw-handle query: ``torch.cuda.current_stream()``
+    builds a Python Stream object per call, ~15 us, and the step makes ~30 such calls)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import time
 from typing import Optional, Tuple
 
 import torch
@@ -20,6 +21,9 @@ from . import _C
 TILE_SIZE = 16
 
 _pinned = {}
+# seconds the host has spent blocked on the intersection-count readback (the pipeline's one host sync): a step whose
+# share of this is ~0 is limited by the host's launch rate, not by the GPU (bench.py reports it per step)
+HOST_WAIT_S = [0.0]
 
 
 def _pinned_i64(device) -> Tensor:
@@ -132,13 +136,16 @@ def cumsum_tiles(tiles_per_gauss: Tensor, between=None, grad_enabled: bool = Tru
     host = _pinned_i64(dev)
     host.copy_(total, non_blocking=True)
     if between is None:
+        t0 = time.perf_counter()
         torch.cuda.current_stream().synchronize()
     else:
         ev = torch.cuda.Event()
         ev.record()
         with torch.set_grad_enabled(grad_enabled):
             between()
+        t0 = time.perf_counter()
         ev.synchronize()
+    HOST_WAIT_S[0] += time.perf_counter() - t0
     return cum, int(host.item())
 
 

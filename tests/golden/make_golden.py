@@ -180,7 +180,7 @@ def main():
     print("golden fixtures written to", HERE)
 
 
-if __name__ == "__main__" and not any(a in sys.argv for a in ("--s3g", "--hexplane", "--losses", "--modules", "--deformable")):
+if __name__ == "__main__" and not any(a in sys.argv for a in ("--s3g", "--hexplane", "--losses", "--modules", "--deformable", "--densify")):
     main()
 
 
@@ -401,6 +401,32 @@ if __name__ == "__main__" and "--modules" in sys.argv:
     make_modules_golden()
 
 
+def make_densify_golden():
+    """VanillaGaussians.after_train (OmniRe/models/gaussians/vanilla.py:163-191), the reference's own method, three
+    successive training steps on the CPU -> tests/golden/densify.npz."""
+    _stub(["open3d", "omegaconf", "pytorch3d", "pytorch3d.transforms", "pytorch3d.ops", "gsplat", "gsplat.rendering",
+           "gsplat.cuda", "gsplat.cuda._wrapper", "nvdiffrast", "nvdiffrast.torch", "imageio", "matplotlib",
+           "matplotlib.pyplot", "trimesh", "kornia", "third_party", "third_party.smplx", "third_party.smplx.smplx",
+           "third_party.smplx.smplx.lbs", "third_party.smplx.smplx.utils", "smplx", "sklearn", "sklearn.neighbors"])
+    _cpuify()
+    sys.path.insert(0, f"{REF}/OmniRe")
+    vanilla = importlib.import_module("models.gaussians.vanilla")
+    g = torch.Generator().manual_seed(77)
+    n, steps = 500, 3
+    me = types.SimpleNamespace(num_points=n, filter_mask=torch.ones(n, dtype=torch.bool), xys_grad_norm=None, vis_counts=None,
+                               max_2Dsize=None)
+    radii = (torch.randint(0, 40, (steps, n), generator=g) * (torch.rand(steps, n, generator=g) < 0.6)).to(torch.int32)
+    grads = 1e-3 * torch.randn(steps, n, 2, generator=g)
+    out = dict(radii=radii.numpy(), grads=grads.numpy(), last_size=np.int64(960))
+    for s_ in range(steps):
+        vanilla.VanillaGaussians.after_train(me, radii[s_], grads[s_], 960)
+        out[f"s{s_}_xys_grad_norm"] = me.xys_grad_norm.clone().numpy()
+        out[f"s{s_}_vis_counts"] = me.vis_counts.clone().numpy()
+        out[f"s{s_}_max_2Dsize"] = me.max_2Dsize.clone().numpy()
+    np.savez_compressed(f"{HERE}/densify.npz", **out)
+    print("wrote densify.npz")
+
+
 def make_deformable_golden():
     """The reference's own ``DeformableNodes.get_gaussians`` (OmniRe/models/nodes/deformable.py:49-113, with
     ``get_deformation`` :35-47 and the ``ConditionalDeformNetwork`` of models/modules.py) run on the CPU ->
@@ -502,3 +528,6 @@ def make_deformable_golden():
 
 if __name__ == "__main__" and "--deformable" in sys.argv:
     make_deformable_golden()
+
+if __name__ == "__main__" and "--densify" in sys.argv:
+    make_densify_golden()

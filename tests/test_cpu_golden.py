@@ -249,3 +249,14 @@ def test_deformable_nodes_golden():
         if step > 3000:
             assert float(net["linear.0.weight"].grad.abs().max()) > 0 and float(c["instances_embedding"].grad.abs().max()) > 0
             assert (c["means"].grad is None) == bool(stop)     # stop_optimizing_canonical_xyz detaches the canonical means
+
+
+def test_densify_oracle_matches_reference_after_train():
+    """oracle.densify.after_train == VanillaGaussians.after_train (vanilla.py:163-191) over three successive steps."""
+    from oracle import densify as OD
+    z = np.load(os.path.join(G, "densify.npz"))
+    state = {}
+    for s_ in range(z["radii"].shape[0]):
+        OD.after_train(state, torch.from_numpy(z["radii"][s_]), torch.from_numpy(z["grads"][s_]), int(z["last_size"]))
+        for k in ("xys_grad_norm", "vis_counts", "max_2Dsize"):
+            assert torch.equal(state[k], torch.from_numpy(z[f"s{s_}_{k}"])), (s_, k)

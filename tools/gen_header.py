@@ -20,7 +20,7 @@ GROUPS = [
     ("K1d  S3Gaussian EMD deformation MLP", ["emd_linear_bwd_workspace_bytes", "emd_linear_fwd", "emd_linear_fwd_tc", "emd_linear_bwd", "emd_linear_bwd_tc", "emd_temb_fwd", "emd_temb_bwd"]),
     ("K1e  HexPlane feature gather (input of the S3Gaussian EMD MLP)", ["emd_hexplane_fwd", "emd_hexplane_bwd_workspace_bytes",
                                                                        "emd_hexplane_bwd"]),
-    ("Next (SURVEY 8f-2): fused Adam step", ["emd_adam_max_tensors", "emd_adam_step"]),
+    ("Next (SURVEY 8f-2): fused Adam step + densification statistics", ["emd_adam_max_tensors", "emd_adam_step", "emd_densify_stats"]),
     ("Next (SURVEY 8f-3): fused image losses between the rasterizer forward and backward",
      ["emd_image_loss_partials_floats", "emd_image_loss_fwd", "emd_image_loss_bwd"]),
     ("Next (SURVEY 8f-4): voxel LBS weights of the SMPL nodes (K1f)",
@@ -119,6 +119,10 @@ DOC = {
                      "emd_adam_max_tensors() fp32 tensors.  All arrays are HOST arrays [n_tensors]; params/grads/exp_avg/exp_avg_sq "
                      "hold DEVICE pointers; step[i] is the 1-based count after this update; grad_scale multiplies the gradients "
                      "(1/world_size after a sum all-reduce); L2 weight decay as in torch (g += wd * p).",
+    "emd_densify_stats": "BasicTrainer.postprocess_per_train_step + VanillaGaussians.after_train (OmniRe/models/trainers/base.py:279-297, "
+                         "OmniRe/models/gaussians/vanilla.py:163-191) for all Gaussian classes and the C cameras of a step in one "
+                         "launch: xys_grad_norm += |grad * (W/2, H/2)|, vis_counts += 1, max_2Dsize = max(., radius / last_size) "
+                         "where radius > 0; `first` reproduces the reference's first-call initialisation.",
     "emd_image_loss_partials_floats": "Floats of the `partials` scratch buffer of emd_image_loss_fwd.",
     "emd_image_loss_fwd": "Replaces the image terms of BasicTrainer.compute_losses (OmniRe/models/trainers/base.py:518-587: rgb L1, "
                           "pytorch_msssim SSIM, sky-opacity BCE / SafeBCE of models/losses.py:33-83, DepthLoss :91-172, opacity "
