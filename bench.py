@@ -215,22 +215,40 @@ def run_ours(args):
                     torch.set_num_threads(max(1, min(4, len(mine))))
             except OSError:
                 pass
-        dist.init_process_group("nccl", device_id=dev)
+        pg_opts = None
+        if os.environ.get("EMD_BENCH_NCCL_PRIORITY", "1") == "1":
+            # the collective's CTAs share the SMs with the backward's kernels: a high-priority stream lets them in first
+            try:
+                pg_opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            except Exception:  # noqa: BLE001
+                pg_opts = None
+        dist.init_process_group("nccl", device_id=dev, pg_options=pg_opts)
 
     (bg, rigid, smpl), host = build_inputs(args, rank, world)
     scene = P.StreetScene(bg, rigid, smpl, dev)
     params = scene.parameters()
     # gradient exchange: the background SH coefficients (2/3 of the bytes) go out from an autograd hook while the
     # backward pass is still running; everything else in one grouped launch at the end of the step
+    # early groups: SH coefficients.  Their gradients are complete right after the colour node's backward, i.e. before the
+    # projection / activation / EMD backward; group 1 = the background's higher-order coefficients (2/3 of all bytes),
+    # group 2 = every other SH tensor (background DC, the node classes' DC + rest)
+    sh_other = [scene.bg["features_dc"]] + [node.p[k] for node in scene._nodes() for k in ("_features_dc", "_features_rest")
+                                           if isinstance(node.p.get(k), torch.Tensor) and node.p[k].requires_grad]
     groups = {"rest": [[scene.bg["features_rest"]]],
-              "rest+dc": [[scene.bg["features_rest"]], [scene.bg["features_dc"]]]}
+              "rest+dc": [[scene.bg["features_rest"]], [scene.bg["features_dc"]]],
+              "sh": [[scene.bg["features_rest"]], sh_other]}
     early = groups[os.environ.get("EMD_BENCH_EARLY", "rest")]
-    ar_mode = os.environ.get("EMD_BENCH_ALLREDUCE", "hooks")   # experiments only: "finish" = no overlap, "none" = skip
-    # EMD_BENCH_DEFER=1 (experiment; measured SLOWER at 8 GPUs, profiles/r02k_*): the early groups' all-reduce is left in
-    # flight at the end of the step and completed where the NEXT step first needs those parameters (its SH colour
-    # evaluation, after projection / binning / sort have been issued)
+    # experiments only: "finish" = no overlap, "none" = skip, "sync" = a 4-byte all-reduce per step (rank skew alone)
+    ar_mode = os.environ.get("EMD_BENCH_ALLREDUCE", "hooks")
+    same_frames = os.environ.get("EMD_BENCH_SAME_FRAMES", "0") == "1"
+    sync_token = torch.zeros(1, device=dev)
+    # EMD_BENCH_DEFER=1 (experiment, measured NOT faster at 8 GPUs -- profiles/r02r_*, timeline profiles/r02t_*): the early
+    # group's all-reduce is left in flight at the end of the step and completed where the NEXT step first needs those
+    # parameters (its SH colour evaluation), the rest travels on a second communicator.  Under the profiler the two
+    # collectives then share the links and the SMs with the front end and each takes 1.3-1.9 ms instead of 0.95 + 0.56.
     defer = world > 1 and ar_mode == "hooks" and os.environ.get("EMD_BENCH_DEFER", "0") == "1"
-    reducer = D.GradReducer(params, early=early if ar_mode == "hooks" else None, defer_early=defer)
+    reducer = D.GradReducer(params, early=early if ar_mode == "hooks" else None, defer_early=defer,
+                            tail_group=dist.new_group() if defer else None)
     early_ids = {id(q) for grp in early for q in grp} if defer else set()
     early_params = [q for grp in early for q in grp] if defer else []
     late = {"opt": None}     # optimizer of the early parameters, run after their deferred exchange (with_optimizer leg)
@@ -270,7 +288,8 @@ def run_ours(args):
         prefetched[i] = (t, ev)
 
     def step(i, e2e: bool, last: bool = False):
-        frame = (7 + 13 * (i * world + rank)) % n_frames
+        # every rank renders its own timestep (EMD_BENCH_SAME_FRAMES=1, diagnostic: all ranks the same one -> no load skew)
+        frame = (7 + 13 * (i if same_frames else (i * world + rank))) % n_frames
         s = i % n_sets
         if e2e:  # host -> device copy of this step's inputs from pinned memory, inside the timed region
             c2w = host["c2w"].to(dev, non_blocking=True)
@@ -303,7 +322,9 @@ def run_ours(args):
                                            lidar_depth_map=sup[2])
             loss = terms.sum()
         loss.backward()
-        if world > 1 and ar_mode != "none":
+        if world > 1 and ar_mode == "sync":
+            dist.all_reduce(sync_token)
+        elif world > 1 and ar_mode != "none":
             stats["allreduce_early_bytes"] = reducer.early_bytes
             stats["allreduce_bytes"] = reducer.finish()
         if e2e:  # device -> host read of the step's result
@@ -387,6 +408,18 @@ def run_ours(args):
         step_opt(i, False)
     ms_opt, launches_opt, _, _ = timed(args.steps, False, args.warmup + 3 * args.steps, fn=step_opt)
 
+    if os.environ.get("EMD_BENCH_TRACE"):     # diagnostic: a kernel / collective timeline of three steps on every rank
+        from torch.profiler import ProfilerActivity, profile as tprofile
+        barrier()
+        with tprofile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as tp:
+            for i in range(3):
+                step(1000 + i, False)
+            if defer:
+                before_colors()
+            torch.cuda.synchronize()
+        if rank == 0:
+            tp.export_chrome_trace(os.environ["EMD_BENCH_TRACE"])
+        barrier()
     reducer.close()      # the measurement passes below run single-rank work: no gradient hooks
     pix = C * H_IMG * W_IMG
     ms_step = ms_dev / args.steps

@@ -100,7 +100,13 @@ __global__ void __launch_bounds__(PROJ_THREADS) projection_fwd_kernel(
     }
 }
 
-__global__ void __launch_bounds__(PROJ_THREADS) projection_bwd_kernel(
+constexpr int PROJ_BWD_CAMS = 8;   // camera constants kept in shared memory per pass over the cameras
+
+// One thread per Gaussian.  The per-camera constants of up to 8 cameras are built by 8 threads at once (not by thread 0
+// camera after camera), and the camera loop holds no barrier: the cotangents of a (camera, Gaussian) pair are read
+// straight from global memory (consecutive threads read consecutive 8 / 12-byte items, every line is consumed whole by
+// the warp), so the loads of the next camera can be in flight under the arithmetic of the current one.
+__global__ void __launch_bounds__(PROJ_THREADS, 3) projection_bwd_kernel(
     const float* __restrict__ means, const float* __restrict__ quats, const float* __restrict__ scales,
     const float* __restrict__ viewmats, const float* __restrict__ Ks, int64_t N, int C, int width, int height,
     float eps2d, float near_plane, float far_plane, float radius_clip, const int32_t* __restrict__ radii,
@@ -108,12 +114,14 @@ __global__ void __launch_bounds__(PROJ_THREADS) projection_bwd_kernel(
     float* __restrict__ v_means, float* __restrict__ v_quats, float* __restrict__ v_scales) {
     __shared__ __align__(16) float s_a[PROJ_THREADS * 3];
     __shared__ __align__(16) float s_b[PROJ_THREADS * 3];
-    __shared__ CamConst s_cam;
+    __shared__ CamConst s_cam[PROJ_BWD_CAMS];
 
     const int64_t base = (int64_t)blockIdx.x * PROJ_THREADS;
     const int64_t i = base + threadIdx.x;
     stage_vec3(means, base, N, s_a);
     stage_vec3(scales, base, N, s_b);
+    if (threadIdx.x < min(C, PROJ_BWD_CAMS))
+        make_cam_const(viewmats + threadIdx.x * 16, Ks + threadIdx.x * 9, width, height, s_cam[threadIdx.x]);
     __syncthreads();
     const bool live = i < N;
     float R[9], M[9], S[6], qn[4], m[3], s[3];
@@ -128,23 +136,26 @@ __global__ void __launch_bounds__(PROJ_THREADS) projection_bwd_kernel(
     float v_mean[3] = {0.f, 0.f, 0.f};
     float v_S[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     bool any = false;
-    for (int c = 0; c < C; ++c) {
-        __syncthreads();
-        if (threadIdx.x == 0) make_cam_const(viewmats + c * 16, Ks + c * 9, width, height, s_cam);
-        // stage v_conics [C,N,3] slice of this block
-        stage_vec3(v_conics + (int64_t)c * N * 3, base, N, s_a);
-        __syncthreads();
+    for (int c0 = 0; c0 < C; c0 += PROJ_BWD_CAMS) {
+        if (c0 > 0) {   // more than 8 cameras: next group of constants
+            __syncthreads();
+            if (threadIdx.x < min(C - c0, PROJ_BWD_CAMS))
+                make_cam_const(viewmats + (c0 + threadIdx.x) * 16, Ks + (c0 + threadIdx.x) * 9, width, height, s_cam[threadIdx.x]);
+            __syncthreads();
+        }
         if (!live) continue;
-        const int64_t ci = (int64_t)c * N + i;
-        if (radii[ci] <= 0) continue;
-        ProjFwd o;
-        project_gaussian_c(m, S, s_cam, width, height, eps2d, near_plane, far_plane, radius_clip, o);
-        if (o.radius <= 0) continue;  // cannot happen: same arithmetic as forward
-        const float2 vm = __ldg(reinterpret_cast<const float2*>(v_means2d) + ci);
-        const float vz = v_depths ? __ldg(v_depths + ci) : 0.0f;
-        project_gaussian_vjp(o, s_cam, vm.x, vm.y, vz, s_a[threadIdx.x * 3 + 0], s_a[threadIdx.x * 3 + 1],
-                             s_a[threadIdx.x * 3 + 2], v_mean, v_S);
-        any = true;
+        for (int c = c0; c < min(C, c0 + PROJ_BWD_CAMS); ++c) {
+            const int64_t ci = (int64_t)c * N + i;
+            if (radii[ci] <= 0) continue;
+            const float2 vm = __ldg(reinterpret_cast<const float2*>(v_means2d) + ci);
+            const float vz = v_depths ? __ldg(v_depths + ci) : 0.0f;
+            const float vca = __ldg(v_conics + ci * 3 + 0), vcb = __ldg(v_conics + ci * 3 + 1), vcc = __ldg(v_conics + ci * 3 + 2);
+            ProjFwd o;
+            project_gaussian_c(m, S, s_cam[c - c0], width, height, eps2d, near_plane, far_plane, radius_clip, o);
+            if (o.radius <= 0) continue;  // cannot happen: same arithmetic as forward
+            project_gaussian_vjp(o, s_cam[c - c0], vm.x, vm.y, vz, vca, vcb, vcc, v_mean, v_S);
+            any = true;
+        }
     }
     float v_q[4] = {0.f, 0.f, 0.f, 0.f}, v_s[3] = {0.f, 0.f, 0.f};
     if (live && any) covar_world_vjp(qn, inv_norm, R, M, s, v_S, v_q, v_s);

@@ -85,15 +85,15 @@ def allreduce_grads(params: Iterable[Tensor], average: bool = False, bucket_byte
     return total
 
 
-def _allreduce_group_async(tensors: List[Tensor]):
+def _allreduce_group_async(tensors: List[Tensor], group=None):
     """One asynchronous all-reduce over several tensors: a single grouped NCCL launch (``ncclGroupStart/End``
     around one ``ncclAllReduce`` per tensor -- no packing copies), gloo's coalesced all-reduce in the CPU tests."""
     if len(tensors) == 1:
-        return dist.all_reduce(tensors[0], async_op=True)
+        return dist.all_reduce(tensors[0], async_op=True, group=group)
     from torch.distributed.distributed_c10d import _coalescing_manager
-    with _coalescing_manager(async_ops=True) as cm:
+    with _coalescing_manager(group=group, async_ops=True) as cm:
         for t in tensors:
-            dist.all_reduce(t)
+            dist.all_reduce(t, group=group)
     return cm
 
 
@@ -116,18 +116,24 @@ class GradReducer:
     long as the early parameters are used by every rank's step; that is the contract of ``early``."""
 
     def __init__(self, params: Sequence[Tensor], early: Optional[Sequence[Sequence[Tensor]]] = None,
-                 average: bool = False, pack_below: int = 4 << 20, drop_unused: bool = False, defer_early: bool = False):
+                 average: bool = False, pack_below: int = 4 << 20, drop_unused: bool = False, defer_early: bool = False,
+                 tail_group=None):
         """``drop_unused``: exchange one flag per parameter so that a parameter no rank used keeps ``grad None`` (costs a
         host read of the flags per step; off, such a parameter gets a zero gradient).
         ``defer_early``: ``finish()`` returns without waiting for the EARLY groups' all-reduces; ``wait_deferred()``
         completes them.  The early groups are the SH coefficients, which the next step only reads after its projection
         and tile binning, so their exchange (and their optimizer update, which the caller runs after
-        ``wait_deferred()``) hides behind the next step's front end."""
+        ``wait_deferred()``) hides behind the next step's front end.
+        ``tail_group``: a second process group (``dist.new_group()``: its own communicator and stream) for what
+        ``finish()`` reduces.  Collectives of one communicator run in issue order, so on the default group the tail would
+        queue behind the early groups' all-reduce and waiting for the tail would wait for both -- with ``defer_early`` the
+        tail needs its own communicator for the deferral to hide anything."""
         self.params = list(params)
         self.average = average
         self.pack_below = pack_below
         self.drop_unused = drop_unused
         self.defer_early = defer_early
+        self.tail_group = tail_group
         self._deferred: List = []
         self._early_works: List = []
         self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
@@ -146,7 +152,10 @@ class GradReducer:
                     self._handles.append(p.register_post_accumulate_grad_hook(self._hook))
 
     def _launch(self, tensors: List[Tensor], early: bool = False) -> int:
-        (self._early_works if early else self._works).append(_allreduce_group_async(tensors))
+        if early:
+            self._early_works.append(_allreduce_group_async(tensors))
+        else:
+            self._works.append(_allreduce_group_async(tensors, group=self.tail_group))
         n = sum(t.numel() * t.element_size() for t in tensors)
         self.bytes += n
         return n

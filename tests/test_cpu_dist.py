@@ -71,7 +71,7 @@ def _worker(rank, world, port, ret):
             assert torch.equal(skip.grad, torch.full_like(skip, 3.0))
         red.close()
         # deferred early groups: finish() leaves their all-reduce in flight, wait_deferred() completes it (and averages)
-        red2 = D.GradReducer(ps, early=[[big]], average=True, defer_early=True)
+        red2 = D.GradReducer(ps, early=[[big]], average=True, defer_early=True, tail_group=dist.new_group())
         for it in range(2):
             red2.wait_deferred()           # start of a step: nothing may still be in flight when grads are reset
             for q in ps:
