@@ -19,6 +19,7 @@ Prints ONE JSON line (see DESIGN.md section 7 for every field).
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import math
 import os
@@ -67,24 +68,66 @@ def workload_cfg(args):
 
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock / power / throttle reasons sampled WHILE the timed region runs.
+
+    In-process NVML (nvidia_ml_py) on a background thread, one light query set every 20 ms: an `nvidia-smi -lms` child
+    polling the full field list was measured to stall kernel launches for milliseconds whenever a poll landed inside the
+    76 ms timed region (the device-resident leg varied 3.79 - 4.66 ms between back-to-back runs with it, the unsampled
+    legs did not).  Falls back to the nvidia-smi line of B200_PROFILING.md when the bindings are missing."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.samples = index, None, [], []
+        self._stop = threading.Event()
+        self.mode = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [int(x) for x in vis.split(",")] if vis and all(x.strip().isdigit() for x in vis.split(",")) else None
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(ids[self.index] if ids and self.index < len(ids) else self.index)
+            self.nv = pynvml
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.mode = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            self.proc = True
+            return
+        except Exception:  # noqa: BLE001
+            self.mode = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
+            self.mode = "nvidia-smi"
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:  # noqa: BLE001
             self.proc = None
+
+    def _poll_nvml(self):
+        nv = self.nv
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))
+        bits = [(n, getattr(nv, a, None) or getattr(nv, b, 0)) for n, a, b in names]
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.samples.append((time.perf_counter(), sm, pw, [n for n, bit in bits if bit and (mask & bit)]))
+                self.lines.append(1)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.02)
 
     def _pump(self):
         for ln in self.proc.stdout:
@@ -92,7 +135,16 @@ class ClockSampler:
 
     def stop(self, t0, t1):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock sampler available"]}
+        if self.mode == "nvml":
+            time.sleep(0.03)
+            self._stop.set()
+            inside = [x for x in self.samples if t0 - 0.02 <= x[0] <= t1 + 0.02]
+            if not inside:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed region"]}
+            sm = sorted(x[1] for x in inside)
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.smax, "power_w_max": round(max(x[2] for x in inside), 2),
+                    "samples": len(inside), "reasons": sorted({r for x in inside for r in x[3]}), "source": "nvml, 20 ms period"}
         time.sleep(0.15)
         self.proc.terminate()
         sm, smax, reasons, pw = [], [], set(), []
@@ -111,7 +163,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed region"]}
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -340,6 +392,16 @@ def run_ours(args):
 
     def timed(k_steps, e2e, first_index, fn=None):
         fn = fn or step
+        # Python's cyclic collector would otherwise pick an arbitrary step for a full pass over the heap (tens of
+        # thousands of live objects: several milliseconds during which no kernel is launched)
+        gc.collect()
+        gc.disable()
+        try:
+            return _timed(k_steps, e2e, first_index, fn)
+        finally:
+            gc.enable()
+
+    def _timed(k_steps, e2e, first_index, fn):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _C.launch_count()
@@ -361,24 +423,30 @@ def run_ours(args):
             ms = float(t.item())
         return ms, _C.launch_count() - l0, t0, t1
 
+    # the clock sampler (an nvidia-smi process polling every 100 ms) starts BEFORE the warm-up: its start-up -- NVML
+    # initialisation, device enumeration -- can stall the driver for tens of milliseconds, which must not land inside
+    # the timed region; once it is polling it stays on through the timed steps
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         step(i, False)
     # the W warm-up steps above are the contract's; the caching allocator may still be growing its pools (the per-step
     # buffer sizes follow the frame's intersection count): keep stepping, untimed, until a step reserves no new memory
-    extra_warm = 0
+    # (and the sampler has delivered its first line)
+    extra_warm, quiet = 0, 0
     while extra_warm < 24:
         before = torch.cuda.memory_reserved(dev)
         step(args.warmup + extra_warm, False)
         extra_warm += 1
-        grew = torch.tensor([float(torch.cuda.memory_reserved(dev) > before)], device=dev)
+        torch.cuda.synchronize()
+        busy = float(torch.cuda.memory_reserved(dev) > before) + float(rank == 0 and sampler.proc is not None and not sampler.lines)
+        grew = torch.tensor([busy], device=dev)
         if world > 1:
             dist.all_reduce(grew, op=dist.ReduceOp.MAX)
-        if extra_warm >= 3 and not bool(grew.item()):
+        quiet = 0 if bool(grew.item()) else quiet + 1
+        if extra_warm >= 3 and quiet >= 3:        # three steps in a row without a new reservation
             break
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
     ms_dev, launches, t0, t1 = timed(args.steps, False, args.warmup + extra_warm)
     host_wait = stats["host_wait_ms_per_step"]
     clocks = sampler.stop(t0, t1) if rank == 0 else None

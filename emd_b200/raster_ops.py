@@ -33,6 +33,27 @@ def _pinned_i64(device) -> Tensor:
     return _pinned[key]
 
 
+_pinned_ring = {}
+
+
+def _pinned_i32_slot(device) -> Tensor:
+    """One of 16 pinned int32 slots per device, handed out round-robin (a forward's entry count is read by its own
+    backward, at most a few steps later): no pinned allocation inside the step."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ring = _pinned_ring.get(key)
+    if ring is None:
+        ring = _pinned_ring[key] = [torch.zeros(16, dtype=torch.int32).pin_memory(), 0]
+    ring[1] = (ring[1] + 1) % 16
+    return ring[0][ring[1]:ring[1] + 1]
+
+
+def _bucket(n: int, quantum: int) -> int:
+    """Sizes of the big per-step buffers follow the frame's intersection count; rounding them up to a coarse quantum
+    keeps the number of distinct sizes the caching allocator sees small, so blocks are reused instead of re-allocated
+    (a fresh cudaMalloc / segment mapping in the middle of a step stalls it for milliseconds)."""
+    return (max(int(n), 1) + quantum - 1) // quantum * quantum
+
+
 def _f32c(t: Tensor) -> Tensor:
     if t.dtype != torch.float32:
         t = t.float()
@@ -158,8 +179,8 @@ def radix_sort_pairs(keys: Tensor, vals: Tensor, begin_bit: int, end_bit: int) -
         return keys, vals
     keys = keys.contiguous()
     vals = vals.contiguous()
-    k1 = torch.empty_like(keys)
-    v1 = torch.empty_like(vals)
+    k1 = torch.empty(_bucket(n, 1 << 19), dtype=keys.dtype, device=keys.device)[:n]
+    v1 = torch.empty(_bucket(n, 1 << 19), dtype=vals.dtype, device=vals.device)[:n]
     ws_bytes = L.emd_radix_sort_workspace_bytes(n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
     which = ctypes.c_int(0)
@@ -179,8 +200,8 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss:
     tw, th, bits = tile_grid(width, height)
     cum, P = cumsum_tiles(tiles_per_gauss, between, grad_enabled)
     dev = radii.device
-    isect_ids = torch.empty(P, dtype=torch.int64, device=dev)
-    flatten_ids = torch.empty(P, dtype=torch.int32, device=dev)
+    isect_ids = torch.empty(_bucket(P, 1 << 19), dtype=torch.int64, device=dev)[:P]
+    flatten_ids = torch.empty(_bucket(P, 1 << 19), dtype=torch.int32, device=dev)[:P]
     if P > 0:
         _C.check(L.emd_isect_emit(_C.ptr(means2d.contiguous(), torch.float32), _C.ptr(radii, torch.int32),
                                   _C.ptr(depths.contiguous(), torch.float32), _C.ptr(cum), N, C, tw, th, bits,
@@ -229,9 +250,9 @@ class _Rasterize(torch.autograd.Function):
                                    _C.ptr(depths_c), 1 if with_depth else 0, _C.ptr(radii, torch.int32), N, C,
                                    _C.ptr(recs), _C.stream()), "emd_raster_pack")
         # the depth-sorted, per-tile-contiguous record stream both compositing kernels read with bulk copies
-        srecs = torch.empty(max(P, 1) * 3, 4, dtype=torch.float32, device=dev)
+        srecs = torch.empty(_bucket(P, 1 << 19) * 3, 4, dtype=torch.float32, device=dev)
         want_bwd = any(ctx.needs_input_grad[:6])
-        cand = torch.empty(max(P, 1), dtype=torch.uint8, device=dev) if want_bwd else None
+        cand = torch.empty(_bucket(P, 1 << 19), dtype=torch.uint8, device=dev) if want_bwd else None
         _C.check(L.emd_raster_sort_records(_C.ptr(recs), _C.ptr(isect_ids, torch.int64), _C.ptr(flatten_ids, torch.int32),
                                            _C.ptr(radii, torch.int32), _C.ptr(cum_tiles, torch.int64), P, tw, th, tile_bits,
                                            int(flavour), _C.ptr(srecs), _C.ptr(cand), _C.stream()), "emd_raster_sort_records")
@@ -241,13 +262,13 @@ class _Rasterize(torch.autograd.Function):
             # gradient entries of the backward: one per (pair, 8x4 pixel block its alpha box reaches); entry_base[slot] =
             # first entry of the pair, entry_base[P] = their number -- read back asynchronously (the backward, which
             # sizes its workspace with it, runs long after the copy has landed: no stall)
-            entry_base = torch.empty(P + 1, dtype=torch.int32, device=dev)
+            entry_base = torch.empty(_bucket(P + 1, 1 << 19), dtype=torch.int32, device=dev)
             ws_bytes = L.emd_scan_workspace_bytes(P)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             _C.check(L.emd_exclusive_scan_u8_u32(_C.ptr(cand), _C.ptr(entry_base), P, entry_base.data_ptr() + 4 * P,
                                                  _C.ptr(ws), ws_bytes, _C.stream()), "emd_exclusive_scan_u8_u32")
-            n_entries_host = torch.empty(1, dtype=torch.int32).pin_memory()
-            n_entries_host.copy_(entry_base[P:], non_blocking=True)
+            n_entries_host = _pinned_i32_slot(dev)
+            n_entries_host.copy_(entry_base[P:P + 1], non_blocking=True)
             n_entries_ev = torch.cuda.Event()
             n_entries_ev.record()
             del ws, cand
@@ -304,7 +325,7 @@ class _Rasterize(torch.autograd.Function):
         n_entries_host, n_entries_ev = ctx.n_entries
         n_entries_ev.synchronize()
         n_entries = int(n_entries_host.item())
-        ws_bytes = L.emd_rasterize_bwd_workspace_bytes(n_entries)
+        ws_bytes = _bucket(L.emd_rasterize_bwd_workspace_bytes(n_entries), 32 << 20)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _C.check(L.emd_rasterize_bwd(
             _C.ptr(srecs), _C.ptr(isect_offsets), _C.ptr(cta_map), _C.ptr(cum_tiles), _C.ptr(entry_base), n_entries, P, N, C,
