@@ -15,7 +15,8 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libemd_b200.so"
-HOSTLIB = PKG / "libemd_b200_hostmath.so"
+HOSTMATH_SRC = PKG.parent / "tests" / "hostmath" / "hostmath.cpp"      # test scaffolding, not product source
+HOSTLIB = PKG.parent / "tests" / "hostmath" / "libemd_b200_hostmath.so"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -76,15 +77,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 def build_hostmath(force: bool = False) -> Path:
-    """Host-only compile of the projection math header (``-ffp-contract=off``) so the
+    """Host-only compile of the kernels' math headers (``-ffp-contract=off``; source under ``tests/hostmath/``) so the
     CPU test-suite can check the product's canonical op order against the oracle
-    without a GPU.  Not used by the product path."""
-    src = PKG / "csrc" / "hostmath.cpp"
+    without a GPU.  Test scaffolding: not used, and not loaded, by the product path."""
+    src = HOSTMATH_SRC
     deps = [src] + list(CSRC.glob("*.cuh"))
     if not force and not _stale(HOSTLIB, deps):
         return HOSTLIB
     cmd = ["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC", "-shared", "-x", "c++",
-           str(src), "-o", str(HOSTLIB)]
+           f"-I{CSRC}", str(src), "-o", str(HOSTLIB)]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"g++ failed on hostmath:\n{r.stdout}")
