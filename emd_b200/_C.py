@@ -52,6 +52,13 @@ _SIGS = {
     "emd_temb_bwd": (c_int, [P, c_int, c_int, P, c_int, P, P, P, P]),
     "emd_hexplane_fwd": (c_int, [P, ctypes.POINTER(c_int64), ctypes.POINTER(c_int), c_int, c_int, ctypes.POINTER(c_float),
                                  P, P, c_int, c_int64, P, P]),
+    "emd_hexplane_fwd_ld": (c_int, [P, ctypes.POINTER(c_int64), ctypes.POINTER(c_int), c_int, c_int, ctypes.POINTER(c_float),
+                                    P, P, c_int, c_int64, P, c_int64, P]),
+    "emd_hexplane_bwd_ld": (c_int, [P, ctypes.POINTER(c_int64), ctypes.POINTER(c_int), c_int, c_int, ctypes.POINTER(c_float),
+                                    P, P, c_int, c_int64, P, c_int64, P, P, P, P, c_size_t, P]),
+    "emd_s3g_apply_blocks": (c_int64, [c_int64]),
+    "emd_s3g_apply_fwd": (c_int, [P] * 10 + [c_int64] + [P] * 4 + [P]),
+    "emd_s3g_apply_bwd": (c_int, [P] * 10 + [c_int64] + [P] * 8 + [P]),
     "emd_hexplane_bwd_workspace_bytes": (c_size_t, [c_int64]),
     "emd_hexplane_bwd": (c_int, [P, ctypes.POINTER(c_int64), ctypes.POINTER(c_int), c_int, c_int, ctypes.POINTER(c_float),
                                  P, P, c_int, c_int64, P, P, P, P, P, c_size_t, P]),

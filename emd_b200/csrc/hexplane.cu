@@ -48,13 +48,13 @@ __device__ __forceinline__ void hex_coords(const HexParams& P, const float* __re
 
 __global__ void __launch_bounds__(HEX_THREADS) hexplane_fwd_kernel(const HexParams P, const float* __restrict__ pts,
                                                                    const float* __restrict__ t, int t_stride, int64_t N,
-                                                                   float* __restrict__ feat) {
+                                                                   float* __restrict__ feat, int64_t ld) {
     const int64_t n = (int64_t)blockIdx.x * HEX_GPB + (threadIdx.x / HEX_LPG);
     const int q = threadIdx.x % HEX_LPG;
     if (n >= N) return;
     float u[4];
     hex_coords(P, pts, t, t_stride, n, u);
-    float4* out = reinterpret_cast<float4*>(feat + n * (int64_t)(P.S * HEX_F)) + q;
+    float4* out = reinterpret_cast<float4*>(feat + n * ld) + q;
     for (int s = 0; s < P.S; ++s) {
         HexAxis ax[4];
 #pragma unroll
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(HEX_THREADS) hexplane_fwd_kernel(const HexPara
 
 __global__ void __launch_bounds__(HEX_THREADS, 2) hexplane_bwd_kernel(const HexParams P, const float* __restrict__ pts,
                                                                    const float* __restrict__ t, int t_stride, int64_t N,
-                                                                   const float* __restrict__ v_feat, float* v_planes,
+                                                                   const float* __restrict__ v_feat, int64_t ld, float* v_planes,
                                                                    float* __restrict__ v_pts, float* __restrict__ v_t,
                                                                    float* __restrict__ t_partial) {
     __shared__ float s_t[HEX_THREADS / 32];
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(HEX_THREADS, 2) hexplane_bwd_kernel(const HexP
     if (n < N) {
         float u[4];
         hex_coords(P, pts, t, t_stride, n, u);
-        const float4* vf = reinterpret_cast<const float4*>(v_feat + n * (int64_t)(P.S * HEX_F)) + q;
+        const float4* vf = reinterpret_cast<const float4*>(v_feat + n * ld) + q;
         for (int s = 0; s < P.S; ++s) {
             HexAxis ax[4];
 #pragma unroll
@@ -223,13 +223,18 @@ static int hex_fill_params(HexParams& P, const char* fn, const float* planes, co
 // feat[N, S*F] = HexPlaneField(pts, t).  planes: flat device buffer, plane (s, p) feature-last [H][W][F] at float
 // offset plane_offsets[s*6+p] (HOST array), H = reso[s*4 + j], W = reso[s*4 + i] for the coordinate pair (i, j) of p
 // (HOST array reso[S*4]); aabb: HOST float[6] = {aabb[0], aabb[1]}; t: DEVICE, one value (t_stride 0) or N (t_stride 1).
-extern "C" int emd_hexplane_fwd(const float* planes, const int64_t* plane_offsets, const int* reso, int S, int F,
-                                const float* aabb, const float* pts, const float* t, int t_stride, int64_t N, float* feat,
-                                cudaStream_t stream) {
+// emd_hexplane_fwd_ld: the same with a row pitch -- row n of the features starts at feat + n * ld floats (ld >= S*F, a
+// multiple of 4), so the gather can write straight into the left columns of the deformation MLP's input [N, S*F + E]
+// (deformation.py:205 concatenates the per-Gaussian embedding behind the features) without a concatenation pass.
+extern "C" int emd_hexplane_fwd_ld(const float* planes, const int64_t* plane_offsets, const int* reso, int S, int F,
+                                   const float* aabb, const float* pts, const float* t, int t_stride, int64_t N, float* feat,
+                                   int64_t ld, cudaStream_t stream) {
     HexParams P;
     int rc = hex_fill_params(P, "emd_hexplane_fwd", planes, plane_offsets, reso, S, F, aabb);
     if (rc != EMD_OK) return rc;
     EMD_CHECK_ARG(N >= 0 && (t_stride == 0 || t_stride == 1), "emd_hexplane_fwd: N=%lld t_stride=%d", (long long)N, t_stride);
+    EMD_CHECK_ARG(ld >= (int64_t)S * F && ld % 4 == 0, "emd_hexplane_fwd: row pitch %lld (need >= %d and a multiple of 4)",
+                  (long long)ld, S * F);
     if (N == 0) return EMD_OK;
     EMD_CHECK_ARG(pts && t && feat, "emd_hexplane_fwd: null argument");
     if (!emd_aligned(feat, 16)) {
@@ -237,23 +242,32 @@ extern "C" int emd_hexplane_fwd(const float* planes, const int64_t* plane_offset
         return EMD_ERR_ALIGN;
     }
     const unsigned grid = (unsigned)emd_cdiv(N, HEX_GPB);
-    EMD_LAUNCH(EK_HEX_FWD, stream, (hexplane_fwd_kernel<<<grid, HEX_THREADS, 0, stream>>>(P, pts, t, t_stride, N, feat)));
+    EMD_LAUNCH(EK_HEX_FWD, stream, (hexplane_fwd_kernel<<<grid, HEX_THREADS, 0, stream>>>(P, pts, t, t_stride, N, feat, ld)));
     EMD_CHECK_LAUNCH("emd_hexplane_fwd");
     return EMD_OK;
+}
+
+extern "C" int emd_hexplane_fwd(const float* planes, const int64_t* plane_offsets, const int* reso, int S, int F,
+                                const float* aabb, const float* pts, const float* t, int t_stride, int64_t N, float* feat,
+                                cudaStream_t stream) {
+    return emd_hexplane_fwd_ld(planes, plane_offsets, reso, S, F, aabb, pts, t, t_stride, N, feat, (int64_t)S * F, stream);
 }
 
 extern "C" size_t emd_hexplane_bwd_workspace_bytes(int64_t N) { return (size_t)(emd_cdiv(N > 0 ? N : 1, HEX_GPB)) * sizeof(float); }
 
 // VJP of emd_hexplane_fwd.  v_planes (same layout as planes) is ADDED into: the caller zero-fills it once per step.
 // v_pts[N,3] may be NULL.  v_t: N values written (t_stride 1) or one value ADDED into (t_stride 0); may be NULL.
-extern "C" int emd_hexplane_bwd(const float* planes, const int64_t* plane_offsets, const int* reso, int S, int F,
-                                const float* aabb, const float* pts, const float* t, int t_stride, int64_t N,
-                                const float* v_feat, float* v_planes, float* v_pts, float* v_t, void* workspace,
-                                size_t workspace_bytes, cudaStream_t stream) {
+// emd_hexplane_bwd_ld: v_feat with a row pitch of ld floats (see emd_hexplane_fwd_ld).
+extern "C" int emd_hexplane_bwd_ld(const float* planes, const int64_t* plane_offsets, const int* reso, int S, int F,
+                                   const float* aabb, const float* pts, const float* t, int t_stride, int64_t N,
+                                   const float* v_feat, int64_t ld, float* v_planes, float* v_pts, float* v_t,
+                                   void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     HexParams P;
     int rc = hex_fill_params(P, "emd_hexplane_bwd", planes, plane_offsets, reso, S, F, aabb);
     if (rc != EMD_OK) return rc;
     EMD_CHECK_ARG(N >= 0 && (t_stride == 0 || t_stride == 1), "emd_hexplane_bwd: N=%lld t_stride=%d", (long long)N, t_stride);
+    EMD_CHECK_ARG(ld >= (int64_t)S * F && ld % 4 == 0, "emd_hexplane_bwd: row pitch %lld (need >= %d and a multiple of 4)",
+                  (long long)ld, S * F);
     if (N == 0) return EMD_OK;
     EMD_CHECK_ARG(pts && t && v_feat && v_planes, "emd_hexplane_bwd: null argument");
     if (!emd_aligned(v_feat, 16) || !emd_aligned(v_planes, 16)) {
@@ -270,11 +284,19 @@ extern "C" int emd_hexplane_bwd(const float* planes, const int64_t* plane_offset
         partial = static_cast<float*>(workspace);
     }
     EMD_LAUNCH(EK_HEX_BWD, stream,
-               (hexplane_bwd_kernel<<<grid, HEX_THREADS, 0, stream>>>(P, pts, t, t_stride, N, v_feat, v_planes, v_pts, v_t, partial)));
+               (hexplane_bwd_kernel<<<grid, HEX_THREADS, 0, stream>>>(P, pts, t, t_stride, N, v_feat, ld, v_planes, v_pts, v_t, partial)));
     EMD_CHECK_LAUNCH("emd_hexplane_bwd");
     if (partial) {
         EMD_LAUNCH(EK_MISC, stream, (hexplane_tsum_kernel<<<1, 256, 0, stream>>>(partial, (int64_t)grid, v_t)));
         EMD_CHECK_LAUNCH("emd_hexplane_bwd(tsum)");
     }
     return EMD_OK;
+}
+
+extern "C" int emd_hexplane_bwd(const float* planes, const int64_t* plane_offsets, const int* reso, int S, int F,
+                                const float* aabb, const float* pts, const float* t, int t_stride, int64_t N,
+                                const float* v_feat, float* v_planes, float* v_pts, float* v_t, void* workspace,
+                                size_t workspace_bytes, cudaStream_t stream) {
+    return emd_hexplane_bwd_ld(planes, plane_offsets, reso, S, F, aabb, pts, t, t_stride, N, v_feat, (int64_t)S * F, v_planes,
+                               v_pts, v_t, workspace, workspace_bytes, stream);
 }

@@ -24,7 +24,9 @@ COMBS = list(itertools.combinations(range(4), 2))
 
 class _HexPlaneFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, planes, pts, t, field):
+    def forward(ctx, planes, pts, t, field, tail=None):
+        """``tail[N,E]`` (optional): the result is ``[features | tail]`` of shape [N, S*F+E], the gather writing its columns
+        in place (row pitch S*F+E) -- the MLP input of deformation.py:205 without a concatenation pass."""
         L = _C.lib()
         planes_c = planes.detach().float().contiguous()
         pts_c = pts.detach().float().contiguous()
@@ -34,13 +36,19 @@ class _HexPlaneFn(torch.autograd.Function):
         if t_stride == 1 and t_c.numel() != N:
             raise ValueError(f"timestamps has {t_c.numel()} values for {N} points")
         S, F = field.num_scales, field.feat_per_plane
-        feat = torch.empty(N, S * F, dtype=torch.float32, device=pts_c.device)
+        E = 0 if tail is None else int(tail.shape[1])
+        if tail is not None and (tail.shape[0] != N or (S * F + E) % 4 != 0):
+            raise ValueError(f"tail must be [N, E] with S*F+E a multiple of 4, got {tuple(tail.shape)} for N={N}, S*F={S * F}")
+        ld = S * F + E
+        feat = torch.empty(N, ld, dtype=torch.float32, device=pts_c.device)
         aabb = field._aabb_host()
-        _C.check(L.emd_hexplane_fwd(_C.ptr(planes_c, torch.float32, "planes"), field._offsets_c, field._reso_c, S, F, aabb,
-                                    _C.ptr(pts_c, torch.float32, "pts"), _C.ptr(t_c, torch.float32, "timestamps"), t_stride,
-                                    N, _C.ptr(feat), _C.stream()), "emd_hexplane_fwd")
+        _C.check(L.emd_hexplane_fwd_ld(_C.ptr(planes_c, torch.float32, "planes"), field._offsets_c, field._reso_c, S, F, aabb,
+                                       _C.ptr(pts_c, torch.float32, "pts"), _C.ptr(t_c, torch.float32, "timestamps"), t_stride,
+                                       N, _C.ptr(feat), ld, _C.stream()), "emd_hexplane_fwd")
+        if E:
+            feat[:, S * F:] = tail.detach()
         ctx.save_for_backward(planes_c, pts_c, t_c)
-        ctx.field, ctx.aabb, ctx.t_stride, ctx.t_shape = field, aabb, t_stride, t.shape
+        ctx.field, ctx.aabb, ctx.t_stride, ctx.t_shape, ctx.ld = field, aabb, t_stride, t.shape, ld
         return feat
 
     @staticmethod
@@ -60,10 +68,11 @@ class _HexPlaneFn(torch.autograd.Function):
                 torch.empty(N, dtype=torch.float32, device=dev)
         ws_bytes = L.emd_hexplane_bwd_workspace_bytes(N)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _C.check(L.emd_hexplane_bwd(_C.ptr(planes_c), field._offsets_c, field._reso_c, S, F, ctx.aabb, _C.ptr(pts_c),
-                                    _C.ptr(t_c), ctx.t_stride, N, _C.ptr(v_feat), _C.ptr(v_planes), _C.ptr(v_pts), _C.ptr(v_t),
-                                    _C.ptr(ws), ws_bytes, _C.stream()), "emd_hexplane_bwd")
-        return v_planes, v_pts, (v_t.reshape(ctx.t_shape) if v_t is not None else None), None
+        _C.check(L.emd_hexplane_bwd_ld(_C.ptr(planes_c), field._offsets_c, field._reso_c, S, F, ctx.aabb, _C.ptr(pts_c),
+                                       _C.ptr(t_c), ctx.t_stride, N, _C.ptr(v_feat), ctx.ld, _C.ptr(v_planes), _C.ptr(v_pts),
+                                       _C.ptr(v_t), _C.ptr(ws), ws_bytes, _C.stream()), "emd_hexplane_bwd")
+        v_tail = v_feat[:, S * F:] if (ctx.ld > S * F and ctx.needs_input_grad[4]) else None
+        return v_planes, v_pts, (v_t.reshape(ctx.t_shape) if v_t is not None else None), None, v_tail
 
 
 class HexPlaneField(nn.Module):
@@ -154,13 +163,16 @@ class HexPlaneField(nn.Module):
             self._aabb_c, self._aabb_key = (_C.c_float * 6)(*vals), key
         return self._aabb_c
 
-    def get_density(self, pts: Tensor, timestamps: Optional[Tensor] = None) -> Tensor:
+    def get_density(self, pts: Tensor, timestamps: Optional[Tensor] = None, tail: Optional[Tensor] = None) -> Tensor:
+        """``tail[N,E]``: return ``cat([features, tail], -1)`` built in place (see ``_HexPlaneFn.forward``)."""
         if timestamps is None:
             raise ValueError("HexPlaneField needs timestamps (input_coordinate_dim = 4)")
         pts = pts.reshape(-1, pts.shape[-1])
         if timestamps.dim() >= 1 and timestamps.numel() > 1 and timestamps.stride(0) == 0:
             timestamps = timestamps.reshape(-1)[:1]                   # an expanded scalar: one shared time
-        return _HexPlaneFn.apply(self.planes, pts, timestamps, self)
+        if tail is not None and (self.feat_dim + tail.shape[-1]) % 4 != 0:
+            return torch.cat([_HexPlaneFn.apply(self.planes, pts, timestamps, self), tail], dim=-1)
+        return _HexPlaneFn.apply(self.planes, pts, timestamps, self, tail)
 
     def forward(self, pts: Tensor, timestamps: Optional[Tensor] = None) -> Tensor:
         return self.get_density(pts, timestamps)

@@ -22,7 +22,7 @@ import torch
 from torch import Tensor
 
 from .diff_gauss_api import GaussianRasterizationSettings, GaussianRasterizer
-from .emd_s3g import S3GDeformation
+from .emd_s3g import REG_KEYS, S3GDeformation
 from .losses import ImageLossConfig, s3g_image_losses
 from .sh_ops import activate_geometry
 
@@ -103,6 +103,7 @@ class S3GGaussians:
         self.sky = sky_model
         self.active_sh_degree = active_sh_degree
         self._deformation_table = None
+        self.fused_residuals = self._features_rest.shape[1] == 15     # the fused kernel is built for SH degree 3
         self.scaling_activation = torch.exp
         self.rotation_activation = torch.nn.functional.normalize
         self.opacity_activation = torch.sigmoid
@@ -125,6 +126,9 @@ class S3GGaussians:
                      is_train=False):
         """``deform_network.forward`` (``deformation.py:484-527``); ``time`` arrives as the [N,1] repeat of one value."""
         t = time.reshape(-1)[0] if isinstance(time, Tensor) else time
+        if shs is None:     # fused residual application: concatenates features_dc / features_rest itself
+            return self.deform(point, scales, rotations, opacity, None, t, embeddings, iteration, cam_no,
+                               shs_parts=(self._features_dc, self._features_rest))
         return self.deform(point, scales, rotations, opacity, shs, t, embeddings, iteration, cam_no)
 
     def activate(self, scales, rotations, opacity):
@@ -162,7 +166,10 @@ def render(args: S3GOptions, viewpoint_camera, pc, bg_color: Tensor, scaling_mod
         projmatrix=viewpoint_camera.full_proj_transform.to(dev), sh_degree=pc.active_sh_degree,
         campos=viewpoint_camera.camera_center.to(dev), prefiltered=False, debug=args.debug)
     rasterizer = GaussianRasterizer(raster_settings=raster_settings)
-    opacity, shs, scales, rotations = pc._opacity, pc.get_features, pc._scaling, pc._rotation
+    # S3GGaussians applies the residuals in a fused kernel that reads features_dc / features_rest directly (shs=None)
+    fused = "fine" in stage and getattr(pc, "fused_residuals", False)
+    opacity, scales, rotations = pc._opacity, pc._scaling, pc._rotation
+    shs = None if fused else pc.get_features
     ddict = None
     if "coarse" in stage:
         means3D_final, scales_final, rotations_final, opacity_final, shs_final = means3D, scales, rotations, opacity, shs
@@ -218,10 +225,13 @@ def training_losses(args: S3GOptions, render_pkg: Dict[str, Tensor], gt_image: T
             if off or lam == 0:
                 continue
             terms = []
-            if not args.no_coarse_deform:
-                terms.append(dd["coarse"][key].abs().mean() * lam)
-            if not args.no_fine_deform:
-                terms.append(dd["fine"][key].abs().mean() * lam)
+            for branch, off_b in (("coarse", args.no_coarse_deform), ("fine", args.no_fine_deform)):
+                if off_b:
+                    continue
+                if "reg_sums" in dd:       # sum |.| from the fused residual kernel (emd_s3g.apply_residuals)
+                    terms.append(dd["reg_sums"][REG_KEYS.index((branch, key))] * (lam / max(dd[branch][key].numel(), 1)))
+                else:
+                    terms.append(dd[branch][key].abs().mean() * lam)
             if key == "dx" and not args.no_fine_deform and not args.no_coarse_deform and args.lambda_f2c != 0:
                 terms.append((dd["fine"]["dx"] - dd["coarse"]["dx"]).abs().mean() * args.lambda_f2c)
             out[key + "_loss"] = sum(terms)

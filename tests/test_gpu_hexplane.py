@@ -150,3 +150,33 @@ def test_deformation_network_with_hexplane():
     for row_g, row_o in zip(f.reference_grids(f.planes.grad), G_c):
         for a, b in zip(row_g, row_o):
             assert rel_l2(a, b.grad) <= 1e-3
+
+
+def test_hexplane_tail_columns_equal_concatenation():
+    """``get_density(..., tail=emb)`` (row-pitched gather writing the MLP input [features | embedding] in place,
+    deformation.py:205) is bit-identical to gather + torch.cat, forward and backward."""
+    from oracle import hexplane as OH
+    reso, mr = [16, 16, 16, 8], [1, 2, 4, 8]
+    grids = OH.hash_planes(reso, mr, salt=3)
+    aabb = torch.tensor([[9.0, 9.0, 9.0], [-9.0, -9.0, -9.0]])
+    g = torch.Generator().manual_seed(11)
+    N = 5003
+    pts = (torch.rand(N, 3, generator=g) * 20 - 10)
+    emb = torch.randn(N, 4, generator=g)
+    cot = torch.randn(N, 132, generator=g).cuda()
+    outs = []
+    for tail in (False, True):
+        f = _field(reso, mr, grids, aabb)
+        pg, eg = pts.cuda().requires_grad_(True), emb.cuda().requires_grad_(True)
+        tg = torch.tensor([0.3]).cuda().requires_grad_(True)
+        x = f.get_density(pg, tg, tail=eg) if tail else torch.cat([f(pg, tg), eg], dim=-1)
+        assert x.shape == (N, 132) and x.is_contiguous()
+        (x * cot).sum().backward()
+        outs.append((x.detach(), pg.grad, eg.grad, tg.grad))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    # the plane gradient is scattered with floating-point atomics: equal up to the order of the additions
+    # (checked against the oracle in test_hexplane_vs_oracle); a pitch that is not a multiple of 4 falls back to cat
+    f = _field(reso, mr, grids, aabb)
+    x3 = f.get_density(pts.cuda(), torch.tensor([0.3]).cuda(), tail=emb[:, :3].cuda())
+    assert x3.shape == (N, 131) and torch.equal(x3[:, :128], outs[0][0][:, :128])

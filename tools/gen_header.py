@@ -18,8 +18,10 @@ GROUPS = [
                                                          "emd_smpl_deform_bwd"]),
     ("K1b  spherical harmonics + node activations", ["emd_sh_fwd", "emd_sh_bwd", "emd_activate_fwd", "emd_activate_bwd"]),
     ("K1d  S3Gaussian EMD deformation MLP", ["emd_linear_bwd_workspace_bytes", "emd_linear_fwd", "emd_linear_fwd_tc", "emd_linear_bwd", "emd_linear_bwd_tc", "emd_temb_fwd", "emd_temb_bwd"]),
-    ("K1e  HexPlane feature gather (input of the S3Gaussian EMD MLP)", ["emd_hexplane_fwd", "emd_hexplane_bwd_workspace_bytes",
-                                                                       "emd_hexplane_bwd"]),
+    ("K1e  HexPlane feature gather (input of the S3Gaussian EMD MLP)", ["emd_hexplane_fwd", "emd_hexplane_fwd_ld", "emd_hexplane_bwd_workspace_bytes",
+                                                                       "emd_hexplane_bwd", "emd_hexplane_bwd_ld"]),
+    ("K1d' residual application of the S3Gaussian deformation + regulariser sums",
+     ["emd_s3g_apply_blocks", "emd_s3g_apply_fwd", "emd_s3g_apply_bwd"]),
     ("Next (SURVEY 8f-2): fused Adam step + densification statistics", ["emd_adam_max_tensors", "emd_adam_step", "emd_densify_stats"]),
     ("Next (SURVEY 8f-3): fused image losses between the rasterizer forward and backward",
      ["emd_image_loss_partials_floats", "emd_image_loss_fwd", "emd_image_loss_bwd"]),
@@ -109,6 +111,19 @@ DOC = {
                         "device buffer, plane (s,p) stored feature-last [H][W][F] at float offset plane_offsets[s*6+p] (HOST "
                         "array); reso: HOST int[S*4] grid size per coordinate (x,y,z,t) and scale; aabb: HOST float[6] = "
                         "{aabb[0], aabb[1]} (hexplane.py:19-20); t: DEVICE, one shared value (t_stride 0) or one per point (1).",
+    "emd_hexplane_fwd_ld": "emd_hexplane_fwd with a row pitch: row n of the features starts at feat + n*ld floats (ld >= S*F, multiple "
+                           "of 4), so the gather writes straight into the left columns of the deformation MLP's input "
+                           "[N, S*F + E] -- the concatenation of deformation.py:205 without a copy pass.",
+    "emd_hexplane_bwd_ld": "emd_hexplane_bwd reading v_feat with a row pitch of ld floats (the gradient of the MLP input, in place).",
+    "emd_s3g_apply_blocks": "Rows of the `partial` array emd_s3g_apply_fwd writes for N Gaussians.",
+    "emd_s3g_apply_fwd": "Residual application of deform_network.forward (S3Gaussian/scene/deformation.py:439-481, 484-527, flag set "
+                         "--no_ds --no_dr): means = point + dx_c + dx_f, opac = opacity + do_c + do_f, shs = cat(dc, rest) + dshs_c + "
+                         "dshs_f -- fused with GaussianModel.get_features' concatenation (scene/gaussian_model.py) and with the sums "
+                         "the trainer's L1 regularisers need (train.py:240-305): partial[emd_s3g_apply_blocks(N)][6] = per-block "
+                         "sums of |dx_c| |dx_f| |do_c| |do_f| |dshs_c| |dshs_f| (fixed order; the caller adds the rows).",
+    "emd_s3g_apply_bwd": "VJP of emd_s3g_apply_fwd: coef is a DEVICE float[6], d loss / d sum_j; v_x = cotangent + coef_j * sign(x) "
+                         "for the six residuals, v_dc / v_rest = the split of v_shs (the gradients of point and opacity are v_means "
+                         "and v_opac themselves).  v_means / v_opac / v_shs may be NULL.",
     "emd_hexplane_bwd_workspace_bytes": "Workspace bytes of emd_hexplane_bwd (per-block partials of the shared-time gradient).",
     "emd_hexplane_bwd": "VJP of emd_hexplane_fwd: v_planes (layout of planes, ADDED into, caller zero-fills; 16-byte vector "
                         "reductions), v_pts[N,3] (may be NULL), v_t (N values written for t_stride 1, one value ADDED into for "
