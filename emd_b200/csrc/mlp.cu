@@ -240,9 +240,9 @@ int wgrad_grid(int64_t M) {
 }  // namespace
 
 extern "C" size_t emd_linear_bwd_workspace_bytes(int64_t M, int K, int Nout) {
-    // masked upstream gradient [M,Nout] + per-CTA weight-gradient partials
+    // masked upstream gradient [M,Nout] + per-CTA weight-gradient partials (+ one slot: the tensor-core path's tail CTA)
     return ((size_t)M * Nout * sizeof(float) + 255) / 256 * 256 +
-           (size_t)wgrad_grid(M) * ((size_t)Nout * K + Nout) * sizeof(float) + 256;
+           ((size_t)wgrad_grid(M) + 1) * ((size_t)Nout * K + Nout) * sizeof(float) + 256;
 }
 
 extern "C" int emd_linear_fwd(const float* X, const float* W, const float* b, int64_t M, int K, int Nout, int relu_in,

@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) linear_fwd_tc_kernel(const floa
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// backward, data gradient:  dG = dY (.) relu'(Y)  (written out for the weight-gradient kernel),
+// backward, data gradient:  dG = dY (.) relu'(Y)  (written out for the weight-gradient kernel when the layer has an
+//                           output ReLU; without one dG == dY and the weight-gradient kernel reads dY itself),
 //                           dX = (dG . W) (.) relu'(X)
 // The same GEMM skeleton as the forward with A = dG [rows x Nout] (reduction over Nout) and B[n][k] = W[k][n].
 // ---------------------------------------------------------------------------------------------------------------
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) linear_dgrad_tc_kernel(
                             const float4 y = __ldg(reinterpret_cast<const float4*>(Y + row * Nout) + jg);
                             if (!(y.x > 0.f)) v.x = 0.f; if (!(y.y > 0.f)) v.y = 0.f; if (!(y.z > 0.f)) v.z = 0.f; if (!(y.w > 0.f)) v.w = 0.f;
                         }
-                        reinterpret_cast<float4*>(dG + row * Nout)[jg] = v;
+                        if (RELU_OUT) reinterpret_cast<float4*>(dG + row * Nout)[jg] = v;
                     } else {
                         float t[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) linear_dgrad_tc_kernel(
                             if (col < Nout) {
                                 float gq = __ldg(dY + row * Nout + col);
                                 if (RELU_OUT && !(__ldg(Y + row * Nout + col) > 0.f)) gq = 0.f;
-                                dG[row * Nout + col] = gq;
+                                if (RELU_OUT) dG[row * Nout + col] = gq;
                                 t[q] = gq;
                             }
                         }
@@ -500,6 +501,155 @@ __global__ void __launch_bounds__(TC_THREADS, 2) linear_wgrad_tc_kernel(const fl
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(tmem_cols) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// weight gradient, bulk-staged (K <= 64): the same MMA schedule as linear_wgrad_tc_kernel, but the operands reach
+// shared memory differently.  The kernel above lets lane = row fetch one float4 of its own row, so every load
+// instruction touches 32 different 128-byte lines: the launch list of the S3G step (profiles/r03f_ncu_s3g_launches.csv)
+// shows it at 217-254 us per 64 x 64 layer against 85 us of HBM time, the L1 tag stage (one line per cycle) being the
+// limiter.  Here a 32-row chunk of X and of dG -- each ONE contiguous block of global memory, rows being dense -- is
+// brought in by two bulk asynchronous copies (cp.async.bulk, the 1-D TMA path) into a 3-deep ring, completion on an
+// mbarrier per stage; the threads then read the raw chunk column-wise (lanes along the features: conflict-free),
+// apply act_in, split hi / lo and store float4s of four consecutive rows straight into the K-major canonical layout
+// (element (m, row) at (row / 4) * LBO + m * 16 + (row % 4) * 4).  A CTA owns a contiguous range of whole chunks;
+// the < 32 rows behind the last whole chunk are handled by one CTA of the kernel above (one more partial slot).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TC_WST = 3;                         // raw-chunk stages in flight per CTA
+
+template <bool RELU_IN>
+__global__ void __launch_bounds__(TC_THREADS, 2) linear_wgrad_tc_bulk_kernel(const float* __restrict__ X, const float* __restrict__ dG,
+                                                                             int64_t nch, int K, int Nout, int tmem_cols,
+                                                                             float* __restrict__ partial) {
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_full[TC_WST];
+    __shared__ uint32_t s_tmem;
+    const int npad = (K + 1 + 15) / 16 * 16;          // columns of [X | 1], padded to N % 16 == 0
+    const int x_lbo = npad * 16 + 16;
+    const int g_bytes = (TC_WR / 4) * TC_A_LBO, x_bytes = (TC_WR / 4) * x_lbo;
+    const int xr_bytes = TC_WR * K * 4, gr_bytes = TC_WR * Nout * 4;   // raw chunk: multiples of 16 (K % 4 == 0; 128 Nout)
+    const int st_bytes = xr_bytes + gr_bytes;
+    unsigned char* sGhi = tc_smem;
+    unsigned char* sGlo = sGhi + g_bytes;
+    unsigned char* sXhi = sGlo + g_bytes;
+    unsigned char* sXlo = sXhi + x_bytes;
+    unsigned char* raw = sXlo + x_bytes;              // 128-byte aligned: g_bytes and x_bytes are multiples of 128
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t beg = nch * (int64_t)blockIdx.x / gridDim.x, end = nch * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    const int n_my = (int)(end - beg);
+
+    for (int e = tid; e < (2 * g_bytes + 2 * x_bytes) / 16; e += TC_THREADS) reinterpret_cast<float4*>(tc_smem)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t bar = smem_u32(&s_bar);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+#pragma unroll
+        for (int s = 0; s < TC_WST; ++s) mbar_init(smem_u32(&s_full[s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // the ones column of [X | 1] (db = colsum(dG)): feature K, all 32 rows of the chunk; never overwritten afterwards
+    if (tid < TC_WR / 4) *reinterpret_cast<float4*>(sXhi + tid * x_lbo + K * 16) = make_float4(1.f, 1.f, 1.f, 1.f);
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = umma_idesc_tf32(TC_ROWS, npad);
+    const uint32_t gHi = smem_u32(sGhi), gLo = smem_u32(sGlo), xHi = smem_u32(sXhi), xLo = smem_u32(sXlo);
+
+    // one thread: chunk i of this CTA -> stage i % TC_WST (two bulk copies, one transaction count)
+    auto issue = [&](int i) {
+        const int s = i % TC_WST;
+        const uint32_t fb = smem_u32(&s_full[s]);
+        const uint32_t dst = smem_u32(raw + s * st_bytes);
+        const float* xs = X + (beg + i) * (int64_t)(TC_WR * K);
+        const float* gs = dG + (beg + i) * (int64_t)(TC_WR * Nout);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(fb), "r"((uint32_t)st_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(dst), "l"(xs), "r"((uint32_t)xr_bytes), "r"(fb) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(dst + (uint32_t)xr_bytes), "l"(gs), "r"((uint32_t)gr_bytes), "r"(fb) : "memory");
+    };
+    if (tid == 0)
+        for (int i = 0; i < min(TC_WST, n_my); ++i) issue(i);
+
+    uint32_t phase = 0;
+    bool pending = false;
+    for (int i = 0; i < n_my; ++i) {
+        const int s = i % TC_WST;
+        mbar_wait(smem_u32(&s_full[s]), (uint32_t)((i / TC_WST) & 1));   // the raw chunk has landed
+        if (pending) {   // the previous chunk's MMAs have read the operand buffers
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        }
+        const float* rx = reinterpret_cast<const float*>(raw + s * st_bytes);
+        const float* rg = reinterpret_cast<const float*>(raw + s * st_bytes + xr_bytes);
+        for (int e = tid; e < (TC_WR / 4) * K; e += TC_THREADS) {
+            const int rq = e / K, m = e - rq * K;            // rows 4 rq .. 4 rq + 3 of feature m
+            float4 x = make_float4(rx[(4 * rq + 0) * K + m], rx[(4 * rq + 1) * K + m], rx[(4 * rq + 2) * K + m], rx[(4 * rq + 3) * K + m]);
+            if (RELU_IN) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            float4 hi, lo;
+            split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+            *reinterpret_cast<float4*>(sXhi + rq * x_lbo + m * 16) = hi;
+            *reinterpret_cast<float4*>(sXlo + rq * x_lbo + m * 16) = lo;
+        }
+        for (int e = tid; e < (TC_WR / 4) * Nout; e += TC_THREADS) {
+            const int rq = e / Nout, m = e - rq * Nout;
+            const float4 g = make_float4(rg[(4 * rq + 0) * Nout + m], rg[(4 * rq + 1) * Nout + m], rg[(4 * rq + 2) * Nout + m], rg[(4 * rq + 3) * Nout + m]);
+            float4 hi, lo;
+            split_tf32(g.x, hi.x, lo.x); split_tf32(g.y, hi.y, lo.y); split_tf32(g.z, hi.z, lo.z); split_tf32(g.w, hi.w, lo.w);
+            *reinterpret_cast<float4*>(sGhi + rq * TC_A_LBO + m * 16) = hi;
+            *reinterpret_cast<float4*>(sGlo + rq * TC_A_LBO + m * 16) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();   // operands complete; every thread is done reading raw stage s
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int ks = 0; ks < TC_WR / 8; ++ks) {   // one MMA k-step = 8 rows = 2 core-matrix columns
+                const uint64_t dAh = umma_desc(gHi + 2 * ks * TC_A_LBO, TC_A_LBO, TC_SBO);
+                const uint64_t dAl = umma_desc(gLo + 2 * ks * TC_A_LBO, TC_A_LBO, TC_SBO);
+                const uint64_t dBh = umma_desc(xHi + 2 * ks * x_lbo, x_lbo, TC_SBO);
+                const uint64_t dBl = umma_desc(xLo + 2 * ks * x_lbo, x_lbo, TC_SBO);
+                umma_tf32(tmem, dAl, dBh, idesc, (i == 0 && ks == 0) ? 0u : 1u);
+                umma_tf32(tmem, dAh, dBl, idesc, 1u);
+                umma_tf32(tmem, dAh, dBh, idesc, 1u);
+            }
+            umma_commit(bar);
+            if (i + TC_WST < n_my) issue(i + TC_WST);   // refill the stage just consumed
+        }
+        pending = true;
+    }
+    float* out = partial + (size_t)blockIdx.x * ((size_t)Nout * K + Nout);
+    if (n_my == 0) {
+        for (int e = tid; e < Nout * K + Nout; e += TC_THREADS) out[e] = 0.f;
+    } else {
+        mbar_wait(bar, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int m = (warp & 3) * 32 + lane;            // output feature = TMEM lane
+        const int split = ((npad / 16 + 1) / 2) * 16;
+        const int cbeg = warp < 4 ? 0 : split, cend = warp < 4 ? split : npad;
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
+            if (m < Nout) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const int col = c0 + c;
+                    if (col < K) out[(size_t)m * K + col] = v[c];
+                    else if (col == K) out[(size_t)Nout * K + m] = v[c];
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(tmem_cols) : "memory");
+}
+
 __global__ void linear_wgrad_tc_reduce_kernel(const float* __restrict__ partial, int nparts, int count,
                                               float* __restrict__ dW, float* __restrict__ db, int nW) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -567,7 +717,9 @@ extern "C" int emd_linear_bwd_tc(const float* X, const float* W, const float* Y,
     float* dG = reinterpret_cast<float*>(workspace);
     float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ((size_t)M * Nout * sizeof(float) + 255) / 256 * 256);
     const int grid = tc_grid(M);
-    {
+    // without an output ReLU the masked gradient IS dY: nothing to write, the weight gradient reads dY
+    const float* dGr = relu_out ? dG : dY;
+    if (relu_out || dX) {
         const TcLayout L(Nout, K);
         const size_t smem = L.total();
         const int tcols = tmem_cols_for(L.npad);
@@ -582,19 +734,46 @@ extern "C" int emd_linear_bwd_tc(const float* X, const float* W, const float* Y,
         else EMD_TC_DG(false, false);
 #undef EMD_TC_DG
     }
+    int nparts = grid;
     {
         const int npad = (K + 1 + 15) / 16 * 16;
         const size_t smem = 2 * (size_t)(TC_WR / 4) * (TC_A_LBO + npad * 16 + 16);
         const int tcols = tmem_cols_for(npad);
-        if (relu_in) {
-            cudaFuncSetAttribute(linear_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            EMD_LAUNCH(EK_MLP_BWD, stream, (linear_wgrad_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(X, dG, M, K, Nout, tcols, partial)));
-        } else {
-            cudaFuncSetAttribute(linear_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            EMD_LAUNCH(EK_MLP_BWD, stream, (linear_wgrad_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(X, dG, M, K, Nout, tcols, partial)));
+        const int64_t nch = M / TC_WR;                      // whole 32-row chunks
+        const float* Xt = X;
+        const float* Gt = dGr;
+        int64_t Mt = M;
+        int tgrid = grid;
+        float* tpart = partial;
+        if (K <= 64 && nch > 0) {
+            // bulk-staged kernel over the whole chunks; the rows behind them (< 32) go through the row-wise kernel below
+            const size_t bsmem = smem + (size_t)TC_WST * TC_WR * (K + Nout) * sizeof(float);
+            const int bgrid = (int)(nch < grid ? nch : grid);
+            if (relu_in) {
+                cudaFuncSetAttribute(linear_wgrad_tc_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
+                EMD_LAUNCH(EK_MLP_BWD, stream, (linear_wgrad_tc_bulk_kernel<true><<<bgrid, TC_THREADS, bsmem, stream>>>(X, dGr, nch, K, Nout, tcols, partial)));
+            } else {
+                cudaFuncSetAttribute(linear_wgrad_tc_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
+                EMD_LAUNCH(EK_MLP_BWD, stream, (linear_wgrad_tc_bulk_kernel<false><<<bgrid, TC_THREADS, bsmem, stream>>>(X, dGr, nch, K, Nout, tcols, partial)));
+            }
+            Xt = X + nch * TC_WR * K;
+            Gt = dGr + nch * TC_WR * Nout;
+            Mt = M - nch * TC_WR;
+            tgrid = 1;
+            tpart = partial + (size_t)bgrid * count;
+            nparts = bgrid + (Mt > 0 ? 1 : 0);
+        }
+        if (Mt > 0) {
+            if (relu_in) {
+                cudaFuncSetAttribute(linear_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                EMD_LAUNCH(EK_MLP_BWD, stream, (linear_wgrad_tc_kernel<true><<<tgrid, TC_THREADS, smem, stream>>>(Xt, Gt, Mt, K, Nout, tcols, tpart)));
+            } else {
+                cudaFuncSetAttribute(linear_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                EMD_LAUNCH(EK_MLP_BWD, stream, (linear_wgrad_tc_kernel<false><<<tgrid, TC_THREADS, smem, stream>>>(Xt, Gt, Mt, K, Nout, tcols, tpart)));
+            }
         }
     }
-    EMD_LAUNCH(EK_MLP_BWD, stream, (linear_wgrad_tc_reduce_kernel<<<(count + 127) / 128, 128, 0, stream>>>(partial, grid, count, dW, db, Nout * K)));
+    EMD_LAUNCH(EK_MLP_BWD, stream, (linear_wgrad_tc_reduce_kernel<<<(count + 127) / 128, 128, 0, stream>>>(partial, nparts, count, dW, db, Nout * K)));
     EMD_CHECK_LAUNCH("linear_bwd_tc");
     return EMD_OK;
 }

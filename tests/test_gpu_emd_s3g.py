@@ -14,7 +14,14 @@ G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 @pytest.mark.parametrize("M,K,Nout,ri,ro", [(1000, 64, 64, True, True), (777, 132, 64, False, False),
                                              (513, 4, 64, False, False), (300, 64, 48, False, False),
                                              (129, 64, 1, False, False), (5000, 64, 3, True, False),
-                                             (128, 64, 64, False, True), (1, 64, 64, True, True)])
+                                             (128, 64, 64, False, True), (1, 64, 64, True, True),
+                                             # the bulk-staged weight gradient: ~32 chunks per CTA (ring phases), no tail
+                                             # rows, one whole chunk + tail, Nout not a multiple of 4.  No output ReLU at
+                                             # these sizes: among 2e7 outputs some lie within rounding of 0, and a mask
+                                             # that flips there changes a whole gradient row (the mask itself is
+                                             # per element and covered by the small cases)
+                                             (300017, 64, 64, True, False), (65536, 4, 64, False, False),
+                                             (40, 64, 3, False, False), (100000, 64, 48, True, False)])
 def test_linear_layer(M, K, Nout, ri, ro):
     from emd_b200.mlp_ops import linear
     g = torch.Generator().manual_seed(M + K + Nout)
