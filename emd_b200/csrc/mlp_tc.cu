@@ -45,6 +45,47 @@ struct TcLayout {
     __host__ __device__ size_t total() const { return 2 * (size_t)TC_A_CHUNK_BYTES + 2 * (size_t)b_bytes; }
 };
 
+// Epilogue store of a 32-row x 16-column accumulator block held one row per lane (tcgen05.ld 32x32b).  Stored straight
+// from those registers, every store instruction touches 32 different 128-byte lines with 16 bytes each; the launch
+// list of the S3G step showed the epilogues, not HBM, bounding these kernels.  The block is therefore passed through a
+// per-warp staging area (32 rows x 80 B: conflict-free float4 writes) and written back with FOUR lanes per row: one
+// instruction covers 8 rows x 64 contiguous bytes -- whole 32-byte sectors, a quarter of the line visits.
+//   dst / mask: address of (first row of the block, first column of the block); ld: row pitch in floats (% 4 == 0);
+//   rows: valid rows of the block (<= 0: none); cols: valid columns (a multiple of 4, may exceed 16);
+//   mask != nullptr: the value is zeroed where mask <= 0 (the ReLU derivative of the layer input).
+constexpr int TC_STAGE_LD = 20;                                  // floats per staged row (16 + 4: bank spread)
+constexpr int TC_STAGE_WARP = 32 * TC_STAGE_LD;                  // floats per warp; 8 warps = 20 480 B <= the A chunk buffers
+
+__device__ __forceinline__ void warp_block_store16(float* __restrict__ stage, const float (&v)[16], int lane,
+                                                   float* __restrict__ dst, const float* __restrict__ mask, int64_t ld,
+                                                   int rows, int cols) {
+    float4* w = reinterpret_cast<float4*>(stage + lane * TC_STAGE_LD);
+    w[0] = make_float4(v[0], v[1], v[2], v[3]);
+    w[1] = make_float4(v[4], v[5], v[6], v[7]);
+    w[2] = make_float4(v[8], v[9], v[10], v[11]);
+    w[3] = make_float4(v[12], v[13], v[14], v[15]);
+    __syncwarp();
+    const int q = lane & 3, rr = lane >> 2;
+    if (4 * q + 4 <= cols) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int row = r * 8 + rr;
+            if (row < rows) {
+                float4 o = *reinterpret_cast<const float4*>(stage + row * TC_STAGE_LD + q * 4);
+                if (mask) {
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(mask + row * ld + q * 4));
+                    if (!(x.x > 0.f)) o.x = 0.f;
+                    if (!(x.y > 0.f)) o.y = 0.f;
+                    if (!(x.z > 0.f)) o.z = 0.f;
+                    if (!(x.w > 0.f)) o.w = 0.f;
+                }
+                *reinterpret_cast<float4*>(dst + row * ld + q * 4) = o;
+            }
+        }
+    }
+    __syncwarp();   // the staging rows are rewritten by the next block
+}
+
 template <bool RELU_IN, bool RELU_OUT>
 __global__ void __launch_bounds__(TC_THREADS, 2) linear_fwd_tc_kernel(const float* __restrict__ X, const float* __restrict__ W,
                                                                       const float* __restrict__ bias, int64_t M, int K,
@@ -152,29 +193,31 @@ __global__ void __launch_bounds__(TC_THREADS, 2) linear_fwd_tc_kernel(const floa
         phase ^= 1u;
         mma_pending = false;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31; warps 4-7 take the upper half of the columns ----
-        const int64_t row = row0 + (warp & 3) * 32 + lane;
+        // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31; warps 4-7 take the upper half of the columns.
+        // The A chunk buffers are free here (every MMA of the tile has completed, the next chunk is still in registers):
+        // they stage the coalesced store.
+        const int64_t rbase = row0 + (warp & 3) * 32;
+        const int64_t row = rbase + lane;
+        const int rows_valid = (int)(M - rbase < 32 ? M - rbase : 32);
+        float* stage = reinterpret_cast<float*>(tc_smem) + warp * TC_STAGE_WARP;
         const int cbeg = (warp >> 2) * 32;                       // warps 0-3: columns [0, 32), warps 4-7: [32, npad)
         const int cend = min(L.npad, cbeg + 32);
         for (int c0 = cbeg; c0 < cend; c0 += 16) {
             float v[16];
             tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
-            if (row < M) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    float y = v[c] + s_bias[c0 + c];
-                    if (RELU_OUT) y = fmaxf(y, 0.f);
-                    v[c] = y;
-                }
+            for (int c = 0; c < 16; ++c) {
+                float y = v[c] + s_bias[c0 + c];
+                if (RELU_OUT) y = fmaxf(y, 0.f);
+                v[c] = y;
+            }
+            if ((Nout & 3) == 0) {
+                if (c0 < Nout) warp_block_store16(stage, v, lane, Y + rbase * Nout + c0, nullptr, Nout, rows_valid, Nout - c0);
+            } else if (row < M) {
                 float* yr = Y + row * Nout + c0;
-                if ((Nout & 3) == 0 && c0 + 16 <= Nout) {
 #pragma unroll
-                    for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(yr + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 16; ++c)
-                        if (c0 + c < Nout) yr[c] = v[c];
-                }
+                for (int c = 0; c < 16; ++c)
+                    if (c0 + c < Nout) yr[c] = v[c];
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -307,25 +350,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) linear_dgrad_tc_kernel(
         mbar_wait(bar, phase);
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int64_t row = row0 + (warp & 3) * 32 + lane;
+        // coalesced store (and ReLU-derivative mask read) through the free A chunk buffers: see warp_block_store16
+        const int64_t rbase = row0 + (warp & 3) * 32;
+        const int rows_valid = (int)(M - rbase < 32 ? M - rbase : 32);
+        float* stage = reinterpret_cast<float*>(tc_smem) + warp * TC_STAGE_WARP;
         const int cbeg = warp < 4 ? 0 : split, cend = warp < 4 ? split : L.npad;
         for (int c0 = cbeg; c0 < cend; c0 += 16) {
             float v[16];
             tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
-            if (row < M) {
-#pragma unroll
-                for (int cc = 0; cc < 16; cc += 4) {
-                    const int col = c0 + cc;
-                    if (col + 4 <= K) {   // K % 4 == 0: whole float4 groups only
-                        float4 o = make_float4(v[cc], v[cc + 1], v[cc + 2], v[cc + 3]);
-                        if (RELU_IN) {
-                            const float4 x = __ldg(reinterpret_cast<const float4*>(X + row * K + col));
-                            if (!(x.x > 0.f)) o.x = 0.f; if (!(x.y > 0.f)) o.y = 0.f; if (!(x.z > 0.f)) o.z = 0.f; if (!(x.w > 0.f)) o.w = 0.f;
-                        }
-                        *reinterpret_cast<float4*>(dX + row * K + col) = o;
-                    }
-                }
-            }
+            if (c0 < K)   // K % 4 == 0: whole float4 groups only
+                warp_block_store16(stage, v, lane, dX + rbase * K + c0, RELU_IN ? X + rbase * K + c0 : nullptr, K, rows_valid, K - c0);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
