@@ -828,9 +828,36 @@ def run_s3g(args):
                      "algorithmic": f"121.6 kFLOP x 3 (fwd + bwd) x {n} Gaussians per step", "ms_per_step": round(mlp_ms, 4),
                      "traffic": None, "per_kernel": per_kernel},
     }
+    # the same kernels against the bound that holds today: every layer streams its activations through HBM
+    hbm_peak = float(peaks.get("hbm_gbs", 6551.0))
+    fb, bb = s3g_mlp_bytes_per_gaussian()
+    line["roofline"]["hbm_view"] = {
+        "bytes_per_gaussian": {"fwd": fb, "bwd": bb}, "peak": hbm_peak, "unit": "GB/s",
+        "fwd_frac": round(fb * n / (kern.get("mlp_fwd", (0, 1))[0] / k_steps * 1e-3) / 1e9 / hbm_peak, 4) if kern.get("mlp_fwd", (0, 1))[0] > 0 else None,
+        "bwd_frac": round(bb * n / (kern.get("mlp_bwd", (0, 1))[0] / k_steps * 1e-3) / 1e9 / hbm_peak, 4) if kern.get("mlp_bwd", (0, 1))[0] > 0 else None,
+        "note": "per-layer kernels: activations round-trip HBM between layers, so HBM (not the tensor pipe) bounds them"}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_s3g(args)
     print(json.dumps(line))
+
+
+# the 20 Linear layers of the S3G deformation network as emd_s3g.S3GDeformation runs them (K, Nout, relu_in, relu_out):
+# feature_out(_f).0, then pos / opacity / shs heads (ReLU, Linear, ReLU, Linear) and dino_head (Linear, ReLU, Linear, ReLU, Linear)
+def s3g_mlp_layers():
+    heads = [(64, 64, True, True), (64, 3, False, False), (64, 64, True, True), (64, 1, False, False),
+             (64, 64, True, True), (64, 48, False, False), (64, 64, False, True), (64, 64, False, True), (64, 3, False, False)]
+    return [(132, 64, False, False)] + heads + [(4, 64, False, False)] + heads
+
+
+def s3g_mlp_bytes_per_gaussian():
+    """Algorithmic HBM bytes per Gaussian of the per-layer kernels: forward reads X and writes Y; the data
+    gradient reads dY (+ Y and writes dG with an output ReLU, + X with an input ReLU) and writes dX; the weight gradient
+    reads X and dG.  -> (forward, backward)."""
+    fwd = bwd = 0
+    for K, N, ri, ro in s3g_mlp_layers():
+        fwd += 4 * (K + N)
+        bwd += 4 * (N + (2 * N if ro else 0) + (K if ri else 0) + K) + 4 * (K + N)
+    return fwd, bwd
 
 
 def cpu_baseline_s3g(args):

@@ -56,3 +56,40 @@ def test_committed_launch_lists_parse():
         assert any("hexplane_bwd_kernel" in n for n in names) and any("raster_bwd_kernel" in n for n in names)
     after = {launch_table.short(n) for n, _ in launch_table.rows_of(os.path.join(ROOT, "profiles", "r03k_ncu_s3g_launches.csv"))}
     assert any("linear_wgrad_tc_bulk_kernel" in n for n in after) and any("s3g_apply_fwd_kernel" in n for n in after)
+
+
+def test_s3g_mlp_layer_table_matches_the_network():
+    """bench.py's layer table (the algorithmic bytes of the S3G roofline's HBM view) against the shapes
+    ``S3GDeformation`` actually launches: same 20 (K, Nout, relu_in, relu_out), recorded by a stand-in ``linear``."""
+    import importlib.util
+    import numpy as np
+    from emd_b200 import emd_s3g as E
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "emd_s3g.npz"))
+    pre = "w.deformation_net."
+    w = {k[len(pre):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(pre)}
+    seen = []
+
+    def fake_linear(X, W, b, relu_in=False, relu_out=False):
+        seen.append((X.shape[1], W.shape[0], bool(relu_in), bool(relu_out)))
+        x = torch.relu(X) if relu_in else X
+        y = torch.nn.functional.linear(x, W, b)
+        return torch.relu(y) if relu_out else y
+
+    def fake_temb(table, t, cur):
+        return torch.zeros(table.shape[1])
+
+    orig = (E.linear, E.temporal_embed)
+    E.linear, E.temporal_embed = fake_linear, fake_temb
+    try:
+        n = 7
+        net = E.S3GDeformation(w)
+        net(torch.zeros(n, 3), torch.zeros(n, 3), torch.zeros(n, 4), torch.zeros(n, 1), torch.zeros(n, 16, 3), 0.1,
+            torch.zeros(n, 4), 20000, 0, hex_feat=torch.zeros(n, 128))
+    finally:
+        E.linear, E.temporal_embed = orig
+    assert sorted(seen) == sorted(bench.s3g_mlp_layers())
+    fwd, bwd = bench.s3g_mlp_bytes_per_gaussian()
+    assert fwd == sum(4 * (k + n_) for k, n_, _, _ in seen) and bwd > 2 * fwd
